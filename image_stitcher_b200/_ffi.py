@@ -1,0 +1,283 @@
+"""ctypes binding of libstitchb200.so (include/stitchb200.h).
+
+The library is the product; this file only marshals pointers.  There is no CPU
+fallback: if the shared library is missing or no CUDA device is usable the
+import-time loader / ``Context()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libstitchb200.so")
+
+SB_MEM_HOST, SB_MEM_DEVICE = 0, 1
+SB_U16, SB_U8 = 0, 1
+SB_FIELD_F32, SB_FIELD_F64 = 0, 1
+SB_BLEND_PASTE, SB_BLEND_LINEAR, SB_BLEND_FEATHER = 0, 1, 2
+SB_LAYOUT_ROWMAJOR, SB_LAYOUT_CHUNKED = 0, 1
+SB_PREC_F32, SB_PREC_F64, SB_PREC_AUTO = 0, 1, 2
+SB_DIR_HORIZONTAL, SB_DIR_VERTICAL = 0, 1
+BLEND_MODES = {"paste": SB_BLEND_PASTE, "linear": SB_BLEND_LINEAR, "feather": SB_BLEND_FEATHER}
+
+EXPORTS = [
+    "sb_version", "sb_create", "sb_destroy", "sb_last_error", "sb_kernel_launches", "sb_num_lanes",
+    "sb_device_sm_count", "sb_host_alloc", "sb_host_free", "sb_device_alloc", "sb_device_free",
+    "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_set_flatfield", "sb_set_darkfield", "sb_clear_fields",
+    "sb_flatfield_apply", "sb_fuse_region", "sb_sync", "sb_set_lane_stream", "sb_canvas_pitch",
+    "sb_chunked_plane_elems", "sb_register_pairs", "sb_normalize",
+]
+
+
+class SbTile(C.Structure):
+    _fields_ = [("px", C.c_void_p), ("x", C.c_int32), ("y", C.c_int32), ("c", C.c_int32), ("z", C.c_int32),
+                ("crop_t", C.c_int32), ("crop_b", C.c_int32), ("crop_l", C.c_int32), ("crop_r", C.c_int32)]
+
+
+class SbFuseJob(C.Structure):
+    _fields_ = [("tiles", C.POINTER(SbTile)), ("n_tiles", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),
+                ("dtype", C.c_int32), ("tile_mem", C.c_int32), ("num_c", C.c_int32), ("num_z", C.c_int32),
+                ("height", C.c_int32), ("width", C.c_int32), ("apply_flatfield", C.c_int32), ("blend", C.c_int32),
+                ("blend_ov_x", C.c_int32), ("blend_ov_y", C.c_int32), ("out", C.c_void_p), ("out_mem", C.c_int32),
+                ("out_layout", C.c_int32), ("out_row_pitch", C.c_int64), ("chunk_h", C.c_int32),
+                ("chunk_w", C.c_int32)]
+
+
+class SbPair(C.Structure):
+    _fields_ = [("ref", C.c_void_p), ("mov", C.c_void_p), ("dir", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SbPairResult(C.Structure):
+    _fields_ = [("dy", C.c_int32), ("dx", C.c_int32), ("shift", C.c_double * 2), ("coarse", C.c_int32 * 2),
+                ("fine", C.c_int32 * 2), ("peak", C.c_float), ("runner_up", C.c_float), ("fine_peak", C.c_float),
+                ("ref_min", C.c_int32), ("ref_max", C.c_int32), ("mov_min", C.c_int32), ("mov_max", C.c_int32),
+                ("precision", C.c_int32)]
+
+
+class SbRegisterJob(C.Structure):
+    _fields_ = [("pairs", C.POINTER(SbPair)), ("n_pairs", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),
+                ("dtype", C.c_int32), ("mem", C.c_int32), ("max_overlap_x", C.c_int32), ("max_overlap_y", C.c_int32),
+                ("upsample_factor", C.c_int32), ("precision", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the C-ABI library and declare its prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.isfile(path):
+        raise RuntimeError(f"{path} not found: build it with `python -m image_stitcher_b200.build` "
+                           "(there is no CPU fallback for the CUDA hot path)")
+    lib = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    lib.sb_version.restype = i32
+    lib.sb_create.argtypes = [i32, C.POINTER(vp)]
+    lib.sb_destroy.argtypes = [vp]
+    lib.sb_destroy.restype = None
+    lib.sb_last_error.argtypes = [vp]
+    lib.sb_last_error.restype = C.c_char_p
+    lib.sb_kernel_launches.argtypes = [vp]
+    lib.sb_kernel_launches.restype = i64
+    lib.sb_num_lanes.argtypes = [vp]
+    lib.sb_device_sm_count.argtypes = [vp]
+    lib.sb_host_alloc.argtypes = [vp, C.c_size_t]
+    lib.sb_host_alloc.restype = vp
+    lib.sb_host_free.argtypes = [vp, vp]
+    lib.sb_host_free.restype = None
+    lib.sb_device_alloc.argtypes = [vp, C.c_size_t]
+    lib.sb_device_alloc.restype = vp
+    lib.sb_device_free.argtypes = [vp, vp]
+    lib.sb_device_free.restype = None
+    lib.sb_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.sb_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    for fn in (lib.sb_set_flatfield, lib.sb_set_darkfield):
+        fn.argtypes = [vp, i32, vp, i32, i32, i32, i32]
+    lib.sb_clear_fields.argtypes = [vp]
+    lib.sb_flatfield_apply.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, i32]
+    lib.sb_fuse_region.argtypes = [vp, C.POINTER(SbFuseJob), i32]
+    lib.sb_sync.argtypes = [vp, i32]
+    lib.sb_set_lane_stream.argtypes = [vp, i32, vp]
+    lib.sb_canvas_pitch.argtypes = [C.c_int32]
+    lib.sb_canvas_pitch.restype = i64
+    lib.sb_chunked_plane_elems.argtypes = [C.c_int32] * 4
+    lib.sb_chunked_plane_elems.restype = i64
+    lib.sb_register_pairs.argtypes = [vp, C.POINTER(SbRegisterJob), C.POINTER(SbPairResult)]
+    lib.sb_normalize.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32]
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _ptr(a) -> int:
+    """Address of a numpy array's first element, a raw int address, or a torch tensor's data_ptr."""
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return int(a.data_ptr())
+    raise TypeError(f"cannot take the address of {type(a)}")
+
+
+class Context:
+    """One ``sb_ctx``: create it lazily inside the worker process (after fork), one per device."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.sb_create(int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"sb_create(device={device}) failed [{rc}]: {self.lib.sb_last_error(None).decode()}")
+        self.handle = h
+        self.device = device
+        self._pinned = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed [{rc}]: {self.lib.sb_last_error(self.handle).decode()}")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            for addr in list(self._pinned):
+                self.lib.sb_host_free(self.handle, addr)
+            self._pinned.clear()
+            self.lib.sb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.sb_kernel_launches(self.handle))
+
+    @property
+    def num_lanes(self) -> int:
+        return int(self.lib.sb_num_lanes(self.handle))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self.lib.sb_device_sm_count(self.handle))
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """A numpy array over page-locked host memory (freed when the context closes)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        addr = self.lib.sb_host_alloc(self.handle, max(n, 1))
+        if not addr:
+            raise MemoryError(self.lib.sb_last_error(self.handle).decode())
+        self._pinned[addr] = n
+        buf = (C.c_uint8 * max(n, 1)).from_address(addr)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def sync(self, lane: int = -1):
+        self._check(self.lib.sb_sync(self.handle, lane), "sb_sync")
+
+    def set_lane_stream(self, lane: int, stream_ptr: Optional[int]):
+        self._check(self.lib.sb_set_lane_stream(self.handle, lane, C.c_void_p(stream_ptr or 0)), "sb_set_lane_stream")
+
+    # ------------------------------------------------------------------ fields
+    @staticmethod
+    def _field_args(field, mem):
+        if mem == SB_MEM_HOST:
+            field = np.ascontiguousarray(field)
+            if field.dtype not in (np.float32, np.float64):
+                field = field.astype(np.float64)
+            dt = SB_FIELD_F64 if field.dtype == np.float64 else SB_FIELD_F32
+            return field, dt, field.shape
+        dt = SB_FIELD_F64 if "float64" in str(field.dtype) else SB_FIELD_F32
+        return field, dt, tuple(field.shape)
+
+    def set_flatfield(self, channel: int, field, mem: int = SB_MEM_HOST):
+        field, dt, shape = self._field_args(field, mem)
+        self._check(self.lib.sb_set_flatfield(self.handle, channel, _ptr(field), dt, mem, shape[0], shape[1]),
+                    "sb_set_flatfield")
+
+    def set_darkfield(self, channel: int, field, mem: int = SB_MEM_HOST):
+        field, dt, shape = self._field_args(field, mem)
+        self._check(self.lib.sb_set_darkfield(self.handle, channel, _ptr(field), dt, mem, shape[0], shape[1]),
+                    "sb_set_darkfield")
+
+    def clear_fields(self):
+        self._check(self.lib.sb_clear_fields(self.handle), "sb_clear_fields")
+
+    def flatfield_apply(self, channel: int, tiles: np.ndarray) -> np.ndarray:
+        tiles = np.ascontiguousarray(tiles)
+        assert tiles.dtype == np.uint16
+        t3 = tiles.reshape((-1,) + tiles.shape[-2:])
+        out = np.empty_like(t3)
+        self._check(self.lib.sb_flatfield_apply(self.handle, channel, _ptr(t3), _ptr(out), t3.shape[0], t3.shape[1],
+                                                t3.shape[2], SB_U16, SB_MEM_HOST), "sb_flatfield_apply")
+        return out.reshape(tiles.shape)
+
+    # ------------------------------------------------------------------ fusion
+    def fuse_region(self, tiles: Sequence[tuple], tile_shape, canvas_shape, *, out, tile_mem=SB_MEM_HOST,
+                    out_mem=SB_MEM_HOST, apply_flatfield=False, blend=SB_BLEND_PASTE, blend_ov=(0, 0),
+                    layout=SB_LAYOUT_ROWMAJOR, out_row_pitch=0, chunk=(0, 0), lane=-1, keepalive=None):
+        """``tiles``: sequence of ``(px, x, y, c, z, crop_t, crop_b, crop_l, crop_r)`` in paste order.
+
+        ``canvas_shape`` = ``(num_c, num_z, height, width)``.  ``out`` is a numpy array / address / tensor.
+        """
+        n = len(tiles)
+        arr = (SbTile * max(n, 1))()
+        for i, t in enumerate(tiles):
+            px, x, y, c, z, ct, cb, cl, cr = t
+            arr[i] = SbTile(_ptr(px), int(x), int(y), int(c), int(z), int(ct), int(cb), int(cl), int(cr))
+        job = SbFuseJob(arr, n, int(tile_shape[0]), int(tile_shape[1]), SB_U16, tile_mem,
+                        int(canvas_shape[0]), int(canvas_shape[1]), int(canvas_shape[2]), int(canvas_shape[3]),
+                        int(bool(apply_flatfield)), int(blend), int(blend_ov[0]), int(blend_ov[1]),
+                        _ptr(out), out_mem, layout, int(out_row_pitch), int(chunk[0]), int(chunk[1]))
+        self._check(self.lib.sb_fuse_region(self.handle, C.byref(job), lane), "sb_fuse_region")
+
+    # ------------------------------------------------------------------ registration
+    def register_pairs(self, pairs: Sequence[tuple], tile_shape, max_overlap_x: int, max_overlap_y: int, *,
+                       mem=SB_MEM_HOST, upsample_factor: int = 10, precision: int = SB_PREC_AUTO):
+        """``pairs``: sequence of ``(ref, mov, dir)``.  Returns a list of dicts (see ``sb_pair_result``)."""
+        n = len(pairs)
+        if n == 0:
+            return []
+        arr = (SbPair * n)()
+        for i, (ref, mov, d) in enumerate(pairs):
+            arr[i] = SbPair(_ptr(ref), _ptr(mov), int(d), 0)
+        res = (SbPairResult * n)()
+        job = SbRegisterJob(arr, n, int(tile_shape[0]), int(tile_shape[1]), SB_U16, mem, int(max_overlap_x),
+                            int(max_overlap_y), int(upsample_factor), int(precision))
+        self._check(self.lib.sb_register_pairs(self.handle, C.byref(job), res), "sb_register_pairs")
+        out = []
+        for r in res:
+            out.append({"dy": r.dy, "dx": r.dx, "shift": (r.shift[0], r.shift[1]),
+                        "coarse": (r.coarse[0], r.coarse[1]), "fine": (r.fine[0], r.fine[1]), "peak": r.peak,
+                        "runner_up": r.runner_up, "fine_peak": r.fine_peak, "ref_minmax": (r.ref_min, r.ref_max),
+                        "mov_minmax": (r.mov_min, r.mov_max), "precision": r.precision})
+        return out
+
+    def normalize(self, tiles: np.ndarray) -> np.ndarray:
+        tiles = np.ascontiguousarray(tiles)
+        assert tiles.dtype == np.uint16
+        t3 = tiles.reshape((-1,) + tiles.shape[-2:])
+        out = np.empty_like(t3)
+        self._check(self.lib.sb_normalize(self.handle, _ptr(t3), _ptr(out), t3.shape[0], t3.shape[1], t3.shape[2],
+                                          SB_U16, SB_MEM_HOST), "sb_normalize")
+        return out.reshape(tiles.shape)
+
+
+def canvas_pitch(width: int) -> int:
+    return int(load_library().sb_canvas_pitch(int(width)))

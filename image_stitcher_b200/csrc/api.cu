@@ -1,0 +1,275 @@
+// C-ABI entry points of libstitchb200 (include/stitchb200.h): context lifecycle, memory helpers,
+// flat/dark-field storage.  The compute entry points forward to fuse.cu / reg.cu.
+#include "sb_common.cuh"
+
+#include <mutex>
+
+static thread_local std::string g_create_error;
+
+int sb_fail(sb_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    if (code == SB_ERR_CUDA) cudaGetLastError();   // clear the sticky-less error state
+    return code;
+}
+
+int sb_reserve(sb_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return SB_OK;
+    if (b.p) {
+        // growing a buffer that earlier asynchronous work may still use: drain first
+        cudaDeviceSynchronize();
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    const size_t want = round_up64((int64_t)bytes, 1 << 20);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return sb_fail(ctx, SB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return SB_OK;
+}
+
+int sb_reserve_pinned(sb_ctx* ctx, void** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return SB_OK;
+    if (*p) {
+        cudaDeviceSynchronize();
+        cudaFreeHost(*p);
+        *p = nullptr;
+        *cap = 0;
+    }
+    const size_t want = round_up64((int64_t)bytes, 1 << 16);
+    cudaError_t e = cudaMallocHost(p, want);
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return sb_fail(ctx, SB_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    *cap = want;
+    return SB_OK;
+}
+
+Lane* sb_lane(sb_ctx* ctx, int lane) {
+    if (!ctx || lane < 0 || lane >= SB_NUM_LANES) return nullptr;
+    return &ctx->lanes[lane];
+}
+
+extern "C" {
+
+int sb_version(void) { return SB_ABI_VERSION; }
+
+int sb_create(int device, sb_ctx** out) {
+    if (!out) return sb_fail(nullptr, SB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return sb_fail(nullptr, SB_ERR_NODEVICE, "no CUDA device available (%s); libstitchb200 has no CPU path",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return sb_fail(nullptr, SB_ERR_INVALID, "device %d out of range [0, %d)", device, n);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return sb_fail(nullptr, SB_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return sb_fail(nullptr, SB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return sb_fail(nullptr, SB_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                       prop.major, prop.minor);
+    sb_ctx* ctx = new sb_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < SB_NUM_LANES; ++i) {
+        Lane& l = ctx->lanes[i];
+        if (cudaStreamCreateWithFlags(&l.own, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.meta_free, cudaEventDisableTiming) != cudaSuccess) {
+            sb_fail(nullptr, SB_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            delete ctx;
+            return SB_ERR_CUDA;
+        }
+        l.stream = l.own;
+    }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        sb_fail(nullptr, SB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        delete ctx;
+        return SB_ERR_CUDA;
+    }
+    ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
+    *out = ctx;
+    return SB_OK;
+}
+
+static void free_field(FieldPool& f) {
+    if (f.dev) cudaFree(f.dev);
+    f = FieldPool();
+}
+
+void sb_destroy(sb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < SB_NUM_LANES; ++i) {
+        Lane& l = ctx->lanes[i];
+        for (DevBuf* b : {&l.tiles, &l.canvas, &l.meta, &l.work})
+            if (b->p) cudaFree(b->p);
+        if (l.meta_host) cudaFreeHost(l.meta_host);
+        if (l.meta_free) cudaEventDestroy(l.meta_free);
+        if (l.own) cudaStreamDestroy(l.own);
+    }
+    for (DevBuf* b : {&ctx->reg_tiles, &ctx->reg_work, &ctx->reg_meta})
+        if (b->p) cudaFree(b->p);
+    if (ctx->reg_meta_host) cudaFreeHost(ctx->reg_meta_host);
+    for (auto& kv : ctx->twiddle_cache)
+        if (kv.second.p) cudaFree(kv.second.p);
+    free_field(ctx->flat);
+    free_field(ctx->dark);
+    delete ctx;
+}
+
+const char* sb_last_error(const sb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int64_t sb_kernel_launches(const sb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int sb_num_lanes(const sb_ctx*) { return SB_NUM_LANES; }
+int sb_device_sm_count(const sb_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+void* sb_host_alloc(sb_ctx* ctx, size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        sb_fail(ctx, SB_ERR_NOMEM, "cudaMallocHost(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void sb_host_free(sb_ctx*, void* p) {
+    if (p) cudaFreeHost(p);
+}
+void* sb_device_alloc(sb_ctx* ctx, size_t bytes) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        sb_fail(ctx, SB_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void sb_device_free(sb_ctx*, void* p) {
+    if (p) cudaFree(p);
+}
+int sb_memcpy_h2d(sb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    SB_CUDA(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return SB_OK;
+}
+int sb_memcpy_d2h(sb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    SB_CUDA(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+static int set_field(sb_ctx* ctx, FieldPool& pool, const char* what, int channel, const void* field, int dtype, int mem,
+                     int h, int w) {
+    SB_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    SB_CHECK(ctx, channel >= 0 && channel < 4096, "%s: channel %d out of range", what, channel);
+    SB_CHECK(ctx, field != nullptr && h > 0 && w > 0, "%s: bad field", what);
+    SB_CHECK(ctx, dtype == SB_FIELD_F32 || dtype == SB_FIELD_F64, "%s: unknown dtype %d", what, dtype);
+    const size_t eb = dtype == SB_FIELD_F64 ? 8 : 4;
+    if (pool.dev && (pool.h != h || pool.w != w || pool.dtype != dtype))
+        return sb_fail(ctx, SB_ERR_INVALID, "%s: shape/dtype differs from fields already set; call sb_clear_fields first",
+                       what);
+    if ((int)pool.slot_of_channel.size() <= channel) pool.slot_of_channel.resize(channel + 1, -1);
+    int slot = pool.slot_of_channel[channel];
+    // Element-shifted copies so that a copy exists whose TMA box start is 16-byte aligned for any
+    // tile offset: copy e holds field[row][i - e] at column i (row pitch w + 4, zero elsewhere).
+    const int ncopy = 16 / (int)eb;
+    const size_t fpitch = (size_t)(w + 4) * eb;
+    const size_t plane = (size_t)h * fpitch;
+    const size_t one = plane * ncopy;
+    if (slot < 0) {
+        // grow the contiguous pool by one slot (fields are set once per run: simplicity over speed)
+        void* nd = nullptr;
+        cudaDeviceSynchronize();
+        if (cudaMalloc(&nd, one * (pool.n_slots + 1)) != cudaSuccess)
+            return sb_fail(ctx, SB_ERR_NOMEM, "%s: cudaMalloc failed", what);
+        if (pool.dev) {
+            cudaMemcpy(nd, pool.dev, one * pool.n_slots, cudaMemcpyDeviceToDevice);
+            cudaFree(pool.dev);
+        }
+        pool.dev = nd;
+        slot = pool.n_slots++;
+        pool.slot_of_channel[channel] = slot;
+        pool.h = h;
+        pool.w = w;
+        pool.dtype = dtype;
+    }
+    uint8_t* base = (uint8_t*)pool.dev + (size_t)slot * one;
+    SB_CUDA(ctx, cudaMemset(base, 0, one));
+    for (int e = 0; e < ncopy; ++e)
+        SB_CUDA(ctx, cudaMemcpy2D(base + (size_t)e * plane + (size_t)e * eb, fpitch, field, (size_t)w * eb, (size_t)w * eb, h,
+                                  mem == SB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    SB_CUDA(ctx, cudaDeviceSynchronize());
+    return SB_OK;
+}
+
+int sb_set_flatfield(sb_ctx* ctx, int channel, const void* field, int dtype, int mem, int h, int w) {
+    return set_field(ctx, ctx->flat, "sb_set_flatfield", channel, field, dtype, mem, h, w);
+}
+int sb_set_darkfield(sb_ctx* ctx, int channel, const void* field, int dtype, int mem, int h, int w) {
+    return set_field(ctx, ctx->dark, "sb_set_darkfield", channel, field, dtype, mem, h, w);
+}
+int sb_clear_fields(sb_ctx* ctx) {
+    SB_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    cudaDeviceSynchronize();
+    free_field(ctx->flat);
+    free_field(ctx->dark);
+    return SB_OK;
+}
+
+int64_t sb_canvas_pitch(int32_t width) { return round_up64(width, 64); }
+int64_t sb_chunked_plane_elems(int32_t height, int32_t width, int32_t chunk_h, int32_t chunk_w) {
+    if (chunk_h <= 0 || chunk_w <= 0) return 0;
+    return (int64_t)((height + chunk_h - 1) / chunk_h) * ((width + chunk_w - 1) / chunk_w) * chunk_h * chunk_w;
+}
+
+int sb_fuse_region(sb_ctx* ctx, const sb_fuse_job* job, int lane) {
+    if (!ctx) return SB_ERR_INVALID;
+    if (lane >= SB_NUM_LANES) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
+    return sb_fuse_region_impl(ctx, job, lane);
+}
+
+int sb_sync(sb_ctx* ctx, int lane) {
+    if (!ctx) return SB_ERR_INVALID;
+    if (lane >= SB_NUM_LANES) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
+    for (int i = 0; i < SB_NUM_LANES; ++i)
+        if (lane < 0 || lane == i) SB_CUDA(ctx, cudaStreamSynchronize(ctx->lanes[i].stream));
+    return SB_OK;
+}
+
+int sb_set_lane_stream(sb_ctx* ctx, int lane, void* cuda_stream) {
+    Lane* l = sb_lane(ctx, lane);
+    if (!l) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
+    SB_CUDA(ctx, cudaStreamSynchronize(l->stream));
+    l->stream = cuda_stream ? (cudaStream_t)cuda_stream : l->own;
+    return SB_OK;
+}
+
+int sb_flatfield_apply(sb_ctx* ctx, int channel, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w,
+                       int dtype, int mem) {
+    if (!ctx) return SB_ERR_INVALID;
+    return sb_flatfield_apply_impl(ctx, channel, tiles, out, n_tiles, tile_h, tile_w, dtype, mem);
+}
+
+int sb_register_pairs(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out) {
+    if (!ctx) return SB_ERR_INVALID;
+    return sb_register_pairs_impl(ctx, job, out);
+}
+
+int sb_normalize(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int dtype, int mem) {
+    if (!ctx) return SB_ERR_INVALID;
+    return sb_normalize_impl(ctx, tiles, out, n_tiles, tile_h, tile_w, dtype, mem);
+}
+
+}  // extern "C"

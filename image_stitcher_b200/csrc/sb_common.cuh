@@ -1,0 +1,147 @@
+// Shared host/device plumbing for libstitchb200: context, lanes, error handling, PTX wrappers.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/stitchb200.h"
+
+#define SB_NUM_LANES 3
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct FieldPool {            // flat- or dark-fields of all channels, one contiguous device array
+    void* dev = nullptr;      // [n_slots][ncopy][h][w] of float or double; copy d holds field[.., i + d]
+    int ncopy() const { return dtype == SB_FIELD_F64 ? 2 : 4; }
+    int dtype = SB_FIELD_F32;
+    int h = 0, w = 0;
+    int n_slots = 0;
+    std::vector<int> slot_of_channel;   // channel -> slot or -1
+    bool any() const { for (int s : slot_of_channel) if (s >= 0) return true; return false; }
+    int slot(int c) const { return (c >= 0 && c < (int)slot_of_channel.size()) ? slot_of_channel[c] : -1; }
+};
+
+struct Lane {
+    cudaStream_t own = nullptr;
+    cudaStream_t stream = nullptr;
+    DevBuf tiles, canvas, meta, work;
+    void* meta_host = nullptr;      // pinned staging for per-job metadata
+    size_t meta_host_cap = 0;
+    cudaEvent_t meta_free = nullptr; // the previous job's metadata H2D has been consumed
+};
+
+struct sb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    int64_t launches = 0;
+    Lane lanes[SB_NUM_LANES];
+    FieldPool flat, dark;
+    // driver entry point for TMA descriptors (resolved through the runtime: no libcuda link dependency)
+    CUresult (*encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
+    // registration workspace (grown on demand)
+    DevBuf reg_tiles, reg_work, reg_meta;
+    void* reg_meta_host = nullptr;
+    size_t reg_meta_host_cap = 0;
+    std::unordered_map<uint64_t, DevBuf> twiddle_cache;   // key: (n << 1 | is_double)
+};
+
+int sb_fail(sb_ctx* ctx, int code, const char* fmt, ...);
+int sb_reserve(sb_ctx* ctx, DevBuf& b, size_t bytes);
+int sb_reserve_pinned(sb_ctx* ctx, void** p, size_t* cap, size_t bytes);
+Lane* sb_lane(sb_ctx* ctx, int lane);
+
+#define SB_CUDA(ctx, call)                                                                       \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return sb_fail((ctx), SB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                           __FILE__, __LINE__);                                                  \
+    } while (0)
+
+#define SB_CHECK(ctx, cond, ...)                                        \
+    do {                                                                \
+        if (!(cond)) return sb_fail((ctx), SB_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+static inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// entry points implemented in fuse.cu / reg.cu, called from api.cu
+int sb_fuse_region_impl(sb_ctx* ctx, const sb_fuse_job* job, int lane);
+int sb_flatfield_apply_impl(sb_ctx* ctx, int channel, const void* tiles, void* out, int n_tiles, int tile_h,
+                            int tile_w, int dtype, int mem);
+int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out);
+int sb_normalize_impl(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int dtype,
+                      int mem);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------- device-side PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SB_DONE;\n"
+        "bra SB_WAIT;\n"
+        "SB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// 2-D tiled TMA load global -> shared, completion on an mbarrier, with an L2 eviction hint.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// streaming 128-bit store: written once, never re-read by this kernel
+__device__ __forceinline__ void st_stream_v4(void* p, uint4 v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+#endif  // __CUDACC__

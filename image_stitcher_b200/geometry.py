@@ -1,0 +1,137 @@
+"""Host-side placement geometry of the fusion path (product code; pure integer/float64 Python).
+
+The CUDA kernels receive integers only; everything the reference derives from stage
+coordinates and the registration lattice is computed here with the reference's own
+rounding rules so that the canvas is bit-identical:
+
+* canvas size          -- ``calculate_output_dimensions`` (stitcher_process.py:423-477)
+* tile origin          -- ``stitch_region`` (stitcher_process.py:919-942)
+* seam crops           -- ``place_single_channel_tile`` (stitcher_process.py:789-806)
+* strip widths         -- ``calculate_shifts`` (stitcher_process.py:602-609)
+
+Quirks kept on purpose: the registered canvas height uses
+``H - v_shift[0]`` (over-allocates for the usual negative v_shift); stage coordinates
+are truncated with ``int()``; Python ``//`` floors negative numbers.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class Lattice:
+    """Registration result applied to every region (self.h_shift / v_shift / h_shift_rev*)."""
+    h_shift: Tuple[int, int] = (0, 0)
+    v_shift: Tuple[int, int] = (0, 0)
+    h_shift_rev: Tuple[int, int] = (0, 0)
+    h_shift_rev_odd: int = 0
+    s_pattern: bool = False
+
+    def h_for_row(self, row: int) -> Tuple[int, int]:
+        if self.s_pattern and row % 2 == self.h_shift_rev_odd:
+            return self.h_shift_rev
+        return self.h_shift
+
+
+@dataclass(frozen=True)
+class Placement:
+    """Where one tile lands: uncropped origin + seam crops (ints handed to ``sb_tile``)."""
+    x: int
+    y: int
+    crop_t: int = 0
+    crop_b: int = 0
+    crop_l: int = 0
+    crop_r: int = 0
+
+
+def strip_overlaps(tile_w: int, tile_h: int, x_positions: Sequence[float], y_positions: Sequence[float],
+                   pixel_size_um: float, pixel_binning: int) -> Tuple[int, int]:
+    """Strip extents used for registration (stitcher_process.py:602-609).
+
+    ``round(|W - dx_px| * 1.05) // 2 * binning`` -- floor-divide first, then scale.
+    """
+    def extent(n_px: int, pos: Sequence[float]) -> int:
+        step_px = (pos[1] - pos[0]) * 1000 / pixel_size_um
+        return round(abs(n_px - step_px) * 1.05) // 2 * pixel_binning
+    return extent(tile_w, x_positions), extent(tile_h, y_positions)
+
+
+def canvas_size(tile_w: int, tile_h: int, x_positions: Sequence[float], y_positions: Sequence[float],
+                pixel_size_um: float, lattice: Optional[Lattice]) -> Tuple[int, int]:
+    """(width, height) of the stitched region (stitcher_process.py:441-466)."""
+    if lattice is not None:
+        n_cols, n_rows = len(x_positions), len(y_positions)
+        if lattice.s_pattern:
+            mh0 = max(abs(lattice.h_shift[0]), abs(lattice.h_shift_rev[0]))
+            mh1 = max(abs(lattice.h_shift[1]), abs(lattice.h_shift_rev[1]))
+        else:
+            mh0, mh1 = abs(lattice.h_shift[0]), abs(lattice.h_shift[1])
+        width = int(tile_w + (n_cols - 1) * (tile_w - mh1)) + abs((n_rows - 1) * lattice.v_shift[1])
+        # reference quirk (:457): minus a (normally negative) v_shift[0] -> taller than needed
+        height = int(tile_h + (n_rows - 1) * (tile_h - lattice.v_shift[0])) + abs((n_cols - 1) * mh0)
+        return width, height
+    width_mm = max(x_positions) - min(x_positions) + (tile_w * pixel_size_um / 1000)
+    height_mm = max(y_positions) - min(y_positions) + (tile_h * pixel_size_um / 1000)
+    return int(np.ceil(width_mm * 1000 / pixel_size_um)), int(np.ceil(height_mm * 1000 / pixel_size_um))
+
+
+def pyramid_levels(width: int, height: int, n_regions: int = 1, region_grid_max_dim: int = 1) -> int:
+    """stitcher_process.py:468-475."""
+    max_dimension = region_grid_max_dim if n_regions > 1 else 1
+    return max(1, math.ceil(np.log2(max(width, height) / 1024 * max_dimension)))
+
+
+def place_tile(x_mm: float, y_mm: float, tile_w: int, tile_h: int, x_positions: Sequence[float],
+               y_positions: Sequence[float], pixel_size_um: float, lattice: Optional[Lattice]) -> Placement:
+    """Origin and seam crops of one tile (stitcher_process.py:919-942 and :789-806)."""
+    if lattice is None:
+        return Placement(int((x_mm - min(x_positions)) * 1000 / pixel_size_um),
+                         int((y_mm - min(y_positions)) * 1000 / pixel_size_um))
+    col, row = x_positions.index(x_mm), y_positions.index(y_mm)
+    n_cols, n_rows = len(x_positions), len(y_positions)
+    h, v = lattice.h_for_row(row), lattice.v_shift
+    x = int(col * (tile_w + h[1]))
+    y = int(row * (tile_h + v[0]))
+    y += int((n_cols - 1 - col) * abs(h[0])) if h[0] < 0 else int(col * h[0])
+    x += int((n_rows - 1 - row) * abs(v[1])) if v[1] < 0 else int(row * v[1])
+    vert = max(0, (-v[0] // 2) - abs(h[0]) // 2)
+    horz = max(0, (-h[1] // 2) - abs(v[1]) // 2)
+    return Placement(x, y,
+                     crop_t=vert if row > 0 else 0, crop_b=vert if row < n_rows - 1 else 0,
+                     crop_l=horz if col > 0 else 0, crop_r=horz if col < n_cols - 1 else 0)
+
+
+def center_pairs(x_positions: Sequence[float], y_positions: Sequence[float], s_pattern: bool):
+    """The 2 (3 for S-Pattern) tile pairs ``calculate_shifts`` registers (stitcher_process.py:612-660).
+
+    Returns a list of ``(kind, (x, y) of ref, (x, y) of mov)`` with kind in {'h', 'v', 'h_rev'} and
+    ``h_shift_rev_odd``.
+    """
+    cx, cy = (len(x_positions) - 1) // 2, (len(y_positions) - 1) // 2
+    pairs = []
+    right = x_positions[cx + 1] if cx + 1 < len(x_positions) else None
+    below = y_positions[cy + 1] if cy + 1 < len(y_positions) else None
+    if right is not None:
+        pairs.append(("h", (x_positions[cx], y_positions[cy]), (right, y_positions[cy])))
+    if below is not None:
+        pairs.append(("v", (x_positions[cx], y_positions[cy]), (x_positions[cx], below)))
+    # truthiness test on the coordinates, as the reference writes it (:649)
+    if s_pattern and right and below:
+        pairs.append(("h_rev", (x_positions[cx], below), (right, below)))
+    return pairs, (cy % 2 == 0)
+
+
+def grid_pairs(n_rows: int, n_cols: int) -> List[Tuple[str, Tuple[int, int], Tuple[int, int]]]:
+    """All adjacent pairs of a rows x cols grid (all-pairs mode behind ``dynamic_registration``)."""
+    out = []
+    for r in range(n_rows):
+        for c in range(n_cols):
+            if c + 1 < n_cols:
+                out.append(("h", (r, c), (r, c + 1)))
+            if r + 1 < n_rows:
+                out.append(("v", (r, c), (r + 1, c)))
+    return out

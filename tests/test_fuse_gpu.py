@@ -1,0 +1,168 @@
+"""GPU parity tests of the fusion kernel (K5) through the C ABI against the oracle and the
+reference-generated golden canvases.  Bar: bit-exact for paste mode; within 1 LSB for the
+(extension) blend modes."""
+import numpy as np
+import pytest
+
+from conftest import SMALL_GOLDENS, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from image_stitcher_b200 import _ffi
+    c = _ffi.Context(0)
+    yield c
+    c.close()
+
+
+def golden_job(g, st, tiles):
+    """sb_tile tuples for a golden case using the PRODUCT geometry and the golden's shifts."""
+    from image_stitcher_b200 import geometry as geo
+    xs = sorted(set(t.x_mm for t in tiles))
+    ys = sorted(set(t.y_mm for t in tiles))
+    lat = None
+    if st.use_registration:
+        lat = geo.Lattice(tuple(int(v) for v in g["h_shift"]), tuple(int(v) for v in g["v_shift"]),
+                          tuple(int(v) for v in g["h_shift_rev"]), int(g["h_shift_rev_odd"]),
+                          st.scan_pattern == "S-Pattern")
+    width, height = geo.canvas_size(st.tile_w, st.tile_h, xs, ys, st.pixel_size_um, lat)
+    job = []
+    for t in tiles:
+        p = geo.place_tile(t.x_mm, t.y_mm, st.tile_w, st.tile_h, xs, ys, st.pixel_size_um, lat)
+        job.append((np.ascontiguousarray(t.pixels), p.x, p.y, st.monochrome_channels.index(t.channel), t.z_level,
+                    p.crop_t, p.crop_b, p.crop_l, p.crop_r))
+    return job, (st.num_c, st.num_z, height, width)
+
+
+@pytest.mark.parametrize("name", SMALL_GOLDENS)
+def test_paste_matches_reference_golden(ctx, name):
+    g, st, tiles, kw = load_golden(name)
+    job, cshape = golden_job(g, st, tiles)
+    assert (1,) + cshape == tuple(g["canvas_shape"])
+    ctx.clear_fields()
+    for c, ff in st.flatfields.items():
+        ctx.set_flatfield(c, ff)
+    out = np.full((1,) + cshape, 0xABCD, np.uint16)
+    ctx.fuse_region(job, (st.tile_h, st.tile_w), cshape, out=out, apply_flatfield=st.apply_flatfield)
+    assert np.array_equal(out, g["canvas"])
+
+
+def random_job(rng, n_tiles, th, tw, C, Z, Hc, Wc, crops=True):
+    job = []
+    for i in range(n_tiles):
+        px = rng.integers(0, 65536, (th, tw), dtype=np.uint16)
+        x = int(rng.integers(0, max(1, Wc - tw // 2)))
+        y = int(rng.integers(0, max(1, Hc - th // 2)))
+        cr = [int(v) for v in rng.integers(0, 9, 4)] if crops else [0, 0, 0, 0]
+        job.append((px, x, y, int(rng.integers(0, C)), int(rng.integers(0, Z)), *cr))
+    return job
+
+
+@pytest.mark.parametrize("seed,fields", [(0, "none"), (1, "flat"), (2, "flat+dark"), (3, "flat")])
+def test_paste_random_geometry(ctx, seed, fields):
+    from oracle import blend_ref
+    rng = np.random.default_rng(seed)
+    th, tw, C, Z, Hc, Wc = 96, 136, 2, 2, 333, 517
+    job = random_job(rng, 23, th, tw, C, Z, Hc, Wc)
+    flats = darks = None
+    ctx.clear_fields()
+    if "flat" in fields:
+        flats = {0: rng.uniform(0.6, 1.4, (th, tw)).astype(np.float32)}          # channel 1 passes through
+        if seed == 3:
+            flats[0][5, 7] = 0.0                                                  # x/0 -> inf -> 65535 ; 0/0 -> 0
+            job[0][0][5, 7] = 0
+        ctx.set_flatfield(0, flats[0])
+    if "dark" in fields:
+        darks = {0: rng.uniform(0, 300, (th, tw)).astype(np.float32), 1: rng.uniform(0, 300, (th, tw)).astype(np.float32)}
+        for c, d in darks.items():
+            ctx.set_darkfield(c, d)
+    out = np.full((1, C, Z, Hc, Wc), 7, np.uint16)
+    ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=out, apply_flatfield=fields != "none")
+    exp = blend_ref.fuse_paste(job, (C, Z, Hc, Wc), flats, darks)
+    assert np.array_equal(out, exp)
+
+
+@pytest.mark.parametrize("mode", ["linear", "feather"])
+@pytest.mark.parametrize("fields", ["none", "flat+dark"])
+def test_blend_modes_within_one_lsb(ctx, mode, fields):
+    from image_stitcher_b200 import _ffi
+    from oracle import blend_ref
+    rng = np.random.default_rng(5)
+    th, tw, C, Z, Hc, Wc = 128, 160, 2, 1, 300, 420
+    job = random_job(rng, 14, th, tw, C, Z, Hc, Wc, crops=False)
+    flats = darks = None
+    ctx.clear_fields()
+    if fields != "none":
+        flats = {c: rng.uniform(0.7, 1.2, (th, tw)).astype(np.float32) for c in range(C)}
+        darks = {c: rng.uniform(0, 100, (th, tw)).astype(np.float32) for c in range(C)}
+        for c in range(C):
+            ctx.set_flatfield(c, flats[c])
+            ctx.set_darkfield(c, darks[c])
+    out = np.empty((1, C, Z, Hc, Wc), np.uint16)
+    ov = (17, 13)
+    ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=out, apply_flatfield=fields != "none",
+                    blend=_ffi.BLEND_MODES[mode], blend_ov=ov)
+    exp = blend_ref.fuse_blend(job, (C, Z, Hc, Wc), mode, ov, flats, darks)
+    diff = np.abs(out.astype(np.int32) - exp.astype(np.int32))
+    assert diff.max() <= 1
+    assert (diff != 0).mean() < 0.01           # disagreements only at exact .5 ties
+
+
+def test_chunked_layout_equals_rowmajor(ctx):
+    from image_stitcher_b200 import _ffi
+    rng = np.random.default_rng(8)
+    th, tw, C, Z, Hc, Wc = 100, 120, 1, 2, 300, 411
+    job = random_job(rng, 9, th, tw, C, Z, Hc, Wc)
+    ctx.clear_fields()
+    ref = np.empty((1, C, Z, Hc, Wc), np.uint16)
+    ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=ref)
+    ch, cw = 128, 256
+    ncy, ncx = -(-Hc // ch), -(-Wc // cw)
+    out = np.empty((C * Z, ncy, ncx, ch, cw), np.uint16)
+    ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=out, layout=_ffi.SB_LAYOUT_CHUNKED, chunk=(ch, cw))
+    full = out.transpose(0, 1, 3, 2, 4).reshape(C * Z, ncy * ch, ncx * cw)
+    assert np.array_equal(full[:, :Hc, :Wc], ref.reshape(C * Z, Hc, Wc))
+    assert not full[:, Hc:, :].any() and not full[:, :, Wc:].any()      # zarr-v2 edge chunks are zero padded
+
+
+def test_empty_region_is_zero(ctx):
+    out = np.full((1, 1, 1, 70, 90), 5, np.uint16)
+    ctx.fuse_region([], (64, 64), (1, 1, 70, 90), out=out)
+    assert not out.any()
+
+
+def test_device_memory_path_and_lanes(ctx):
+    import torch
+    from image_stitcher_b200 import _ffi
+    from oracle import blend_ref
+    rng = np.random.default_rng(9)
+    th, tw, C, Z, Hc, Wc = 64, 128, 1, 1, 200, 500
+    job = random_job(rng, 12, th, tw, C, Z, Hc, Wc)
+    pool = torch.from_numpy(np.stack([t[0] for t in job]).view(np.int16)).cuda()
+    dev_job = [(pool[i].data_ptr(),) + t[1:] for i, t in enumerate(job)]
+    pitch = _ffi.canvas_pitch(Wc)
+    outs = []
+    ctx.clear_fields()
+    for lane in range(ctx.num_lanes):
+        out = torch.full((C * Z, Hc, pitch), -1, dtype=torch.int16, device="cuda")
+        torch.cuda.synchronize()
+        ctx.fuse_region(dev_job, (th, tw), (C, Z, Hc, Wc), out=out, tile_mem=_ffi.SB_MEM_DEVICE,
+                        out_mem=_ffi.SB_MEM_DEVICE, lane=lane)
+        outs.append(out)
+    ctx.sync()
+    exp = blend_ref.fuse_paste(job, (C, Z, Hc, Wc))
+    for out in outs:
+        got = out.cpu().numpy().view(np.uint16)
+        assert np.array_equal(got[:, :, :Wc], exp.reshape(C * Z, Hc, Wc))
+        assert not got[:, :, Wc:].any()
+
+
+def test_errors_are_reported(ctx):
+    with pytest.raises(RuntimeError, match="plane"):
+        ctx.fuse_region([(np.zeros((8, 8), np.uint16), 0, 0, 3, 0, 0, 0, 0, 0)], (8, 8), (1, 1, 16, 16),
+                        out=np.zeros((1, 1, 1, 16, 16), np.uint16))
+    with pytest.raises(RuntimeError, match="negative"):
+        ctx.fuse_region([(np.zeros((8, 8), np.uint16), -4, 0, 0, 0, 0, 0, 0, 0)], (8, 8), (1, 1, 16, 16),
+                        out=np.zeros((1, 1, 1, 16, 16), np.uint16))
