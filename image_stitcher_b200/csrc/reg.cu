@@ -1,8 +1,796 @@
-// placeholder until the registration chain lands
+// K0-K4: pairwise phase-cross-correlation registration of overlap strips (sm_100a).
+//
+// Replaces, for a batch of tile pairs, calculate_horizontal_shift / calculate_vertical_shift
+// (stitcher_process.py:664-708), normalize_image (:844-855) and the un-vendored third-party
+// skimage.registration.phase_cross_correlation(a, b, upsample_factor=uf) they call (algorithm
+// restated in oracle/pcc_ref.py).  Chain per pair, all on the device:
+//
+//   K0 tile_minmax      whole-tile min/max (normalize_image stretches the WHOLE tile, :852)
+//   K1 rows_fwd         strip crop + float64 stretch + truncating cast fused into the load;
+//                       both strips packed as z = a + i b; FFT along x           -> Z
+//   K2 cols_xpower      FFT along y of column pairs (kx, -kx); unpack the two real spectra,
+//                       R = A conj(B) / max(|A conj(B)|, 100 eps); store R (for K4); inverse FFT
+//                       along y                                                   -> Y (in place)
+//   K3 rows_inv_argmax  rows packed two at a time (R is Hermitian, so the result is real), inverse
+//                       FFT along x, |cc|, first-maximum argmax (warp shuffles)   -> coarse peak
+//   K4 updft            skimage's matrix-multiply upsampled DFT in a ceil(1.5 uf)^2 window around
+//                       the coarse peak: T = conj(R) Ex^T, out = Ey T, argmax     -> fine peak
+//
+// The kernels return INTEGER peak indices; the float64 shift and the reference's Python round()
+// are rebuilt from them on the host, so the integer shifts are exact by construction.
+// Arithmetic is float32 or float64 (template); SB_PREC_AUTO redoes low-confidence pairs in float64.
 #include "sb_common.cuh"
-int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job*, sb_pair_result*) {
-    return sb_fail(ctx, SB_ERR_UNSUPPORTED, "registration not built yet");
+#include "fft.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+
+namespace {
+
+constexpr double kInScale = 1.0 / 65536.0;                       // exact power-of-two input scaling
+constexpr double kClamp = 100.0 * 2.220446049250313e-16 * kInScale * kInScale;   // 100*eps64, same scaling as P
+
+struct PairDesc {            // device-side description of one pair of a batch
+    const uint16_t* a;       // first pixel of the reference strip
+    const uint16_t* b;       // first pixel of the moving strip
+    int32_t a_tile, b_tile;  // indices into the min/max table
+};
+
+struct CtaBest {             // block-local first maximum; double keeps the float64 path's resolution
+    double val;
+    int32_t idx;
+    int32_t pad;
+};
+
+struct PeakOut {             // per pair, written by the device, read back by the host
+    int32_t coarse_y, coarse_x;
+    int32_t fine_y, fine_x;
+    float peak, runner_up, fine_peak;
+    int32_t pad;
+};
+
+// ------------------------------------------------------------------------------------------ K0
+__global__ void __launch_bounds__(256) minmax_init_kernel(int2* mm, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mm[i] = make_int2(0x7fffffff, -1);
 }
-int sb_normalize_impl(sb_ctx* ctx, const void*, void*, int, int, int, int, int) {
-    return sb_fail(ctx, SB_ERR_UNSUPPORTED, "normalize not built yet");
+
+// grid = (blocks_per_tile, n_tiles).  128-bit loads, warp shuffles, one atomic pair per block.
+__global__ void __launch_bounds__(256) tile_minmax_kernel(const uint16_t* const* __restrict__ tiles, int64_t px, int2* mm) {
+    const uint16_t* t = tiles[blockIdx.y];
+    unsigned lo = 0xffffu, hi = 0u;
+    const int64_t nvec = ((reinterpret_cast<uintptr_t>(t) & 15) == 0) ? px / 8 : 0;
+    const uint4* tv = reinterpret_cast<const uint4*>(t);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(tv + i);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned mn2 = __vminu2(w[k], lo | (lo << 16));
+            const unsigned mx2 = __vmaxu2(w[k], hi | (hi << 16));
+            lo = min(mn2 & 0xffffu, mn2 >> 16);
+            hi = max(mx2 & 0xffffu, mx2 >> 16);
+        }
+    }
+    for (int64_t i = nvec * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned v = t[i];
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ unsigned slo[8], shi[8];
+    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = min(lo, slo[w]); hi = max(hi, shi[w]); }
+        atomicMin(&mm[blockIdx.y].x, (int)lo);
+        atomicMax(&mm[blockIdx.y].y, (int)hi);
+    }
+}
+
+// normalize_image (:844-855): ((v - min) / (max - min)) * 65535 in float64, truncating cast.
+__device__ __forceinline__ int stretch_px(unsigned v, int mn, int mx) {
+    if (mx <= mn) return 0;                       // 0/0 -> NaN -> undefined cast in the reference; defined as 0
+    const double q = __ddiv_rn((double)((int)v - mn), (double)(mx - mn));
+    return (int)(q * 65535.0);
+}
+
+__global__ void __launch_bounds__(256) normalize_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
+                                                        const int2* __restrict__ mm, int64_t px) {
+    const int2 m = mm[blockIdx.y];
+    const uint16_t* t = in + (int64_t)blockIdx.y * px;
+    uint16_t* o = out + (int64_t)blockIdx.y * px;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px; i += (int64_t)gridDim.x * blockDim.x)
+        o[i] = (uint16_t)stretch_px(t[i], m.x, m.y);
+}
+
+// ------------------------------------------------------------------------------------------ K1
+template <typename T, int LB>
+__global__ void __launch_bounds__(256) rows_fwd_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm,
+                                                       int tile_w, int Sh, int Sw, int lpb, int nrb,
+                                                       const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
+                                                       typename Vec2<T>::type* __restrict__ Z, int* __restrict__ nonzero) {
+    using T2 = typename Vec2<T>::type;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    T2* buf0 = reinterpret_cast<T2*>(smem_raw);
+    T2* buf1 = buf0 + (size_t)lpb * Sw;
+    T2* tw = buf1 + (size_t)lpb * Sw;
+    const int p = blockIdx.x / nrb, rb = blockIdx.x - p * nrb;
+    const int y0 = rb * lpb;
+    const PairDesc pd = pairs[p];
+    int seen = 0;                                // bit 0: strip a has a non-zero pixel, bit 1: strip b
+    const int2 ma = mm[pd.a_tile], mb = mm[pd.b_tile];
+    for (int i = threadIdx.x; i < Sw; i += blockDim.x) tw[i] = tw_g[i];
+    for (int i = threadIdx.x; i < lpb * Sw; i += blockDim.x) {
+        const int l = i / Sw, x = i - l * Sw;
+        const int y = y0 + l;
+        T2 z = mk2<T2, T>(0, 0);
+        if (y < Sh) {
+            const size_t off = (size_t)y * tile_w + x;
+            const int na = stretch_px(pd.a[off], ma.x, ma.y), nb = stretch_px(pd.b[off], mb.x, mb.y);
+            seen |= (na != 0 ? 1 : 0) | (nb != 0 ? 2 : 0);
+            z.x = (T)(na * kInScale);
+            z.y = (T)(nb * kInScale);
+        }
+        buf0[i] = z;
+    }
+    // An all-zero strip has an exactly zero spectrum in the reference (P == 0 -> cc == 0 -> argmax 0);
+    // the packed transform only gets it to rounding noise, so record the fact instead.
+    const int any_a = __syncthreads_or(seen & 1), any_b = __syncthreads_or(seen & 2);   // predicate OR, not bitwise
+    if (threadIdx.x == 0 && (any_a || any_b)) atomicOr(&nonzero[p], (any_a ? 1 : 0) | (any_b ? 2 : 0));
+    T2* res = fft_lines<T2, LB>(buf0, buf1, tw, plan, lpb, false);
+    T2* zp = Z + (size_t)p * Sh * Sw;
+    for (int i = threadIdx.x; i < lpb * Sw; i += blockDim.x) {
+        const int l = i / Sw;
+        if (y0 + l < Sh) zp[(size_t)y0 * Sw + i] = res[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K2
+// One block owns G columns kx and their mirrors (Sw - kx) % Sw: 2G lines of length Sh.
+template <typename T, int G>
+__global__ void __launch_bounds__(256) cols_xpower_kernel(int Sh, int Sw, int ncg,
+                                                          const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
+                                                          typename Vec2<T>::type* __restrict__ Z,
+                                                          typename Vec2<T>::type* __restrict__ Rbuf) {
+    using T2 = typename Vec2<T>::type;
+    constexpr int NL = 2 * G;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    T2* buf0 = reinterpret_cast<T2*>(smem_raw);
+    T2* buf1 = buf0 + (size_t)NL * Sh;
+    T2* tw = buf1 + (size_t)NL * Sh;
+    const int p = blockIdx.x / ncg, cg = blockIdx.x - p * ncg;
+    T2* zp = Z + (size_t)p * Sh * Sw;
+    T2* rp = Rbuf + (size_t)p * Sh * Sw;
+    const int half = Sw / 2;                    // columns 0..half own their mirrors
+    for (int i = threadIdx.x; i < Sh; i += blockDim.x) tw[i] = tw_g[i];
+    // line l < G: column kx = cg*G + l ; line G + l: its mirror (unused when the column is self-mirrored)
+    for (int i = threadIdx.x; i < NL * Sh; i += blockDim.x) {
+        const int y = i / NL, l = i - y * NL;   // l fastest: neighbouring columns are adjacent in memory
+        const int kx = cg * G + (l % G);
+        T2 z = mk2<T2, T>(0, 0);
+        if (kx <= half) {
+            const int kxm = (Sw - kx) % Sw;
+            if (l < G) z = zp[(size_t)y * Sw + kx];
+            else if (kxm != kx) z = zp[(size_t)y * Sw + kxm];
+        }
+        buf0[(size_t)l * Sh + y] = z;
+    }
+    __syncthreads();
+    T2* f = fft_lines<T2, NL>(buf0, buf1, tw, plan, NL, false);
+    // unpack A = FFT(a), B = FFT(b) from Z = FFT(a + i b); R = A conj(B) / max(|A conj(B)|, clamp)
+    for (int i = threadIdx.x; i < G * Sh; i += blockDim.x) {
+        const int l = i / Sh, ky = i - l * Sh;
+        const int kx = cg * G + l;
+        if (kx > half) continue;
+        const int kxm = (Sw - kx) % Sw;
+        const int kym = (Sh - ky) % Sh;
+        const bool self = (kxm == kx);
+        if (self && ky > kym) continue;         // the partner (kym, kx) lives in the same line: handle each pair once
+        T2* l1 = f + (size_t)l * Sh;
+        T2* l2 = self ? l1 : f + (size_t)(G + l) * Sh;
+        const T2 z1 = l1[ky], z2 = l2[kym];
+        const T ax = (T)0.5 * (z1.x + z2.x), ay = (T)0.5 * (z1.y - z2.y);
+        const T bx = (T)0.5 * (z1.y + z2.y), by = (T)-0.5 * (z1.x - z2.x);
+        T px = ax * bx + ay * by, py = ay * bx - ax * by;
+        const T mag = sqrt(px * px + py * py);
+        const T den = mag > (T)kClamp ? mag : (T)kClamp;
+        px /= den;
+        py /= den;
+        if (self && ky == kym) py = 0;          // self-conjugate bin: exactly real
+        l1[ky] = mk2<T2, T>(px, py);
+        l2[kym] = mk2<T2, T>(px, -py);
+        rp[(size_t)ky * Sw + kx] = mk2<T2, T>(px, py);
+        rp[(size_t)kym * Sw + kxm] = mk2<T2, T>(px, -py);
+    }
+    __syncthreads();
+    T2* other = (f == buf0) ? buf1 : buf0;
+    T2* y = fft_lines<T2, NL>(f, other, tw, plan, NL, true);
+    for (int i = threadIdx.x; i < NL * Sh; i += blockDim.x) {
+        const int yy = i / NL, l = i - yy * NL;
+        const int kx = cg * G + (l % G);
+        if (kx > half) continue;
+        const int kxm = (Sw - kx) % Sw;
+        if (l < G) zp[(size_t)yy * Sw + kx] = y[(size_t)l * Sh + yy];
+        else if (kxm != kx) zp[(size_t)yy * Sw + kxm] = y[(size_t)l * Sh + yy];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K3
+template <typename V>
+__device__ __forceinline__ void best_update(V& bv, int& bi, V v, int i) {
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+}
+
+template <typename T, int LB>
+__global__ void __launch_bounds__(256) rows_inv_argmax_kernel(int Sh, int Sw, int lpb, int nrb,
+                                                              const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
+                                                              const typename Vec2<T>::type* __restrict__ Y,
+                                                              CtaBest* __restrict__ best) {
+    using T2 = typename Vec2<T>::type;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    T2* buf0 = reinterpret_cast<T2*>(smem_raw);
+    T2* buf1 = buf0 + (size_t)lpb * Sw;
+    T2* tw = buf1 + (size_t)lpb * Sw;
+    const int p = blockIdx.x / nrb, rb = blockIdx.x - p * nrb;
+    const int l0 = rb * lpb;                                 // first packed line of this block
+    const T2* yp = Y + (size_t)p * Sh * Sw;
+    for (int i = threadIdx.x; i < Sw; i += blockDim.x) tw[i] = tw_g[i];
+    for (int i = threadIdx.x; i < lpb * Sw; i += blockDim.x) {
+        const int l = i / Sw, x = i - l * Sw;
+        const int y1 = 2 * (l0 + l), y2 = y1 + 1;
+        T2 v = mk2<T2, T>(0, 0);
+        if (y1 < Sh) {
+            const T2 r1 = yp[(size_t)y1 * Sw + x];
+            v = r1;
+            if (y2 < Sh) {                                   // + i * row y2
+                const T2 r2 = yp[(size_t)y2 * Sw + x];
+                v.x -= r2.y;
+                v.y += r2.x;
+            }
+        }
+        buf0[i] = v;
+    }
+    __syncthreads();
+    const T2* res = fft_lines<T2, LB>(buf0, buf1, tw, plan, lpb, true);
+    T bv = (T)-1;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < lpb * Sw; i += blockDim.x) {
+        const int l = i / Sw, x = i - l * Sw;
+        const int y1 = 2 * (l0 + l), y2 = y1 + 1;
+        if (y1 < Sh) best_update<T>(bv, bi, fabs(res[i].x), y1 * Sw + x);
+        if (y2 < Sh) best_update<T>(bv, bi, fabs(res[i].y), y2 * Sw + x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const T ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        best_update<T>(bv, bi, ov, oi);
+    }
+    __shared__ double sv[8];
+    __shared__ int si[8];
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = (double)bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = (double)bv;
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best_update<double>(b, bi, sv[w], si[w]);
+        best[(size_t)p * nrb + rb].val = b / ((double)Sh * (double)Sw);
+        best[(size_t)p * nrb + rb].idx = bi;
+    }
+}
+
+// one warp per pair: global first-maximum and the best value found by any OTHER block
+__global__ void __launch_bounds__(32) peak_final_kernel(const CtaBest* __restrict__ best, int nrb, int Sw,
+                                                        const int* __restrict__ nonzero, PeakOut* out) {
+    const int p = blockIdx.x;
+    if (nonzero[p] != 3) {                       // a strip is identically zero: cc == 0 everywhere, first index wins
+        if (threadIdx.x == 0) {
+            out[p].coarse_y = out[p].coarse_x = 0;
+            out[p].peak = out[p].runner_up = out[p].fine_peak = 0.f;
+            out[p].fine_y = out[p].fine_x = -1;
+        }
+        return;
+    }
+    double bv = -1.0;
+    int bi = 0x7fffffff, bb = -1;
+    for (int i = threadIdx.x; i < nrb; i += 32) {
+        const CtaBest c = best[(size_t)p * nrb + i];
+        if (c.val > bv || (c.val == bv && c.idx < bi)) { bv = c.val; bi = c.idx; bb = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int ob = __shfl_xor_sync(0xffffffffu, bb, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bb = ob; }
+    }
+    double ru = 0.0;
+    for (int i = threadIdx.x; i < nrb; i += 32)
+        if (i != bb) ru = fmax(ru, best[(size_t)p * nrb + i].val);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ru = fmax(ru, __shfl_xor_sync(0xffffffffu, ru, o));
+    if (threadIdx.x == 0) {
+        out[p].coarse_y = bi / Sw;
+        out[p].coarse_x = bi - (bi / Sw) * Sw;
+        out[p].peak = (float)bv;
+        out[p].runner_up = (float)ru;
+        out[p].fine_y = out[p].fine_x = -1;
+        out[p].fine_peak = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K4
+// Twiddles of skimage's _upsampled_dft: exp(-2 pi i (u - off) fftfreq(n, uf)[x]) with
+// off = dftshift - shift*uf; (u - off) and n*uf*fftfreq are integers, so the phase is reduced
+// exactly in integer arithmetic before sincospi.
+template <typename T>
+__global__ void __launch_bounds__(256) updft_twiddle_kernel(const PeakOut* __restrict__ peaks, int Sh, int Sw, int uf, int rs,
+                                                            int dftshift, typename Vec2<T>::type* __restrict__ Ex,
+                                                            typename Vec2<T>::type* __restrict__ Ey) {
+    using T2 = typename Vec2<T>::type;
+    const int p = blockIdx.y;
+    const PeakOut pk = peaks[p];
+    const int cy = pk.coarse_y > Sh / 2 ? pk.coarse_y - Sh : pk.coarse_y;     // shift[shift > fix(n/2)] -= n
+    const int cx = pk.coarse_x > Sw / 2 ? pk.coarse_x - Sw : pk.coarse_x;
+    const int total = rs * (Sw + Sh);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const bool isx = i < rs * Sw;
+        const int n = isx ? Sw : Sh;
+        const int ii = isx ? i : i - rs * Sw;
+        const int u = ii / n, k = ii - u * n;
+        const long long m = (long long)u - dftshift + (long long)(isx ? cx : cy) * uf;
+        const int sk = (k < (n + 1) / 2) ? k : k - n;                        // n * fftfreq(n)[k]
+        const long long den = (long long)n * uf;
+        long long num = (m * sk) % den;
+        if (num < 0) num += den;
+        double s, c;
+        sincospi(-2.0 * (double)num / (double)den, &s, &c);
+        T2 w = mk2<T2, T>((T)c, (T)s);
+        if (isx) Ex[((size_t)p * rs + u) * Sw + k] = w;
+        else Ey[((size_t)p * rs + u) * Sh + k] = w;
+    }
+}
+
+// T[u][y] = sum_x conj(R[y][x]) Ex[u][x]; one warp per row, u tiled by 16.
+template <typename T>
+__global__ void __launch_bounds__(256) updft_rows_kernel(int Sh, int Sw, int rs, int rows_per_block, int nrb,
+                                                         const typename Vec2<T>::type* __restrict__ Rbuf,
+                                                         const typename Vec2<T>::type* __restrict__ Ex,
+                                                         typename Vec2<T>::type* __restrict__ Tm) {
+    using T2 = typename Vec2<T>::type;
+    constexpr int UT = 16;
+    const int p = blockIdx.x / nrb, rb = blockIdx.x - p * nrb;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const T2* rp = Rbuf + (size_t)p * Sh * Sw;
+    const T2* ex = Ex + (size_t)p * rs * Sw;
+    T2* tp = Tm + (size_t)p * rs * Sh;
+    for (int yl = warp; yl < rows_per_block; yl += (blockDim.x >> 5)) {
+        const int y = rb * rows_per_block + yl;
+        if (y >= Sh) break;
+        for (int u0 = 0; u0 < rs; u0 += UT) {
+            T2 acc[UT];
+#pragma unroll
+            for (int u = 0; u < UT; ++u) acc[u].x = acc[u].y = 0;
+            for (int x = lane; x < Sw; x += 32) {
+                T2 r = rp[(size_t)y * Sw + x];
+                r.y = -r.y;
+#pragma unroll
+                for (int u = 0; u < UT; ++u)
+                    if (u0 + u < rs) cfma(acc[u], r, ex[(size_t)(u0 + u) * Sw + x]);
+            }
+#pragma unroll
+            for (int u = 0; u < UT; ++u) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    acc[u].x += __shfl_xor_sync(0xffffffffu, acc[u].x, o);
+                    acc[u].y += __shfl_xor_sync(0xffffffffu, acc[u].y, o);
+                }
+                if (lane == 0 && u0 + u < rs) tp[(size_t)(u0 + u) * Sh + y] = acc[u];
+            }
+        }
+    }
+}
+
+// out[v][u] = sum_y Ey[v][y] T[u][y]; |conj(out)| argmax, first maximum in C order. One block per pair.
+template <typename T>
+__global__ void __launch_bounds__(256) updft_final_kernel(int Sh, int rs, const typename Vec2<T>::type* __restrict__ Tm,
+                                                          const typename Vec2<T>::type* __restrict__ Ey, float inv_n,
+                                                          const int* __restrict__ nonzero, PeakOut* __restrict__ peaks) {
+    using T2 = typename Vec2<T>::type;
+    const int p = blockIdx.x;
+    if (nonzero[p] != 3) {                       // zero cross-power: the upsampled window is all zero -> index 0
+        if (threadIdx.x == 0) { peaks[p].fine_y = peaks[p].fine_x = 0; peaks[p].fine_peak = 0.f; }
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const T2* tp = Tm + (size_t)p * rs * Sh;
+    const T2* ey = Ey + (size_t)p * rs * Sh;
+    T bv = (T)-1;
+    int bi = 0x7fffffff;
+    for (int o = warp; o < rs * rs; o += nw) {
+        const int v = o / rs, u = o - v * rs;
+        T2 acc = mk2<T2, T>(0, 0);
+        for (int y = lane; y < Sh; y += 32) cfma(acc, ey[(size_t)v * Sh + y], tp[(size_t)u * Sh + y]);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+        }
+        best_update<T>(bv, bi, acc.x * acc.x + acc.y * acc.y, o);      // |.|^2 is monotone in |.|
+    }
+    __shared__ double sv[8];
+    __shared__ int si[8];
+    if (lane == 0) { sv[warp] = (double)bv; si[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = (double)bv;
+        for (int w = 1; w < nw; ++w) best_update<double>(b, bi, sv[w], si[w]);
+        peaks[p].fine_y = bi / rs;
+        peaks[p].fine_x = bi - (bi / rs) * rs;
+        peaks[p].fine_peak = (float)(sqrt(b) * (double)inv_n);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+
+FftPlan make_plan(int n) {
+    // prime factors, twos merged into fours, largest radix first (the order is free for Stockham)
+    std::vector<int> f;
+    int m = n, twos = 0;
+    while (m % 2 == 0) { ++twos; m /= 2; }
+    for (int p = 3; (long long)p * p <= m; p += 2)
+        while (m % p == 0) { f.push_back(p); m /= p; }
+    if (m > 1) f.push_back(m);
+    for (; twos >= 2; twos -= 2) f.push_back(4);
+    if (twos) f.push_back(2);
+    std::sort(f.begin(), f.end(), [](int a, int b) { return a > b; });
+    FftPlan pl;
+    pl.n = n;
+    pl.nfac = 0;
+    for (int v : f) pl.fac[pl.nfac++] = v;
+    return pl;
+}
+
+template <typename T>
+int get_twiddles(sb_ctx* ctx, int n, const typename Vec2<T>::type** out) {
+    using T2 = typename Vec2<T>::type;
+    const uint64_t key = ((uint64_t)n << 1) | (sizeof(T) == 8 ? 1 : 0);
+    auto it = ctx->twiddle_cache.find(key);
+    if (it == ctx->twiddle_cache.end()) {
+        std::vector<T2> h(n);
+        const long double tau = 6.283185307179586476925286766559L;
+        for (int m = 0; m < n; ++m) {
+            const long double a = -tau * (long double)m / (long double)n;
+            h[m].x = (T)cosl(a);
+            h[m].y = (T)sinl(a);
+        }
+        DevBuf b;
+        int rc = sb_reserve(ctx, b, (size_t)n * sizeof(T2));
+        if (rc) return rc;
+        SB_CUDA(ctx, cudaMemcpy(b.p, h.data(), (size_t)n * sizeof(T2), cudaMemcpyHostToDevice));
+        it = ctx->twiddle_cache.emplace(key, b).first;
+    }
+    *out = reinterpret_cast<const T2*>(it->second.p);
+    return SB_OK;
+}
+
+struct GroupGeom {          // strips of one direction
+    int Sh, Sw;
+    int a_y0, a_x0, b_y0, b_x0;
+};
+
+// lines per block so that 2 buffers + the twiddle table fit comfortably in shared memory
+int pick_lines(int n, size_t elem, int lb, size_t budget) {
+    if ((size_t)n * elem * 3 > budget) return 0;
+    int l = (int)((budget - (size_t)n * elem) / (2 * (size_t)n * elem));
+    l = std::min(l, 16);
+    l = l / lb * lb;
+    return l;
+}
+
+template <typename T>
+int run_group(sb_ctx* ctx, cudaStream_t st, const std::vector<PairDesc>& pairs, const GroupGeom& g, int tile_w,
+              const int2* d_mm, int uf, std::vector<PeakOut>& results) {
+    using T2 = typename Vec2<T>::type;
+    const int n = (int)pairs.size();
+    const int Sh = g.Sh, Sw = g.Sw;
+    const size_t strip = (size_t)Sh * Sw;
+    const FftPlan plan_x = make_plan(Sw), plan_y = make_plan(Sh);
+    const T2 *tw_x = nullptr, *tw_y = nullptr;
+    int rc = get_twiddles<T>(ctx, Sw, &tw_x);
+    if (rc) return rc;
+    rc = get_twiddles<T>(ctx, Sh, &tw_y);
+    if (rc) return rc;
+
+    const int rs = (3 * uf + 1) / 2;            // ceil(1.5 * uf)
+    const int dftshift = rs / 2;                // fix(rs / 2)
+
+    // sub-batches sized so that Z + R of a sub-batch stay L2 resident
+    const size_t per_pair = 2 * strip * sizeof(T2);
+    int B = (int)std::max<size_t>(1, (size_t)(64u << 20) / per_pair);
+    B = std::min(B, n);
+
+    // launch geometry
+    constexpr size_t kBudget = 96 * 1024;
+    int lbx = 4, lpbx = pick_lines(Sw, sizeof(T2), 4, kBudget);
+    if (lpbx < 4) { lbx = 1; lpbx = pick_lines(Sw, sizeof(T2), 1, 200 * 1024); }
+    if (lpbx < 1) return sb_fail(ctx, SB_ERR_UNSUPPORTED, "strip width %d too large for the shared-memory FFT", Sw);
+    const size_t smem_x = (size_t)(2 * lpbx + 1) * Sw * sizeof(T2);
+    int G = 2;
+    size_t smem_y = (size_t)(2 * 2 * G + 1) * Sh * sizeof(T2);
+    if (smem_y > 200 * 1024) { G = 1; smem_y = (size_t)(2 * 2 * G + 1) * Sh * sizeof(T2); }
+    if (smem_y > 227 * 1024) return sb_fail(ctx, SB_ERR_UNSUPPORTED, "strip height %d too large for the shared-memory FFT", Sh);
+    const int nrb_fwd = (Sh + lpbx - 1) / lpbx;
+    const int nlines_inv = (Sh + 1) / 2;
+    const int nrb_inv = (nlines_inv + lpbx - 1) / lpbx;
+    const int ncg = (Sw / 2 + 1 + G - 1) / G;
+    const int rows_per_block = 32;
+    const int nrb_up = (Sh + rows_per_block - 1) / rows_per_block;
+
+    // workspace: Z | R | Ex | Ey | T | best | peaks | pair descriptors
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += round_up64((int64_t)bytes, 256); return o; };
+    const size_t o_Z = carve((size_t)B * strip * sizeof(T2));
+    const size_t o_R = carve((size_t)B * strip * sizeof(T2));
+    const size_t o_Ex = carve((size_t)B * rs * Sw * sizeof(T2));
+    const size_t o_Ey = carve((size_t)B * rs * Sh * sizeof(T2));
+    const size_t o_T = carve((size_t)B * rs * Sh * sizeof(T2));
+    const size_t o_best = carve((size_t)B * nrb_inv * sizeof(CtaBest));
+    const size_t o_peaks = carve((size_t)n * sizeof(PeakOut));
+    const size_t o_pairs = carve((size_t)n * sizeof(PairDesc));
+    const size_t o_nz = carve((size_t)n * sizeof(int));
+    rc = sb_reserve(ctx, ctx->reg_work, off);
+    if (rc) return rc;
+    uint8_t* w = (uint8_t*)ctx->reg_work.p;
+    T2* Z = (T2*)(w + o_Z);
+    T2* Rb = (T2*)(w + o_R);
+    T2* Ex = (T2*)(w + o_Ex);
+    T2* Ey = (T2*)(w + o_Ey);
+    T2* Tm = (T2*)(w + o_T);
+    CtaBest* best = (CtaBest*)(w + o_best);
+    PeakOut* peaks = (PeakOut*)(w + o_peaks);
+    PairDesc* d_pairs = (PairDesc*)(w + o_pairs);
+    int* d_nz = (int*)(w + o_nz);
+    SB_CUDA(ctx, cudaMemsetAsync(d_nz, 0, (size_t)n * sizeof(int), st));
+    SB_CUDA(ctx, cudaMemcpyAsync(d_pairs, pairs.data(), (size_t)n * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+
+    auto k1 = lbx == 4 ? rows_fwd_kernel<T, 4> : rows_fwd_kernel<T, 1>;
+    auto k3 = lbx == 4 ? rows_inv_argmax_kernel<T, 4> : rows_inv_argmax_kernel<T, 1>;
+    auto k2 = G == 2 ? cols_xpower_kernel<T, 2> : cols_xpower_kernel<T, 1>;
+    SB_CUDA(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+    SB_CUDA(ctx, cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+    SB_CUDA(ctx, cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_y));
+
+    const float inv_n = 1.0f / ((float)Sh * (float)Sw);
+    for (int p0 = 0; p0 < n; p0 += B) {
+        const int nb = std::min(B, n - p0);
+        k1<<<nb * nrb_fwd, 256, smem_x, st>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, tw_x, plan_x, Z, d_nz + p0);
+        k2<<<nb * ncg, 256, smem_y, st>>>(Sh, Sw, ncg, tw_y, plan_y, Z, Rb);
+        k3<<<nb * nrb_inv, 256, smem_x, st>>>(Sh, Sw, lpbx, nrb_inv, tw_x, plan_x, Z, best);
+        peak_final_kernel<<<nb, 32, 0, st>>>(best, nrb_inv, Sw, d_nz + p0, peaks + p0);
+        ctx->launches += 4;
+        if (uf > 1) {
+            updft_twiddle_kernel<T><<<dim3(8, nb), 256, 0, st>>>(peaks + p0, Sh, Sw, uf, rs, dftshift, Ex, Ey);
+            updft_rows_kernel<T><<<nb * nrb_up, 256, 0, st>>>(Sh, Sw, rs, rows_per_block, nrb_up, Rb, Ex, Tm);
+            updft_final_kernel<T><<<nb, 256, 0, st>>>(Sh, rs, Tm, Ey, inv_n, d_nz + p0, peaks + p0);
+            ctx->launches += 3;
+        }
+        SB_CUDA(ctx, cudaGetLastError());
+    }
+    results.resize(n);
+    SB_CUDA(ctx, cudaMemcpyAsync(results.data(), peaks, (size_t)n * sizeof(PeakOut), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(ctx, cudaStreamSynchronize(st));
+    return SB_OK;
+}
+
+// skimage's float64 shift from integer indices, then the reference's round() (half-to-even)
+void finish_pair(const PeakOut& pk, const GroupGeom& g, int dir, int uf, sb_pair_result* r) {
+    const int shape[2] = {g.Sh, g.Sw};
+    const int coarse[2] = {pk.coarse_y, pk.coarse_x};
+    const int fine[2] = {pk.fine_y, pk.fine_x};
+    double shift[2];
+    for (int d = 0; d < 2; ++d) {
+        double s = (double)coarse[d];
+        const double mid = std::trunc((double)shape[d] / 2.0);            // np.fix(axis_size / 2)
+        if (s > mid) s -= (double)shape[d];
+        if (uf > 1) {
+            const double ufd = (double)uf;
+            s = std::nearbyint(s * ufd) / ufd;                            // np.round(shift * uf) / uf
+            const double dftshift = std::trunc(std::ceil(ufd * 1.5) / 2.0);
+            s += ((double)fine[d] - dftshift) / ufd;
+        }
+        if (shape[d] == 1) s = 0.0;
+        shift[d] = s;
+    }
+    r->shift[0] = shift[0];
+    r->shift[1] = shift[1];
+    // Python round(float) == round-half-to-even of the binary value == nearbyint in the default mode
+    if (dir == SB_DIR_HORIZONTAL) {
+        r->dy = (int32_t)std::nearbyint(shift[0]);
+        r->dx = (int32_t)std::nearbyint(shift[1] - (double)g.Sw);
+    } else {
+        r->dy = (int32_t)std::nearbyint(shift[0] - (double)g.Sh);
+        r->dx = (int32_t)std::nearbyint(shift[1]);
+    }
+    r->coarse[0] = pk.coarse_y;
+    r->coarse[1] = pk.coarse_x;
+    r->fine[0] = uf > 1 ? pk.fine_y : -1;
+    r->fine[1] = uf > 1 ? pk.fine_x : -1;
+    r->peak = pk.peak;
+    r->runner_up = pk.runner_up;
+    r->fine_peak = pk.fine_peak;
+}
+
+// upload (host) or adopt (device) the unique tiles of a job and compute their min/max
+struct TileSet {
+    std::map<const void*, int> index;       // caller pointer -> tile index
+    std::vector<const uint16_t*> dev;       // device address per tile index
+};
+
+int prepare_tiles(sb_ctx* ctx, cudaStream_t st, const std::vector<const void*>& ptrs, int H, int W, int mem, TileSet& ts,
+                  int2** d_mm_out, std::vector<int2>* h_mm) {
+    for (const void* p : ptrs) {
+        if (!p) return sb_fail(ctx, SB_ERR_INVALID, "NULL tile pointer");
+        if (ts.index.emplace(p, (int)ts.index.size()).second) ts.dev.push_back(nullptr);
+    }
+    const int nt = (int)ts.index.size();
+    const size_t tile_bytes = (size_t)H * W * 2;
+    if (mem == SB_MEM_HOST) {
+        int rc = sb_reserve(ctx, ctx->reg_tiles, tile_bytes * nt);
+        if (rc) return rc;
+        for (auto& kv : ts.index) {
+            uint8_t* d = (uint8_t*)ctx->reg_tiles.p + tile_bytes * kv.second;
+            SB_CUDA(ctx, cudaMemcpyAsync(d, kv.first, tile_bytes, cudaMemcpyHostToDevice, st));
+            ts.dev[kv.second] = (const uint16_t*)d;
+        }
+    } else {
+        for (auto& kv : ts.index) ts.dev[kv.second] = (const uint16_t*)kv.first;
+    }
+    // device table of tile pointers + min/max
+    const size_t meta = round_up64((size_t)nt * sizeof(void*), 256) + (size_t)nt * sizeof(int2);
+    int rc = sb_reserve(ctx, ctx->reg_meta, meta);
+    if (rc) return rc;
+    SB_CUDA(ctx, cudaMemcpyAsync(ctx->reg_meta.p, ts.dev.data(), (size_t)nt * sizeof(void*), cudaMemcpyHostToDevice, st));
+    int2* d_mm = (int2*)((uint8_t*)ctx->reg_meta.p + round_up64((size_t)nt * sizeof(void*), 256));
+    minmax_init_kernel<<<(nt + 255) / 256, 256, 0, st>>>(d_mm, nt);
+    const int bpt = std::max(1, std::min(64, (ctx->sm_count * 8 + nt - 1) / nt));
+    tile_minmax_kernel<<<dim3(bpt, nt), 256, 0, st>>>((const uint16_t* const*)ctx->reg_meta.p, (int64_t)H * W, d_mm);
+    ctx->launches += 2;
+    SB_CUDA(ctx, cudaGetLastError());
+    if (h_mm) {
+        h_mm->resize(nt);
+        SB_CUDA(ctx, cudaMemcpyAsync(h_mm->data(), d_mm, (size_t)nt * sizeof(int2), cudaMemcpyDeviceToHost, st));
+    }
+    *d_mm_out = d_mm;
+    return SB_OK;
+}
+
+}  // namespace
+
+int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out) {
+    SB_CHECK(ctx, job && out, "job/out is NULL");
+    SB_CHECK(ctx, job->dtype == SB_U16, "only uint16 pixels are implemented");
+    SB_CHECK(ctx, job->n_pairs >= 0 && (job->n_pairs == 0 || job->pairs), "bad pair list");
+    SB_CHECK(ctx, job->upsample_factor >= 1 && job->upsample_factor <= 100, "upsample_factor %d out of range [1, 100]",
+             job->upsample_factor);
+    SB_CHECK(ctx, job->precision >= SB_PREC_F32 && job->precision <= SB_PREC_AUTO, "unknown precision %d", job->precision);
+    const int H = job->tile_h, W = job->tile_w, n = job->n_pairs;
+    SB_CHECK(ctx, H > 0 && W > 0, "bad tile shape");
+    if (n == 0) return SB_OK;
+    Lane* lane = sb_lane(ctx, 0);
+    cudaStream_t st = lane->stream;
+
+    std::vector<const void*> ptrs;
+    for (int i = 0; i < n; ++i) {
+        SB_CHECK(ctx, job->pairs[i].dir == SB_DIR_HORIZONTAL || job->pairs[i].dir == SB_DIR_VERTICAL, "pair %d: bad dir", i);
+        ptrs.push_back(job->pairs[i].ref);
+        ptrs.push_back(job->pairs[i].mov);
+    }
+    TileSet ts;
+    int2* d_mm = nullptr;
+    std::vector<int2> h_mm;
+    int rc = prepare_tiles(ctx, st, ptrs, H, W, job->mem, ts, &d_mm, &h_mm);
+    if (rc) return rc;
+
+    for (int dir = 0; dir < 2; ++dir) {
+        std::vector<int> ids;
+        for (int i = 0; i < n; ++i)
+            if (job->pairs[i].dir == dir) ids.push_back(i);
+        if (ids.empty()) continue;
+        GroupGeom g;
+        if (dir == SB_DIR_HORIZONTAL) {
+            // img_left[margin:-margin, -ov:], img_right[margin:-margin, :ov]   (:677-679)
+            const int margin = (int)((double)H * 0.25), ov = job->max_overlap_x;
+            SB_CHECK(ctx, margin >= 1 && H - 2 * margin >= 1, "tile height %d too small for the 25%% margin", H);
+            SB_CHECK(ctx, ov >= 1 && ov <= W, "max_overlap_x %d outside [1, %d]", ov, W);
+            g = {H - 2 * margin, ov, margin, W - ov, margin, 0};
+        } else {
+            // img_top[-ov:, margin:-margin], img_bot[:ov, margin:-margin]      (:700-702)
+            const int margin = (int)((double)W * 0.25), ov = job->max_overlap_y;
+            SB_CHECK(ctx, margin >= 1 && W - 2 * margin >= 1, "tile width %d too small for the 25%% margin", W);
+            SB_CHECK(ctx, ov >= 1 && ov <= H, "max_overlap_y %d outside [1, %d]", ov, H);
+            g = {ov, W - 2 * margin, H - ov, margin, 0, margin};
+        }
+        std::vector<PairDesc> pd(ids.size());
+        for (size_t k = 0; k < ids.size(); ++k) {
+            const sb_pair& sp = job->pairs[ids[k]];
+            const int ia = ts.index[sp.ref], ib = ts.index[sp.mov];
+            pd[k].a = ts.dev[ia] + (size_t)g.a_y0 * W + g.a_x0;
+            pd[k].b = ts.dev[ib] + (size_t)g.b_y0 * W + g.b_x0;
+            pd[k].a_tile = ia;
+            pd[k].b_tile = ib;
+        }
+        std::vector<PeakOut> res;
+        const int first_prec = job->precision == SB_PREC_F64 ? SB_PREC_F64 : SB_PREC_F32;
+        rc = first_prec == SB_PREC_F64 ? run_group<double>(ctx, st, pd, g, W, d_mm, job->upsample_factor, res)
+                                       : run_group<float>(ctx, st, pd, g, W, d_mm, job->upsample_factor, res);
+        if (rc) return rc;
+        std::vector<int> prec(ids.size(), first_prec);
+        if (job->precision == SB_PREC_AUTO) {
+            // A peak that does not stand clear of the correlation noise floor (rms 1/sqrt(N), expected
+            // maximum ~ sqrt(2 ln N / N)) is an argmax among near-equal values: redo those in float64,
+            // the arithmetic the reference uses.
+            const double N = (double)g.Sh * g.Sw;
+            const double floor_max = std::sqrt(2.0 * std::log(N) / N);
+            std::vector<PairDesc> redo;
+            std::vector<int> redo_k;
+            for (size_t k = 0; k < ids.size(); ++k)
+                if (!(res[k].peak > 4.0 * floor_max) || !(res[k].peak > 1.5f * res[k].runner_up)) {
+                    redo.push_back(pd[k]);
+                    redo_k.push_back((int)k);
+                }
+            if (!redo.empty()) {
+                std::vector<PeakOut> res2;
+                rc = run_group<double>(ctx, st, redo, g, W, d_mm, job->upsample_factor, res2);
+                if (rc) return rc;
+                for (size_t j = 0; j < redo_k.size(); ++j) {
+                    res[redo_k[j]] = res2[j];
+                    prec[redo_k[j]] = SB_PREC_F64;
+                }
+            }
+        }
+        for (size_t k = 0; k < ids.size(); ++k) {
+            sb_pair_result* r = &out[ids[k]];
+            memset(r, 0, sizeof(*r));
+            finish_pair(res[k], g, dir, job->upsample_factor, r);
+            const sb_pair& sp = job->pairs[ids[k]];
+            const int2 ma = h_mm[ts.index[sp.ref]], mb = h_mm[ts.index[sp.mov]];
+            r->ref_min = ma.x; r->ref_max = ma.y; r->mov_min = mb.x; r->mov_max = mb.y;
+            r->precision = prec[k];
+        }
+    }
+    return SB_OK;
+}
+
+int sb_normalize_impl(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int dtype, int mem) {
+    SB_CHECK(ctx, dtype == SB_U16, "only uint16 pixels are implemented");
+    SB_CHECK(ctx, tiles && out && n_tiles > 0 && tile_h > 0 && tile_w > 0, "bad arguments");
+    Lane* lane = sb_lane(ctx, 0);
+    cudaStream_t st = lane->stream;
+    const size_t px = (size_t)tile_h * tile_w;
+    std::vector<const void*> ptrs;
+    for (int i = 0; i < n_tiles; ++i) ptrs.push_back((const uint8_t*)tiles + i * px * 2);
+    TileSet ts;
+    int2* d_mm = nullptr;
+    int rc = prepare_tiles(ctx, st, ptrs, tile_h, tile_w, mem, ts, &d_mm, nullptr);
+    if (rc) return rc;
+    // tiles were given contiguously, so tile i has index i and (host case) sits at reg_tiles + i * px
+    const uint16_t* d_in = mem == SB_MEM_HOST ? (const uint16_t*)ctx->reg_tiles.p : (const uint16_t*)tiles;
+    uint16_t* d_out = (uint16_t*)out;
+    if (mem == SB_MEM_HOST) {
+        rc = sb_reserve(ctx, lane->canvas, px * 2 * n_tiles);
+        if (rc) return rc;
+        d_out = (uint16_t*)lane->canvas.p;
+    }
+    normalize_kernel<<<dim3(std::max(1, ctx->sm_count * 4 / n_tiles), n_tiles), 256, 0, st>>>(d_in, d_out, d_mm, (int64_t)px);
+    ctx->launches++;
+    SB_CUDA(ctx, cudaGetLastError());
+    if (mem == SB_MEM_HOST) SB_CUDA(ctx, cudaMemcpyAsync(out, d_out, px * 2 * n_tiles, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(ctx, cudaStreamSynchronize(st));
+    return SB_OK;
 }
