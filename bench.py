@@ -1,0 +1,428 @@
+#!/usr/bin/env python3
+"""bench.py -- registration + fusion of a synthetic 96-well plate (BASELINE.json configs[2], the
+configuration north_star's target is quoted on): 96 wells x 3x3 tiles x 2048^2 uint16 x 4 channels.
+
+One step = (a) all-pairs phase-correlation registration of every well on the registration channel
+(12 adjacent pairs / well, 1152 pairs) and (b) flatfield-corrected fusion of every well's 4 channels
+into its (1, 4, 1, 5734, 5734) canvas in the reference's paste semantics, coordinate placement.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # own arm (CUDA, libstitchb200)
+    python bench.py --impl reference ...                             # CPU arm: the oracle port of the reference
+
+Prints ONE JSON line (rank 0).  `value` = canvas Mpx written per second over the whole job with the
+plate resident in HBM; `e2e` = the same through the public host-buffer API (pinned host tiles in,
+host canvas out, copies inside the timed region).  Multi-GPU: one process per GPU, every rank owns a
+whole plate (weak scaling, no data-path collective); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fused Mpx/s written (registration + fusion step)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--wells", type=int, default=96)
+    ap.add_argument("--tile", type=int, default=2048)
+    ap.add_argument("--channels", type=int, default=4)
+    ap.add_argument("--grid", type=int, default=3)
+    ap.add_argument("--blend", choices=["paste", "linear", "feather"], default="paste")
+    ap.add_argument("--no-flatfield", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the host-buffer leg (default min(steps, 2))")
+    ap.add_argument("--host-wells", type=int, default=6, help="distinct wells kept in pinned host memory for e2e")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-wells", type=int, default=1)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm (oracle)
+def cpu_sample(spec, plate_tiles_host, flat_host, n_wells, use_flat, workers=None):
+    """Time the oracle (NumPy/SciPy restatement of the reference) on `n_wells` wells held in RAM.
+
+    Returns (pairs, px, seconds_registration, seconds_fusion).  File decode is excluded, as in the GPU
+    arms.  This is the one place outside tests/ where oracle/ is executed: as the measured CPU arm.
+    """
+    from oracle import stitch_ref as sr
+    ovx, ovy = spec.strip_overlaps()
+    xs, ys = spec.stage_positions()
+    names = [f"ch{c}" for c in range(spec.channels)]
+    st = sr.RegionState(tile_h=spec.tile_h, tile_w=spec.tile_w, pixel_size_um=spec.pixel_size_um,
+                        pixel_binning=spec.pixel_binning, monochrome_channels=names, channel_names=names,
+                        num_z=spec.num_z, use_registration=False, apply_flatfield=use_flat,
+                        flatfields={c: flat_host[c] for c in range(spec.channels)} if use_flat else {})
+    from image_stitcher_b200 import geometry as geo
+    t_reg = t_fuse = 0.0
+    pairs = px = 0
+    for w in range(n_wells):
+        tiles = plate_tiles_host[w]                       # [rows, cols, C, Z, H, W] uint16
+        t0 = time.perf_counter()
+        for kind, (r0, c0), (r1, c1) in geo.grid_pairs(spec.rows, spec.cols):
+            a, b = tiles[r0, c0, spec.reg_channel, 0], tiles[r1, c1, spec.reg_channel, 0]
+            if kind == "h":
+                sr.calculate_horizontal_shift(a, b, ovx)
+            else:
+                sr.calculate_vertical_shift(a, b, ovy)
+            pairs += 1
+        t_reg += time.perf_counter() - t0
+        recs = []
+        fovs = sorted(range(spec.rows * spec.cols), key=lambda f: str(f))
+        for fov in fovs:
+            r, c = divmod(fov, spec.cols)
+            for z in range(spec.num_z):
+                for ch in range(spec.channels):
+                    recs.append(sr.TileRec(x_mm=xs[c], y_mm=ys[r], z_level=z, channel=names[ch],
+                                           pixels=tiles[r, c, ch, z], fov=fov))
+        t0 = time.perf_counter()
+        canvas = sr.stitch_region(st, recs)
+        t_fuse += time.perf_counter() - t0
+        px += canvas.size
+    return pairs, px, t_reg, t_fuse
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python
+    reference itself cannot travel to the GPU box and its third-party stack is not installed)."""
+    if rank != 0:
+        return
+    from image_stitcher_b200.plate import PlateSpec
+    from oracle import synth
+    spec = PlateSpec(wells=args.wells, rows=args.grid, cols=args.grid, tile_h=args.tile, tile_w=args.tile,
+                     channels=args.channels)
+    use_flat = not args.no_flatfield
+    n = args.cpu_sample_wells
+    rng = np.random.default_rng(0)
+    # bounded sample: n wells generated on the host with the oracle's own generator
+    tiles = np.empty((n, spec.rows, spec.cols, spec.channels, 1, spec.tile_h, spec.tile_w), np.uint16)
+    for w in range(n):
+        st, recs, _ = synth.make_region(spec.rows, spec.cols, spec.tile_h, spec.tile_w, seed=w, jitter=3)
+        for t in recs:
+            r, c = divmod(t.fov, spec.cols)
+            for ch in range(spec.channels):
+                tiles[w, r, c, ch, 0] = t.pixels if ch == spec.reg_channel else (t.pixels // (ch + 2))
+    flat = np.stack([synth.vignette(spec.tile_h, spec.tile_w, 0.35, (0.04 * (c + 1), -0.03 * (c + 1)))
+                     for c in range(spec.channels)])
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(spec, tiles, flat, 1, use_flat)
+    t0 = time.perf_counter()
+    pairs = px = 0
+    t_reg = t_fuse = 0.0
+    for _ in range(args.steps):
+        p, x, a, b = cpu_sample(spec, tiles, flat, n, use_flat)
+        pairs += p; px += x; t_reg += a; t_fuse += b
+    total = time.perf_counter() - t0
+    val = px / 1e6 / (t_reg + t_fuse)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpx/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16 (f64 registration)",
+        "data": "synthetic",
+        "config": {"workload": workload_name(spec, use_flat, args.blend), "sample": f"{n} well(s) per step"},
+        "tile_pairs_per_s": pairs / t_reg, "fusion_mpx_per_s": px / 1e6 / t_fuse,
+        "cpu_baseline": {"value": val, "unit": "Mpx/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{n} well(s) ({pairs // args.steps} pairs, {px // args.steps / 1e6:.0f} Mpx) per step; "
+                                   "NumPy/SciPy oracle port, scipy.fft default workers",
+                         "tile_pairs_per_s": pairs / t_reg, "fusion_mpx_per_s": px / 1e6 / t_fuse},
+        "e2e": {"value": val, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_name(spec, use_flat, blend):
+    return (f"{spec.wells}-well plate, {spec.rows}x{spec.cols} tiles/well, {spec.tile_h}x{spec.tile_w} uint16, "
+            f"{spec.channels} channels, all-pairs registration on one channel + coordinate-placed {blend} fusion, "
+            f"flatfield {'on' if use_flat else 'off'} (BASELINE.json configs[2])")
+
+
+# ------------------------------------------------------------------------------------------ CUDA arm
+def run_b200(args, rank, world, local_rank):
+    import torch
+    from image_stitcher_b200 import _ffi
+    from image_stitcher_b200.plate import FusePlan, PlateSpec, make_plate, well_fuse_tiles, well_pairs
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    spec = PlateSpec(wells=args.wells, rows=args.grid, cols=args.grid, tile_h=args.tile, tile_w=args.tile,
+                     channels=args.channels, seed=rank)
+    use_flat = not args.no_flatfield
+    blend = _ffi.BLEND_MODES[args.blend]
+    ctx = _ffi.Context(local_rank)
+    plate = make_plate(spec, device=f"cuda:{local_rank}", with_flat=True)
+    if use_flat:
+        for c in range(spec.channels):
+            ctx.set_flatfield(c, plate.flat[c], mem=_ffi.SB_MEM_DEVICE)
+    Wc, Hc = spec.canvas_size()
+    pitch = _ffi.canvas_pitch(Wc)
+    planes = spec.channels * spec.num_z
+    canvases = torch.empty((spec.wells, planes, Hc, pitch), dtype=torch.int16, device=f"cuda:{local_rank}")
+    ovx, ovy = spec.strip_overlaps()
+    # a real (non-default) stream: lane 0 launches on it and the timing events are recorded on it
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.synchronize()
+    ctx.set_lane_stream(0, stream.cuda_stream)
+
+    def dev_ptr(w):
+        return lambda r, c, ch, z: plate.pool[w, r, c, ch, z].data_ptr()
+
+    plans, all_pairs = [], []
+    for w in range(spec.wells):
+        plans.append(FusePlan(ctx, well_fuse_tiles(spec, dev_ptr(w)), (spec.tile_h, spec.tile_w),
+                              (spec.channels, spec.num_z, Hc, Wc), canvases[w], tile_mem=_ffi.SB_MEM_DEVICE,
+                              out_mem=_ffi.SB_MEM_DEVICE, apply_flatfield=use_flat, blend=blend, blend_ov=(ovx, ovy)))
+        all_pairs += well_pairs(spec, dev_ptr(w))[0]
+    n_pairs = len(all_pairs)
+    px_per_step = spec.wells * planes * Hc * Wc
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    reg_ms, fuse_ms = [], []
+    last_reg = None
+
+    def step(record):
+        nonlocal last_reg
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record(stream)
+        last_reg = ctx.register_pairs(all_pairs, (spec.tile_h, spec.tile_w), ovx, ovy, mem=_ffi.SB_MEM_DEVICE, lane=0)
+        e1.record(stream)
+        for p in plans:
+            p.run(0)
+        e2.record(stream)
+        if record is not None:
+            record.append((e0, e1, e2))
+
+    for _ in range(args.warmup):
+        step(None)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.kernel_launches
+    torch.cuda.synchronize()
+    t_start, t_end = ev(), ev()
+    recs = []
+    wall0 = time.perf_counter()
+    t_start.record(stream)
+    for _ in range(args.steps):
+        step(recs)
+    t_end.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop()
+    total_ms = t_start.elapsed_time(t_end)
+    reg_ms = [a.elapsed_time(b) for a, b, _ in recs]
+    fuse_ms = [b.elapsed_time(c) for _, b, c in recs]
+    if dist:
+        t = torch.tensor([total_ms, float(np.sum(reg_ms)), float(np.sum(fuse_ms))], device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, reg_sum, fuse_sum = (float(v) for v in t.tolist())
+        l = torch.tensor([launches], device=f"cuda:{local_rank}")
+        dist.all_reduce(l)
+        launches = int(l.item())
+    else:
+        reg_sum, fuse_sum = float(np.sum(reg_ms)), float(np.sum(fuse_ms))
+
+    # parity property at full size: registration recovers the known stage drift of every well
+    ok = 0
+    for w in range(spec.wells):
+        res = last_reg[w * (n_pairs // spec.wells):(w + 1) * (n_pairs // spec.wells)]
+        kinds = well_pairs(spec, lambda *a: 0)[1]
+        ok += all((r["dy"], r["dx"]) == plate.truth[w][k] for r, k in zip(res, kinds))
+
+    # roofline of the fusion kernel: algorithmic bytes / measured launch time
+    peaks = {}
+    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    n_fuse = spec.wells * args.steps
+    fuse_launch_ms = fuse_sum / n_fuse
+    if args.blend == "paste":
+        alg_bytes = 4.0 * planes * Hc * Wc                      # 2 B winning source px + 2 B written, all px covered
+    else:
+        alg_bytes = 2.0 * spec.tiles_per_well * spec.tile_h * spec.tile_w + 2.0 * planes * Hc * Wc
+    achieved = alg_bytes / (fuse_launch_ms * 1e-3) / 1e9
+    Sh_h, Sw_h = spec.tile_h - 2 * int(spec.tile_h * 0.25), ovx
+    reg_bytes = spec.wells * (spec.rows * spec.cols * 2.0 * spec.tile_h * spec.tile_w) + n_pairs * 4.0 * Sh_h * Sw_h
+    reg_achieved = reg_bytes * args.steps / (reg_sum * 1e-3) / 1e9
+
+    out = {
+        "metric": METRIC, "value": px_per_step * args.steps * world / 1e6 / (total_ms * 1e-3), "unit": "Mpx/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16 pixels; f32 flatfield divide; f32 FFT with f64 redo of low-confidence pairs",
+        "data": "synthetic",
+        "config": {"workload": workload_name(spec, use_flat, args.blend), "plates": world,
+                   "pairs_per_step": n_pairs * world, "canvas": [planes, Hc, Wc], "strip": [Sh_h, Sw_h],
+                   "l2": "inputs (29 GB) and outputs (25 GB) per step exceed L2 (126 MB); no flush needed",
+                   "timing": "CUDA events on the launching stream, max over ranks"},
+        "tile_pairs_per_s": n_pairs * args.steps * world / (reg_sum * 1e-3),
+        "fusion_mpx_per_s": px_per_step * args.steps * world / 1e6 / (fuse_sum * 1e-3),
+        "registration_ms_per_step": reg_sum / args.steps, "fusion_ms_per_step": fuse_sum / args.steps,
+        "wall_ms_per_step": wall / args.steps * 1e3,
+        "registration_truth_wells_ok": f"{ok}/{spec.wells}",
+        "registration_f64_redo_pairs": int(sum(r["precision"] == 1 for r in last_reg)),
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "fuse_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fuse_launch_ms,
+                     "frac_of_spec_8000": achieved / 8000.0},
+        "roofline_registration": {"bound": "hbm", "achieved": reg_achieved, "peak": peak_gbs, "unit": "GB/s",
+                                  "frac": reg_achieved / peak_gbs, "algorithmic_bytes_per_step": reg_bytes},
+    }
+
+    # ---------------------------------------------------------------- e2e: host buffers through the public API
+    if not args.no_e2e:
+        from image_stitcher_b200.pipeline import WellPipeline
+        hw = max(1, min(args.host_wells, spec.wells))
+        pipe = WellPipeline(ctx, spec, apply_flatfield=use_flat, blend=args.blend)
+        host_tiles = [ctx.pinned_empty((spec.rows, spec.cols, spec.channels, spec.num_z, spec.tile_h, spec.tile_w),
+                                       np.uint16) for _ in range(hw)]
+        for i in range(hw):
+            host_tiles[i][...] = plate.pool[i].cpu().numpy().view(np.uint16)
+        host_out = [ctx.pinned_empty((1, spec.channels, spec.num_z, Hc, Wc), np.uint16) for _ in range(pipe.depth)]
+        e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(1, min(args.steps, 2))
+        ctx.set_lane_stream(0, None)
+
+        def e2e_step():
+            results = []
+            for w in range(spec.wells):
+                results.append(pipe.submit(host_tiles[w % hw], host_out[w % pipe.depth]))
+            pipe.drain()
+            return results
+
+        e2e_step()                                       # warm-up (allocations, first-touch)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res = e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        # check one well against the device-resident result of the same well
+        got = host_out[(spec.wells - 1) % pipe.depth][0].reshape(planes, Hc, Wc)
+        src_w = (spec.wells - 1) % hw
+        exp = canvases[src_w].cpu().numpy().view(np.uint16)[:, :, :Wc]
+        out["e2e"] = {"value": px_per_step * e2e_steps * world / 1e6 / e2e_s, "unit": "Mpx/s",
+                      "h2d_bytes_per_step": int(spec.wells * spec.tiles_per_well * spec.tile_h * spec.tile_w * 2),
+                      "d2h_bytes_per_step": int(px_per_step * 2), "steps": e2e_steps,
+                      "ms_per_step": e2e_s / e2e_steps * 1e3,
+                      "tile_pairs_per_s": n_pairs * e2e_steps * world / e2e_s,
+                      "api": "WellPipeline.submit(host tiles) -> host canvas (sb_memcpy_async + sb_register_pairs "
+                             "+ sb_fuse_region over 3 lanes)",
+                      "host_wells_distinct": hw, "matches_device_result": bool(np.array_equal(got, exp))}
+    else:
+        out["e2e"] = None
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n = max(1, args.cpu_sample_wells)
+        tiles = plate.pool[:n].cpu().numpy().view(np.uint16)
+        flat = plate.flat.cpu().numpy()
+        p, x, a, b = cpu_sample(spec, tiles, flat, n, use_flat)
+        out["cpu_baseline"] = {"value": x / 1e6 / (a + b), "unit": "Mpx/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"{n} of {spec.wells} wells ({p} pairs, {x / 1e6:.0f} Mpx), arrays in RAM; "
+                                         "NumPy/SciPy oracle port of the reference, scipy.fft default workers",
+                               "tile_pairs_per_s": p / a, "fusion_mpx_per_s": x / 1e6 / b,
+                               "seconds": a + b}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,7 +27,7 @@ BLEND_MODES = {"paste": SB_BLEND_PASTE, "linear": SB_BLEND_LINEAR, "feather": SB
 EXPORTS = [
     "sb_version", "sb_create", "sb_destroy", "sb_last_error", "sb_kernel_launches", "sb_num_lanes",
     "sb_device_sm_count", "sb_host_alloc", "sb_host_free", "sb_device_alloc", "sb_device_free",
-    "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_set_flatfield", "sb_set_darkfield", "sb_clear_fields",
+    "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_memcpy_async", "sb_set_flatfield", "sb_set_darkfield", "sb_clear_fields",
     "sb_flatfield_apply", "sb_fuse_region", "sb_sync", "sb_set_lane_stream", "sb_canvas_pitch",
     "sb_chunked_plane_elems", "sb_register_pairs", "sb_normalize",
 ]
@@ -61,7 +61,7 @@ class SbPairResult(C.Structure):
 class SbRegisterJob(C.Structure):
     _fields_ = [("pairs", C.POINTER(SbPair)), ("n_pairs", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),
                 ("dtype", C.c_int32), ("mem", C.c_int32), ("max_overlap_x", C.c_int32), ("max_overlap_y", C.c_int32),
-                ("upsample_factor", C.c_int32), ("precision", C.c_int32)]
+                ("upsample_factor", C.c_int32), ("precision", C.c_int32), ("lane", C.c_int32)]
 
 
 _lib = None
@@ -98,6 +98,7 @@ def load_library(path: Optional[str] = None):
     lib.sb_device_free.restype = None
     lib.sb_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
     lib.sb_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.sb_memcpy_async.argtypes = [vp, i32, vp, vp, C.c_size_t, i32]
     for fn in (lib.sb_set_flatfield, lib.sb_set_darkfield):
         fn.argtypes = [vp, i32, vp, i32, i32, i32, i32]
     lib.sb_clear_fields.argtypes = [vp]
@@ -248,8 +249,22 @@ class Context:
         self._check(self.lib.sb_fuse_region(self.handle, C.byref(job), lane), "sb_fuse_region")
 
     # ------------------------------------------------------------------ registration
+    def device_alloc(self, nbytes: int) -> int:
+        addr = self.lib.sb_device_alloc(self.handle, int(nbytes))
+        if not addr:
+            raise MemoryError(self.lib.sb_last_error(self.handle).decode())
+        return int(addr)
+
+    def device_free(self, addr: int):
+        self.lib.sb_device_free(self.handle, C.c_void_p(addr))
+
+    def memcpy_async(self, lane: int, dst, src, nbytes: int, kind: int):
+        """kind: 0 = H2D, 1 = D2H, 2 = D2D, on the lane's stream."""
+        self._check(self.lib.sb_memcpy_async(self.handle, lane, _ptr(dst), _ptr(src), int(nbytes), kind),
+                    "sb_memcpy_async")
+
     def register_pairs(self, pairs: Sequence[tuple], tile_shape, max_overlap_x: int, max_overlap_y: int, *,
-                       mem=SB_MEM_HOST, upsample_factor: int = 10, precision: int = SB_PREC_AUTO):
+                       mem=SB_MEM_HOST, upsample_factor: int = 10, precision: int = SB_PREC_AUTO, lane: int = 0):
         """``pairs``: sequence of ``(ref, mov, dir)``.  Returns a list of dicts (see ``sb_pair_result``)."""
         n = len(pairs)
         if n == 0:
@@ -259,7 +274,7 @@ class Context:
             arr[i] = SbPair(_ptr(ref), _ptr(mov), int(d), 0)
         res = (SbPairResult * n)()
         job = SbRegisterJob(arr, n, int(tile_shape[0]), int(tile_shape[1]), SB_U16, mem, int(max_overlap_x),
-                            int(max_overlap_y), int(upsample_factor), int(precision))
+                            int(max_overlap_y), int(upsample_factor), int(precision), int(lane))
         self._check(self.lib.sb_register_pairs(self.handle, C.byref(job), res), "sb_register_pairs")
         out = []
         for r in res:

@@ -170,6 +170,14 @@ int sb_memcpy_d2h(sb_ctx* ctx, void* dst, const void* src, size_t bytes) {
     return SB_OK;
 }
 
+int sb_memcpy_async(sb_ctx* ctx, int lane, void* dst, const void* src, size_t bytes, int kind) {
+    Lane* l = sb_lane(ctx, lane);
+    if (!l) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    SB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, k, l->stream));
+    return SB_OK;
+}
+
 static int set_field(sb_ctx* ctx, FieldPool& pool, const char* what, int channel, const void* field, int dtype, int mem,
                      int h, int w) {
     SB_CHECK(ctx, ctx != nullptr, "ctx is NULL");

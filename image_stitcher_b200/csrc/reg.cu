@@ -682,7 +682,8 @@ int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_resu
     const int H = job->tile_h, W = job->tile_w, n = job->n_pairs;
     SB_CHECK(ctx, H > 0 && W > 0, "bad tile shape");
     if (n == 0) return SB_OK;
-    Lane* lane = sb_lane(ctx, 0);
+    Lane* lane = sb_lane(ctx, job->lane);
+    SB_CHECK(ctx, lane != nullptr, "lane %d out of range", job->lane);
     cudaStream_t st = lane->stream;
 
     std::vector<const void*> ptrs;

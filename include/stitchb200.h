@@ -76,6 +76,9 @@ void* sb_device_alloc(sb_ctx* ctx, size_t bytes);
 void sb_device_free(sb_ctx* ctx, void* p);
 int sb_memcpy_h2d(sb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int sb_memcpy_d2h(sb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+/* Asynchronous copy on a lane's stream (ordered with that lane's kernels); kind: 0 = host->device,
+ * 1 = device->host, 2 = device->device.  Host memory should come from sb_host_alloc. */
+int sb_memcpy_async(sb_ctx* ctx, int lane, void* dst, const void* src, size_t bytes, int kind);
 
 /* ------------------------------------------------------------------ flat / dark fields
  * Replaces the *storage* of self.flatfields (:158, :524): one H x W field per
@@ -172,6 +175,8 @@ typedef struct sb_register_job {
     int32_t max_overlap_y;    /* strip height of vertical pairs (max_y_overlap, :609)  */
     int32_t upsample_factor;  /* reference: 10 (:684, :707) */
     int32_t precision;        /* SB_PREC_* ; AUTO = f32, pairs with a thin peak margin redone in f64 */
+    int32_t lane;             /* stream to run on (ordered after that lane's earlier copies); the call
+                                 still returns only when the results are on the host                  */
 } sb_register_job;
 
 int sb_register_pairs(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out);

@@ -15,7 +15,7 @@ for r in range(rows):
     for c in range(cols):
         for ch in range(C):
             job.append((pool[i].data_ptr(), c * step, r * step, ch, 0, 0, 0, 0, 0)); i += 1
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream(); torch.cuda.synchronize()
 ctx.set_lane_stream(0, stream.cuda_stream)
 def run(flat, blend, reps=10):
     ctx.clear_fields()
