@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libstitchb200.so")
+LIB_PATH = os.environ.get("SB_LIB_PATH") or os.path.join(_HERE, "_lib", "libstitchb200.so")
 
 SB_MEM_HOST, SB_MEM_DEVICE = 0, 1
 SB_U16, SB_U8 = 0, 1

@@ -190,12 +190,7 @@ static int set_field(sb_ctx* ctx, FieldPool& pool, const char* what, int channel
                        what);
     if ((int)pool.slot_of_channel.size() <= channel) pool.slot_of_channel.resize(channel + 1, -1);
     int slot = pool.slot_of_channel[channel];
-    // Element-shifted copies so that a copy exists whose TMA box start is 16-byte aligned for any
-    // tile offset: copy e holds field[row][i - e] at column i (row pitch w + 4, zero elsewhere).
-    const int ncopy = 16 / (int)eb;
-    const size_t fpitch = (size_t)(w + 4) * eb;
-    const size_t plane = (size_t)h * fpitch;
-    const size_t one = plane * ncopy;
+    const size_t one = (size_t)h * w * eb;
     if (slot < 0) {
         // grow the contiguous pool by one slot (fields are set once per run: simplicity over speed)
         void* nd = nullptr;
@@ -213,12 +208,28 @@ static int set_field(sb_ctx* ctx, FieldPool& pool, const char* what, int channel
         pool.w = w;
         pool.dtype = dtype;
     }
-    uint8_t* base = (uint8_t*)pool.dev + (size_t)slot * one;
-    SB_CUDA(ctx, cudaMemset(base, 0, one));
-    for (int e = 0; e < ncopy; ++e)
-        SB_CUDA(ctx, cudaMemcpy2D(base + (size_t)e * plane + (size_t)e * eb, fpitch, field, (size_t)w * eb, (size_t)w * eb, h,
-                                  mem == SB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
-    SB_CUDA(ctx, cudaDeviceSynchronize());
+    SB_CUDA(ctx, cudaMemcpy((uint8_t*)pool.dev + (size_t)slot * one, field, one,
+                            mem == SB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    // Range check, once per field: the paste fast path divides with the branch-free div.rn.f32 sequence,
+    // which is exact only while no operand exponent is extreme (what FCHK guards in the compiler's code).
+    if (dtype == SB_FIELD_F32) {
+        std::vector<float> tmp;
+        const float* h_field = (const float*)field;
+        if (mem == SB_MEM_DEVICE) {
+            tmp.resize((size_t)h * w);
+            SB_CUDA(ctx, cudaMemcpy(tmp.data(), field, one, cudaMemcpyDeviceToHost));
+            h_field = tmp.data();
+        }
+        const bool is_flat = (&pool == &ctx->flat);
+        bool ok = true;
+        for (size_t i = 0; i < (size_t)h * w && ok; ++i) {
+            const float v = h_field[i];
+            ok = is_flat ? (v >= 9.5367431640625e-07f && v <= 1048576.0f) : (v >= -1048576.0f && v <= 1048576.0f);
+        }
+        if (!ok) pool.fast_ok = false;
+    } else {
+        pool.fast_ok = false;      // float64 fields take the generic kernel (float64 divide, as the reference does)
+    }
     return SB_OK;
 }
 

@@ -22,11 +22,11 @@ struct DevBuf {
 };
 
 struct FieldPool {            // flat- or dark-fields of all channels, one contiguous device array
-    void* dev = nullptr;      // [n_slots][ncopy][h][w] of float or double; copy d holds field[.., i + d]
-    int ncopy() const { return dtype == SB_FIELD_F64 ? 2 : 4; }
+    void* dev = nullptr;      // [n_slots][h][w] of float or double
     int dtype = SB_FIELD_F32;
     int h = 0, w = 0;
     int n_slots = 0;
+    bool fast_ok = true;      // every value inside the range where the branch-free float32 divide is exact
     std::vector<int> slot_of_channel;   // channel -> slot or -1
     bool any() const { for (int s : slot_of_channel) if (s >= 0) return true; return false; }
     int slot(int c) const { return (c >= 0 && c < (int)slot_of_channel.size()) ? slot_of_channel[c] : -1; }
