@@ -10,8 +10,13 @@
 //
 // (Ns = product of the radices already applied).  All twiddles are N-th roots of unity and come
 // from one table W_N[m] = exp(-2 pi i m / N) that the host computes in double precision.
-// Work item = (output index, group of LB lines): the twiddle is loaded once and reused for LB
-// lines; neighbouring lanes share j, so their input loads are shared-memory broadcasts.
+//
+// The passes are shared-memory-bandwidth bound (ncu, profiles/r1_registration.md), so they are
+// organised to reuse every shared-memory load:
+//   * radix 4 / radix 2: one thread per butterfly and group of LB lines -- 3 (1) twiddle loads are
+//     shared by the LB lines, each input is read once, each output written once;
+//   * any other radix (large primes included): a thread owns a QT x LB tile (QT outputs q of one
+//     butterfly, LB lines): per term r it loads QT twiddles and LB inputs for QT * LB complex FMAs.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -42,12 +47,234 @@ __device__ __forceinline__ void cfma(T2& acc, const T2 a, const T2 w) {
     acc.y = fma(a.x, w.y, acc.y);
     acc.y = fma(a.y, w.x, acc.y);
 }
+template <typename T2>
+__device__ __forceinline__ T2 cmul(const T2 a, const T2 w) {
+    T2 r;
+    r.x = a.x * w.x - a.y * w.y;
+    r.y = a.x * w.y + a.y * w.x;
+    return r;
+}
+
+template <typename T2, int LB>
+__device__ __forceinline__ void pass_radix4(const T2* __restrict__ a, T2* __restrict__ b, const T2* __restrict__ tw, int N, int Ns,
+                                            int groups, bool inverse) {
+    const int M = N >> 2;
+    const int tstep = N / (Ns * 4);
+    const int items = M * groups;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int g = it / M, j = it - g * M;
+        const int k = j % Ns;
+        T2 w1 = tw[k * tstep], w2 = tw[2 * k * tstep], w3 = tw[3 * k * tstep];
+        if (inverse) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+        const int dst = (j / Ns) * Ns * 4 + k;
+#pragma unroll
+        for (int l = 0; l < LB; ++l) {
+            const T2* in = a + (size_t)(g * LB + l) * N + j;
+            const T2 x0 = in[0], x1 = cmul(in[M], w1), x2 = cmul(in[2 * M], w2), x3 = cmul(in[3 * M], w3);
+            const T2 s02 = mk2<T2>(x0.x + x2.x, x0.y + x2.y), d02 = mk2<T2>(x0.x - x2.x, x0.y - x2.y);
+            const T2 s13 = mk2<T2>(x1.x + x3.x, x1.y + x3.y), d13 = mk2<T2>(x1.x - x3.x, x1.y - x3.y);
+            T2* out = b + (size_t)(g * LB + l) * N + dst;
+            out[0] = mk2<T2>(s02.x + s13.x, s02.y + s13.y);
+            out[2 * Ns] = mk2<T2>(s02.x - s13.x, s02.y - s13.y);
+            // forward: q=1 -> d02 - i d13, q=3 -> d02 + i d13 ; inverse: the conjugates
+            if (!inverse) {
+                out[Ns] = mk2<T2>(d02.x + d13.y, d02.y - d13.x);
+                out[3 * Ns] = mk2<T2>(d02.x - d13.y, d02.y + d13.x);
+            } else {
+                out[Ns] = mk2<T2>(d02.x - d13.y, d02.y + d13.x);
+                out[3 * Ns] = mk2<T2>(d02.x + d13.y, d02.y - d13.x);
+            }
+        }
+    }
+}
+
+template <typename T2, int LB>
+__device__ __forceinline__ void pass_radix2(const T2* __restrict__ a, T2* __restrict__ b, const T2* __restrict__ tw, int N, int Ns,
+                                            int groups, bool inverse) {
+    const int M = N >> 1;
+    const int tstep = N / (Ns * 2);
+    const int items = M * groups;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int g = it / M, j = it - g * M;
+        const int k = j % Ns;
+        T2 w1 = tw[k * tstep];
+        if (inverse) w1.y = -w1.y;
+        const int dst = (j / Ns) * Ns * 2 + k;
+#pragma unroll
+        for (int l = 0; l < LB; ++l) {
+            const T2* in = a + (size_t)(g * LB + l) * N + j;
+            const T2 x0 = in[0], x1 = cmul(in[M], w1);
+            T2* out = b + (size_t)(g * LB + l) * N + dst;
+            out[0] = mk2<T2>(x0.x + x1.x, x0.y + x1.y);
+            out[Ns] = mk2<T2>(x0.x - x1.x, x0.y - x1.y);
+        }
+    }
+}
+
+template <typename T2, int LB, int QT>
+__device__ __forceinline__ void pass_generic(const T2* __restrict__ a, T2* __restrict__ b, const T2* __restrict__ tw, int N, int Ns,
+                                             int R, int groups, bool inverse) {
+    const int M = N / R;
+    const int tstep = N / (Ns * R);
+    const int qtiles = (R + QT - 1) / QT;
+    const int items = M * qtiles * groups;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int g = it / (M * qtiles);
+        const int rem = it - g * (M * qtiles);
+        const int j = rem / qtiles, qt = rem - j * qtiles;      // q tile fastest: neighbouring lanes share j -> broadcast inputs
+        const int k = j % Ns;
+        int step[QT], idx[QT];
+#pragma unroll
+        for (int t = 0; t < QT; ++t) {
+            const int q = min(qt * QT + t, R - 1);
+            step[t] = (int)(((long long)k * tstep + (long long)q * M) % N);
+            idx[t] = 0;
+        }
+        T2 acc[QT][LB];
+#pragma unroll
+        for (int t = 0; t < QT; ++t)
+#pragma unroll
+            for (int l = 0; l < LB; ++l) acc[t][l].x = acc[t][l].y = 0;
+        const T2* in = a + (size_t)g * LB * N + j;
+        for (int r = 0; r < R; ++r) {
+            T2 x[LB];
+#pragma unroll
+            for (int l = 0; l < LB; ++l) x[l] = in[(size_t)l * N + (size_t)r * M];
+#pragma unroll
+            for (int t = 0; t < QT; ++t) {
+                T2 w = tw[idx[t]];
+                if (inverse) w.y = -w.y;
+                idx[t] += step[t];
+                if (idx[t] >= N) idx[t] -= N;
+#pragma unroll
+                for (int l = 0; l < LB; ++l) cfma(acc[t][l], x[l], w);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < QT; ++t) {
+            const int q = qt * QT + t;
+            if (q < R) {
+                const int dst = (j / Ns) * Ns * R + k + q * Ns;
+#pragma unroll
+                for (int l = 0; l < LB; ++l) b[(size_t)(g * LB + l) * N + dst] = acc[t][l];
+            }
+        }
+    }
+}
+
+// Odd radix R (large primes included) exploiting W^{q(R-r)} = conj(W^{qr}):
+//   with e_r = y_r + y_{R-r}, o_r = y_r - y_{R-r} (r = 1..h, h = (R-1)/2, y = pre-twiddled inputs)
+//   X[q]   = y_0 + sum_r e_r cos(2 pi q r / R) -/+ i sum_r o_r sin(2 pi q r / R)
+//   X[R-q] = y_0 + sum_r e_r cos(..)           +/- i sum_r o_r sin(..)
+// i.e. 4 real FMAs per (q, r) pair and TWO outputs -- a quarter of the multiplies of the plain DFT.
+// Step 1 rewrites the input buffer in place (e_r at slot r, o_r at slot R-r); step 2 is the tiled sum.
+template <typename T2, int LB, int QT>
+__device__ __forceinline__ void pass_odd_sym(T2* __restrict__ a, T2* __restrict__ b, const T2* __restrict__ tw, int N, int Ns, int R,
+                                             int groups, bool inverse) {
+    const int M = N / R;
+    const int h = (R - 1) / 2;
+    const int tstep = N / (Ns * R);
+    const int nl = groups * LB;
+    // ---- step 1: pre-twiddle + fold
+    for (int it = threadIdx.x; it < M * h * nl; it += blockDim.x) {
+        const int l = it / (M * h);
+        const int rem = it - l * (M * h);
+        const int r = rem / M + 1, j = rem - (r - 1) * M;
+        const int k = j % Ns;
+        T2* line = a + (size_t)l * N + j;
+        T2 y1 = line[(size_t)r * M], y2 = line[(size_t)(R - r) * M];
+        if (Ns > 1) {
+            T2 w1 = tw[(int)(((long long)r * k * tstep) % N)], w2 = tw[(int)(((long long)(R - r) * k * tstep) % N)];
+            if (inverse) { w1.y = -w1.y; w2.y = -w2.y; }
+            y1 = cmul(y1, w1);
+            y2 = cmul(y2, w2);
+        }
+        line[(size_t)r * M] = mk2<T2>(y1.x + y2.x, y1.y + y2.y);
+        line[(size_t)(R - r) * M] = mk2<T2>(y1.x - y2.x, y1.y - y2.y);
+    }
+    __syncthreads();
+    // ---- step 2: tiles of QT outputs q in [1, h] (plus one item per butterfly for q = 0)
+    const int qtiles = (h + QT - 1) / QT + 1;
+    const int items = M * qtiles * groups;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int g = it / (M * qtiles);
+        const int rem = it - g * (M * qtiles);
+        const int j = rem / qtiles, qt = rem - j * qtiles;
+        const int k = j % Ns;
+        const T2* in = a + (size_t)g * LB * N + j;
+        const int dst0 = (j / Ns) * Ns * R + k;
+        if (qt == qtiles - 1) {                       // X[0] = y_0 + sum_r e_r
+#pragma unroll
+            for (int l = 0; l < LB; ++l) {
+                T2 acc = in[(size_t)l * N];
+                for (int r = 1; r <= h; ++r) {
+                    const T2 e = in[(size_t)l * N + (size_t)r * M];
+                    acc.x += e.x;
+                    acc.y += e.y;
+                }
+                b[(size_t)(g * LB + l) * N + dst0] = acc;
+            }
+            continue;
+        }
+        int step[QT], idx[QT];
+#pragma unroll
+        for (int t = 0; t < QT; ++t) {
+            const int q = min(qt * QT + t + 1, h);
+            step[t] = (int)(((long long)q * M) % N);
+            idx[t] = step[t];                          // r starts at 1
+        }
+        T2 ce[QT][LB], so[QT][LB];
+#pragma unroll
+        for (int t = 0; t < QT; ++t)
+#pragma unroll
+            for (int l = 0; l < LB; ++l) { ce[t][l].x = ce[t][l].y = 0; so[t][l].x = so[t][l].y = 0; }
+        for (int r = 1; r <= h; ++r) {
+            T2 e[LB], o[LB];
+#pragma unroll
+            for (int l = 0; l < LB; ++l) {
+                e[l] = in[(size_t)l * N + (size_t)r * M];
+                o[l] = in[(size_t)l * N + (size_t)(R - r) * M];
+            }
+#pragma unroll
+            for (int t = 0; t < QT; ++t) {
+                const T2 w = tw[idx[t]];               // (cos, -sin) of 2 pi q r / R
+                idx[t] += step[t];
+                if (idx[t] >= N) idx[t] -= N;
+#pragma unroll
+                for (int l = 0; l < LB; ++l) {
+                    ce[t][l].x = fma(e[l].x, w.x, ce[t][l].x);
+                    ce[t][l].y = fma(e[l].y, w.x, ce[t][l].y);
+                    so[t][l].x = fma(o[l].x, -w.y, so[t][l].x);
+                    so[t][l].y = fma(o[l].y, -w.y, so[t][l].y);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < QT; ++t) {
+            const int q = qt * QT + t + 1;
+            if (q <= h) {
+#pragma unroll
+                for (int l = 0; l < LB; ++l) {
+                    const T2 y0 = in[(size_t)l * N];
+                    const T2 base = mk2<T2>(y0.x + ce[t][l].x, y0.y + ce[t][l].y);
+                    // forward: X[q] = base - i So, X[R-q] = base + i So ; inverse: swapped
+                    const T2 lo = mk2<T2>(base.x + so[t][l].y, base.y - so[t][l].x);
+                    const T2 hi = mk2<T2>(base.x - so[t][l].y, base.y + so[t][l].x);
+                    T2* out = b + (size_t)(g * LB + l) * N + dst0;
+                    out[(size_t)q * Ns] = inverse ? hi : lo;
+                    out[(size_t)(R - q) * Ns] = inverse ? lo : hi;
+                }
+            }
+        }
+    }
+}
 
 // In-place (ping-pong) FFT of `nlines` lines of length plan.n held in shared memory, line stride
 // plan.n.  nlines must be a multiple of LB.  Returns the buffer that holds the result.  All
 // threads of the block must call; ends with a __syncthreads().
 template <typename T2, int LB>
 __device__ T2* fft_lines(T2* buf0, T2* buf1, const T2* __restrict__ tw, const FftPlan& plan, int nlines, bool inverse) {
+    // NOTE: odd-radix passes fold their inputs in place, so the input buffer is clobbered.
     const int N = plan.n;
     T2* a = buf0;
     T2* b = buf1;
@@ -55,32 +282,10 @@ __device__ T2* fft_lines(T2* buf0, T2* buf1, const T2* __restrict__ tw, const Ff
     const int groups = nlines / LB;
     for (int f = 0; f < plan.nfac; ++f) {
         const int R = plan.fac[f];
-        const int M = N / R;
-        const int tstep = N / (Ns * R);
-        const int items = N * groups;
-        for (int it = threadIdx.x; it < items; it += blockDim.x) {
-            const int g = it / N;
-            const int o = it - g * N;
-            const int j = o / R, q = o - j * R;          // q fastest: lanes share j -> broadcast input loads
-            const int k = j % Ns;
-            const int step = (int)(((long long)k * tstep + (long long)q * M) % N);
-            T2 acc[LB];
-#pragma unroll
-            for (int l = 0; l < LB; ++l) acc[l].x = acc[l].y = 0;
-            const T2* in = a + (size_t)g * LB * N + j;
-            int idx = 0;
-            for (int r = 0; r < R; ++r) {
-                T2 w = tw[idx];
-                if (inverse) w.y = -w.y;
-                idx += step;
-                if (idx >= N) idx -= N;
-#pragma unroll
-                for (int l = 0; l < LB; ++l) cfma(acc[l], in[(size_t)l * N + (size_t)r * M], w);
-            }
-            const int dst = (j / Ns) * Ns * R + k + q * Ns;
-#pragma unroll
-            for (int l = 0; l < LB; ++l) b[(size_t)(g * LB + l) * N + dst] = acc[l];
-        }
+        if (R == 4) pass_radix4<T2, LB>(a, b, tw, N, Ns, groups, inverse);
+        else if (R == 2) pass_radix2<T2, LB>(a, b, tw, N, Ns, groups, inverse);
+        else if (R & 1) pass_odd_sym<T2, LB, (sizeof(T2) == 8 ? (LB >= 4 ? 4 : 8) : (LB >= 4 ? 2 : 4))>(a, b, tw, N, Ns, R, groups, inverse);
+        else pass_generic<T2, LB, (LB >= 4 ? 4 : 8)>(a, b, tw, N, Ns, R, groups, inverse);
         __syncthreads();
         T2* t = a;
         a = b;

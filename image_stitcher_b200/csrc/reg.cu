@@ -126,18 +126,35 @@ __global__ void __launch_bounds__(256) rows_fwd_kernel(const PairDesc* __restric
     int seen = 0;                                // bit 0: strip a has a non-zero pixel, bit 1: strip b
     const int2 ma = mm[pd.a_tile], mb = mm[pd.b_tile];
     for (int i = threadIdx.x; i < Sw; i += blockDim.x) tw[i] = tw_g[i];
-    for (int i = threadIdx.x; i < lpb * Sw; i += blockDim.x) {
-        const int l = i / Sw, x = i - l * Sw;
-        const int y = y0 + l;
-        T2 z = mk2<T2, T>(0, 0);
-        if (y < Sh) {
-            const size_t off = (size_t)y * tile_w + x;
-            const int na = stretch_px(pd.a[off], ma.x, ma.y), nb = stretch_px(pd.b[off], mb.x, mb.y);
-            seen |= (na != 0 ? 1 : 0) | (nb != 0 ? 2 : 0);
-            z.x = (T)(na * kInScale);
-            z.y = (T)(nb * kInScale);
+    // strip crop + stretch fused into the load; four independent pixel pairs in flight per thread
+    for (int i0 = threadIdx.x; i0 < lpb * Sw; i0 += 4 * blockDim.x) {
+        unsigned av[4], bv[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x;
+            const int l = i / Sw, x = i - l * Sw;
+            ok[u] = i < lpb * Sw && y0 + l < Sh;
+            av[u] = bv[u] = 0;
+            if (ok[u]) {
+                const size_t off = (size_t)(y0 + l) * tile_w + x;
+                av[u] = pd.a[off];
+                bv[u] = pd.b[off];
+            }
         }
-        buf0[i] = z;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i >= lpb * Sw) continue;
+            T2 z = mk2<T2, T>(0, 0);
+            if (ok[u]) {
+                const int na = stretch_px(av[u], ma.x, ma.y), nb = stretch_px(bv[u], mb.x, mb.y);
+                seen |= (na != 0 ? 1 : 0) | (nb != 0 ? 2 : 0);
+                z.x = (T)(na * kInScale);
+                z.y = (T)(nb * kInScale);
+            }
+            buf0[i] = z;
+        }
     }
     // An all-zero strip has an exactly zero spectrum in the reference (P == 0 -> cc == 0 -> argmax 0);
     // the packed transform only gets it to rounding noise, so record the fact instead.
@@ -182,7 +199,8 @@ __global__ void __launch_bounds__(256) cols_xpower_kernel(int Sh, int Sw, int nc
         buf0[(size_t)l * Sh + y] = z;
     }
     __syncthreads();
-    T2* f = fft_lines<T2, NL>(buf0, buf1, tw, plan, NL, false);
+    constexpr int CLB = NL >= 4 ? 4 : NL;
+    T2* f = fft_lines<T2, CLB>(buf0, buf1, tw, plan, NL, false);
     // unpack A = FFT(a), B = FFT(b) from Z = FFT(a + i b); R = A conj(B) / max(|A conj(B)|, clamp)
     for (int i = threadIdx.x; i < G * Sh; i += blockDim.x) {
         const int l = i / Sh, ky = i - l * Sh;
@@ -210,7 +228,7 @@ __global__ void __launch_bounds__(256) cols_xpower_kernel(int Sh, int Sw, int nc
     }
     __syncthreads();
     T2* other = (f == buf0) ? buf1 : buf0;
-    T2* y = fft_lines<T2, NL>(f, other, tw, plan, NL, true);
+    T2* y = fft_lines<T2, CLB>(f, other, tw, plan, NL, true);
     for (int i = threadIdx.x; i < NL * Sh; i += blockDim.x) {
         const int yy = i / NL, l = i - yy * NL;
         const int kx = cg * G + (l % G);
@@ -356,83 +374,107 @@ __global__ void __launch_bounds__(256) updft_twiddle_kernel(const PeakOut* __res
     }
 }
 
-// T[u][y] = sum_x conj(R[y][x]) Ex[u][x]; one warp per row, u tiled by 16.
+// T[u][y] = sum_x conj(R[y][x]) Ex[u][x].  A block owns 16 rows (two per warp); the twiddle rows
+// Ex[u][x0 .. x0+XC) of a u tile are staged in shared memory once per block and reused by all 16 rows.
 template <typename T>
-__global__ void __launch_bounds__(256) updft_rows_kernel(int Sh, int Sw, int rs, int rows_per_block, int nrb,
+__global__ void __launch_bounds__(256) updft_rows_kernel(int Sh, int Sw, int rs, int nrb,
                                                          const typename Vec2<T>::type* __restrict__ Rbuf,
                                                          const typename Vec2<T>::type* __restrict__ Ex,
                                                          typename Vec2<T>::type* __restrict__ Tm) {
     using T2 = typename Vec2<T>::type;
-    constexpr int UT = 16;
+    constexpr int UT = 8;                       // u tile held in registers: 2 rows x 8 accumulators
+    constexpr int XC = 256;                     // x chunk staged in shared memory
+    __shared__ __align__(16) unsigned char ex_raw[UT * XC * sizeof(T2)];
+    T2* exs = reinterpret_cast<T2*>(ex_raw);
     const int p = blockIdx.x / nrb, rb = blockIdx.x - p * nrb;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const T2* rp = Rbuf + (size_t)p * Sh * Sw;
     const T2* ex = Ex + (size_t)p * rs * Sw;
     T2* tp = Tm + (size_t)p * rs * Sh;
-    for (int yl = warp; yl < rows_per_block; yl += (blockDim.x >> 5)) {
-        const int y = rb * rows_per_block + yl;
-        if (y >= Sh) break;
-        for (int u0 = 0; u0 < rs; u0 += UT) {
-            T2 acc[UT];
+    const int y0 = rb * 16 + warp * 2, y1 = y0 + 1;
+    for (int u0 = 0; u0 < rs; u0 += UT) {
+        T2 acc0[UT], acc1[UT];
 #pragma unroll
-            for (int u = 0; u < UT; ++u) acc[u].x = acc[u].y = 0;
-            for (int x = lane; x < Sw; x += 32) {
-                T2 r = rp[(size_t)y * Sw + x];
-                r.y = -r.y;
-#pragma unroll
-                for (int u = 0; u < UT; ++u)
-                    if (u0 + u < rs) cfma(acc[u], r, ex[(size_t)(u0 + u) * Sw + x]);
+        for (int u = 0; u < UT; ++u) { acc0[u].x = acc0[u].y = 0; acc1[u].x = acc1[u].y = 0; }
+        for (int xc = 0; xc < Sw; xc += XC) {
+            const int nx = min(XC, Sw - xc);
+            __syncthreads();
+            for (int i = threadIdx.x; i < UT * nx; i += blockDim.x) {
+                const int u = i / nx, x = i - u * nx;
+                exs[u * XC + x] = (u0 + u < rs) ? ex[(size_t)(u0 + u) * Sw + xc + x] : mk2<T2, T>(0, 0);
             }
+            __syncthreads();
+            for (int x = lane; x < nx; x += 32) {
+                T2 r0 = mk2<T2, T>(0, 0), r1 = mk2<T2, T>(0, 0);
+                if (y0 < Sh) { r0 = rp[(size_t)y0 * Sw + xc + x]; r0.y = -r0.y; }
+                if (y1 < Sh) { r1 = rp[(size_t)y1 * Sw + xc + x]; r1.y = -r1.y; }
 #pragma unroll
-            for (int u = 0; u < UT; ++u) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    acc[u].x += __shfl_xor_sync(0xffffffffu, acc[u].x, o);
-                    acc[u].y += __shfl_xor_sync(0xffffffffu, acc[u].y, o);
+                for (int u = 0; u < UT; ++u) {
+                    const T2 w = exs[u * XC + x];
+                    cfma(acc0[u], r0, w);
+                    cfma(acc1[u], r1, w);
                 }
-                if (lane == 0 && u0 + u < rs) tp[(size_t)(u0 + u) * Sh + y] = acc[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UT; ++u) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc0[u].x += __shfl_xor_sync(0xffffffffu, acc0[u].x, o);
+                acc0[u].y += __shfl_xor_sync(0xffffffffu, acc0[u].y, o);
+                acc1[u].x += __shfl_xor_sync(0xffffffffu, acc1[u].x, o);
+                acc1[u].y += __shfl_xor_sync(0xffffffffu, acc1[u].y, o);
+            }
+            if (lane == 0 && u0 + u < rs) {
+                if (y0 < Sh) tp[(size_t)(u0 + u) * Sh + y0] = acc0[u];
+                if (y1 < Sh) tp[(size_t)(u0 + u) * Sh + y1] = acc1[u];
             }
         }
     }
 }
 
-// out[v][u] = sum_y Ey[v][y] T[u][y]; |conj(out)| argmax, first maximum in C order. One block per pair.
+// out[v][u] = sum_y Ey[v][y] T[u][y].  grid = (pair, v): every warp reduces a few u over y; |out|^2 to global.
 template <typename T>
-__global__ void __launch_bounds__(256) updft_final_kernel(int Sh, int rs, const typename Vec2<T>::type* __restrict__ Tm,
-                                                          const typename Vec2<T>::type* __restrict__ Ey, float inv_n,
-                                                          const int* __restrict__ nonzero, PeakOut* __restrict__ peaks) {
+__global__ void __launch_bounds__(256) updft_cols_kernel(int Sh, int rs, const typename Vec2<T>::type* __restrict__ Tm,
+                                                         const typename Vec2<T>::type* __restrict__ Ey, double* __restrict__ mag2) {
     using T2 = typename Vec2<T>::type;
-    const int p = blockIdx.x;
-    if (nonzero[p] != 3) {                       // zero cross-power: the upsampled window is all zero -> index 0
-        if (threadIdx.x == 0) { peaks[p].fine_y = peaks[p].fine_x = 0; peaks[p].fine_peak = 0.f; }
-        return;
-    }
+    const int p = blockIdx.x / rs, v = blockIdx.x - p * rs;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const T2* tp = Tm + (size_t)p * rs * Sh;
-    const T2* ey = Ey + (size_t)p * rs * Sh;
-    T bv = (T)-1;
-    int bi = 0x7fffffff;
-    for (int o = warp; o < rs * rs; o += nw) {
-        const int v = o / rs, u = o - v * rs;
+    const T2* ey = Ey + ((size_t)p * rs + v) * Sh;
+    for (int u = warp; u < rs; u += nw) {
         T2 acc = mk2<T2, T>(0, 0);
-        for (int y = lane; y < Sh; y += 32) cfma(acc, ey[(size_t)v * Sh + y], tp[(size_t)u * Sh + y]);
+        for (int y = lane; y < Sh; y += 32) cfma(acc, ey[y], tp[(size_t)u * Sh + y]);
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) {
             acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
             acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
         }
-        best_update<T>(bv, bi, acc.x * acc.x + acc.y * acc.y, o);      // |.|^2 is monotone in |.|
+        if (lane == 0) mag2[((size_t)p * rs + v) * rs + u] = (double)(acc.x * acc.x + acc.y * acc.y);   // monotone in |.|
     }
-    __shared__ double sv[8];
-    __shared__ int si[8];
-    if (lane == 0) { sv[warp] = (double)bv; si[warp] = bi; }
-    __syncthreads();
+}
+
+// first maximum (C order) of the rs x rs window; one warp per pair
+__global__ void __launch_bounds__(32) updft_final_kernel(int rs, const double* __restrict__ mag2, float inv_n,
+                                                         const int* __restrict__ nonzero, PeakOut* __restrict__ peaks) {
+    const int p = blockIdx.x;
+    if (nonzero[p] != 3) {                       // zero cross-power: the upsampled window is all zero -> index 0
+        if (threadIdx.x == 0) { peaks[p].fine_y = peaks[p].fine_x = 0; peaks[p].fine_peak = 0.f; }
+        return;
+    }
+    double bv = -1.0;
+    int bi = 0x7fffffff;
+    for (int o = threadIdx.x; o < rs * rs; o += 32) best_update<double>(bv, bi, mag2[(size_t)p * rs * rs + o], o);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, s);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+        best_update<double>(bv, bi, ov, oi);
+    }
     if (threadIdx.x == 0) {
-        double b = (double)bv;
-        for (int w = 1; w < nw; ++w) best_update<double>(b, bi, sv[w], si[w]);
         peaks[p].fine_y = bi / rs;
         peaks[p].fine_x = bi - (bi / rs) * rs;
-        peaks[p].fine_peak = (float)(sqrt(b) * (double)inv_n);
+        peaks[p].fine_peak = (float)(sqrt(bv) * (double)inv_n);
     }
 }
 
@@ -488,7 +530,7 @@ struct GroupGeom {          // strips of one direction
 int pick_lines(int n, size_t elem, int lb, size_t budget) {
     if ((size_t)n * elem * 3 > budget) return 0;
     int l = (int)((budget - (size_t)n * elem) / (2 * (size_t)n * elem));
-    l = std::min(l, 16);
+    l = std::min(l, 32);
     l = l / lb * lb;
     return l;
 }
@@ -516,20 +558,24 @@ int run_group(sb_ctx* ctx, cudaStream_t st, const std::vector<PairDesc>& pairs, 
     B = std::min(B, n);
 
     // launch geometry
-    constexpr size_t kBudget = 96 * 1024;
+    constexpr size_t kBudget = 112 * 1024;    // two blocks per SM
     int lbx = 4, lpbx = pick_lines(Sw, sizeof(T2), 4, kBudget);
     if (lpbx < 4) { lbx = 1; lpbx = pick_lines(Sw, sizeof(T2), 1, 200 * 1024); }
     if (lpbx < 1) return sb_fail(ctx, SB_ERR_UNSUPPORTED, "strip width %d too large for the shared-memory FFT", Sw);
     const size_t smem_x = (size_t)(2 * lpbx + 1) * Sw * sizeof(T2);
-    int G = 2;
-    size_t smem_y = (size_t)(2 * 2 * G + 1) * Sh * sizeof(T2);
-    if (smem_y > 200 * 1024) { G = 1; smem_y = (size_t)(2 * 2 * G + 1) * Sh * sizeof(T2); }
+    // columns per block: short lines (e.g. 214 = 2 * 107) take 8 columns + 8 mirrors so that the prime-radix
+    // pass has enough independent work for 256 threads and global accesses are 64-byte segments
+    int G = 16;
+    auto smem_for = [&](int g) { return (size_t)(2 * 2 * g + 1) * Sh * sizeof(T2); };
+    while (G > 1 && smem_for(G) > 112 * 1024) G >>= 1;
+    if (G == 1 && smem_for(2) <= 200 * 1024) G = 2;
+    const size_t smem_y = smem_for(G);
     if (smem_y > 227 * 1024) return sb_fail(ctx, SB_ERR_UNSUPPORTED, "strip height %d too large for the shared-memory FFT", Sh);
     const int nrb_fwd = (Sh + lpbx - 1) / lpbx;
     const int nlines_inv = (Sh + 1) / 2;
     const int nrb_inv = (nlines_inv + lpbx - 1) / lpbx;
     const int ncg = (Sw / 2 + 1 + G - 1) / G;
-    const int rows_per_block = 32;
+    const int rows_per_block = 16;    // two rows per warp
     const int nrb_up = (Sh + rows_per_block - 1) / rows_per_block;
 
     // workspace: Z | R | Ex | Ey | T | best | peaks | pair descriptors
@@ -541,6 +587,7 @@ int run_group(sb_ctx* ctx, cudaStream_t st, const std::vector<PairDesc>& pairs, 
     const size_t o_Ey = carve((size_t)B * rs * Sh * sizeof(T2));
     const size_t o_T = carve((size_t)B * rs * Sh * sizeof(T2));
     const size_t o_best = carve((size_t)B * nrb_inv * sizeof(CtaBest));
+    const size_t o_mag = carve((size_t)B * rs * rs * sizeof(double));
     const size_t o_peaks = carve((size_t)n * sizeof(PeakOut));
     const size_t o_pairs = carve((size_t)n * sizeof(PairDesc));
     const size_t o_nz = carve((size_t)n * sizeof(int));
@@ -553,6 +600,7 @@ int run_group(sb_ctx* ctx, cudaStream_t st, const std::vector<PairDesc>& pairs, 
     T2* Ey = (T2*)(w + o_Ey);
     T2* Tm = (T2*)(w + o_T);
     CtaBest* best = (CtaBest*)(w + o_best);
+    double* mag2 = (double*)(w + o_mag);
     PeakOut* peaks = (PeakOut*)(w + o_peaks);
     PairDesc* d_pairs = (PairDesc*)(w + o_pairs);
     int* d_nz = (int*)(w + o_nz);
@@ -561,7 +609,7 @@ int run_group(sb_ctx* ctx, cudaStream_t st, const std::vector<PairDesc>& pairs, 
 
     auto k1 = lbx == 4 ? rows_fwd_kernel<T, 4> : rows_fwd_kernel<T, 1>;
     auto k3 = lbx == 4 ? rows_inv_argmax_kernel<T, 4> : rows_inv_argmax_kernel<T, 1>;
-    auto k2 = G == 2 ? cols_xpower_kernel<T, 2> : cols_xpower_kernel<T, 1>;
+    auto k2 = G == 16 ? cols_xpower_kernel<T, 16> : G == 8 ? cols_xpower_kernel<T, 8> : (G == 4 ? cols_xpower_kernel<T, 4> : (G == 2 ? cols_xpower_kernel<T, 2> : cols_xpower_kernel<T, 1>));
     SB_CUDA(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
     SB_CUDA(ctx, cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
     SB_CUDA(ctx, cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_y));
@@ -576,9 +624,10 @@ int run_group(sb_ctx* ctx, cudaStream_t st, const std::vector<PairDesc>& pairs, 
         ctx->launches += 4;
         if (uf > 1) {
             updft_twiddle_kernel<T><<<dim3(8, nb), 256, 0, st>>>(peaks + p0, Sh, Sw, uf, rs, dftshift, Ex, Ey);
-            updft_rows_kernel<T><<<nb * nrb_up, 256, 0, st>>>(Sh, Sw, rs, rows_per_block, nrb_up, Rb, Ex, Tm);
-            updft_final_kernel<T><<<nb, 256, 0, st>>>(Sh, rs, Tm, Ey, inv_n, d_nz + p0, peaks + p0);
-            ctx->launches += 3;
+            updft_rows_kernel<T><<<nb * nrb_up, 256, 0, st>>>(Sh, Sw, rs, nrb_up, Rb, Ex, Tm);
+            updft_cols_kernel<T><<<nb * rs, 256, 0, st>>>(Sh, rs, Tm, Ey, mag2);
+            updft_final_kernel<<<nb, 32, 0, st>>>(rs, mag2, inv_n, d_nz + p0, peaks + p0);
+            ctx->launches += 4;
         }
         SB_CUDA(ctx, cudaGetLastError());
     }
