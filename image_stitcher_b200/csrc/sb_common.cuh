@@ -39,6 +39,8 @@ struct Lane {
     void* meta_host = nullptr;      // pinned staging for per-job metadata
     size_t meta_host_cap = 0;
     cudaEvent_t meta_free = nullptr; // the previous job's metadata H2D has been consumed
+    std::vector<int32_t> perm;      // cached block-row order of the paste kernel (fuse.cu) ...
+    uint64_t perm_sig = 0;          // ... and the geometry signature it was computed for
 };
 
 struct sb_ctx {
@@ -120,6 +122,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {

@@ -1,0 +1,180 @@
+"""Minimal OME-Zarr (NGFF 0.4 on zarr v2) writer for stitched regions.
+
+The reference writes its canvases through third-party stacks (ome_zarr / bioio / aicsimageio,
+stitcher_process.py:958-1549) none of which is installed here, and north_star keeps those writers
+"as they are".  This module exists so that BASELINE.json configs[0] ("... stitch to OME-Zarr") runs
+end to end without them.  It reproduces the *metadata* the reference emits in
+``save_region_ome_zarr`` (stitcher_process.py:1039-1124):
+
+* axes t, c, z, y, x with units second / micrometer (:1085-1091);
+* one ``scale`` transform per level ``[1, 1, dz, px * 2**l, px * 2**l]`` (:1066-1078);
+* ``omero.channels`` with label, 6-hex colour, window 0..dtype max (:1099-1118);
+* chunks ``(1, 1, 1, 2048, 2048)`` (stitcher_process.py:161) or ``(1, 1, 1, 512, 512)`` (stitcher.py:235);
+* the pyramid is nearest-neighbour x2 per level (``Scaler.nearest``, :1061-1062) -- here ``[::2, ::2]``.
+
+Differences, stated: chunks are stored uncompressed by default (``compressor: null``; the reference's
+Blosc default is not available offline) or with the zarr-v2 ``zlib`` codec; nested ``/`` chunk keys.
+
+Two entry points: ``write_ome_zarr`` takes the row-major ``(1, C, Z, Hc, Wc)`` canvas the reference's
+writers take; ``write_ome_zarr_chunked`` takes the library's SB_LAYOUT_CHUNKED output (zarr chunk
+order, edge chunks zero-padded) and writes every chunk with one contiguous ``tofile``.
+"""
+from __future__ import annotations
+
+import json
+import os
+import zlib
+from typing import Optional, Sequence
+
+import numpy as np
+
+AXES = [
+    {"name": "t", "type": "time", "unit": "second"},
+    {"name": "c", "type": "channel"},
+    {"name": "z", "type": "space", "unit": "micrometer"},
+    {"name": "y", "type": "space", "unit": "micrometer"},
+    {"name": "x", "type": "space", "unit": "micrometer"},
+]
+
+
+def _dump(path: str, obj) -> None:
+    with open(path, "w") as fh:
+        json.dump(obj, fh, indent=2)
+
+
+def _zarray(shape, chunks, dtype: np.dtype, compressor: Optional[str]):
+    return {
+        "zarr_format": 2,
+        "shape": [int(s) for s in shape],
+        "chunks": [int(c) for c in chunks],
+        "dtype": np.dtype(dtype).newbyteorder("<").str if np.dtype(dtype).itemsize > 1 else np.dtype(dtype).str,
+        "compressor": {"id": "zlib", "level": 1} if compressor == "zlib" else None,
+        "fill_value": 0,
+        "order": "C",
+        "filters": None,
+        "dimension_separator": "/",
+    }
+
+
+def _encode(chunk: np.ndarray, compressor: Optional[str]) -> bytes:
+    raw = np.ascontiguousarray(chunk).tobytes()
+    return zlib.compress(raw, 1) if compressor == "zlib" else raw
+
+
+def _write_chunk(level_dir: str, idx: Sequence[int], chunk: np.ndarray, compressor: Optional[str]) -> None:
+    d = os.path.join(level_dir, *[str(i) for i in idx[:-1]])
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, str(idx[-1]))
+    if compressor is None and chunk.flags.c_contiguous:
+        chunk.tofile(path)
+    else:
+        with open(path, "wb") as fh:
+            fh.write(_encode(chunk, compressor))
+
+
+def _write_level(level_dir: str, data: np.ndarray, chunks, compressor: Optional[str]) -> None:
+    """``data`` is (T, C, Z, H, W); edge chunks are padded with the fill value (zarr v2 semantics)."""
+    os.makedirs(level_dir, exist_ok=True)
+    ch_y, ch_x = int(chunks[3]), int(chunks[4])
+    _dump(os.path.join(level_dir, ".zarray"), _zarray(data.shape, (1, 1, 1, ch_y, ch_x), data.dtype, compressor))
+    T, C, Z, H, W = data.shape
+    for t in range(T):
+        for c in range(C):
+            for z in range(Z):
+                plane = data[t, c, z]
+                for iy in range(-(-H // ch_y)):
+                    for ix in range(-(-W // ch_x)):
+                        blk = plane[iy * ch_y:(iy + 1) * ch_y, ix * ch_x:(ix + 1) * ch_x]
+                        if blk.shape != (ch_y, ch_x):
+                            full = np.zeros((ch_y, ch_x), dtype=data.dtype)
+                            full[:blk.shape[0], :blk.shape[1]] = blk
+                            blk = full
+                        _write_chunk(level_dir, (t, c, z, iy, ix), np.ascontiguousarray(blk), compressor)
+
+
+def _group_attrs(name, n_levels, pixel_size_um, dz_um, channel_names, channel_colors, dtype):
+    datasets = [{"path": str(l),
+                 "coordinateTransformations": [{"type": "scale",
+                                                "scale": [1, 1, float(dz_um), float(pixel_size_um * 2 ** l),
+                                                          float(pixel_size_um * 2 ** l)]}]}
+                for l in range(n_levels)]
+    vmax = int(np.iinfo(dtype).max) if np.issubdtype(dtype, np.integer) else 1
+    return {
+        "multiscales": [{"version": "0.4", "name": name, "axes": AXES, "datasets": datasets}],
+        "omero": {"id": 1, "name": name, "version": "0.4",
+                  "channels": [{"label": str(nm), "color": f"{int(col):06X}",
+                                "window": {"start": 0, "end": vmax, "min": 0, "max": vmax},
+                                "active": True, "coefficient": 1, "family": "linear"}
+                               for nm, col in zip(channel_names, channel_colors)]},
+    }
+
+
+def write_ome_zarr(path: str, data: np.ndarray, *, pixel_size_um: float, dz_um: float = 1.0,
+                   channel_names: Sequence[str], channel_colors: Sequence[int], num_levels: int = 1,
+                   chunks=(1, 1, 1, 2048, 2048), compressor: Optional[str] = None, name: Optional[str] = None) -> str:
+    """Write a (1, C, Z, H, W) canvas as a multiscale OME-Zarr group; returns ``path``."""
+    if data.ndim != 5:
+        raise ValueError(f"expected a 5-D TCZYX array, got shape {data.shape}")
+    if compressor not in (None, "zlib"):
+        raise ValueError("compressor must be None or 'zlib'")
+    os.makedirs(path, exist_ok=True)
+    _dump(os.path.join(path, ".zgroup"), {"zarr_format": 2})
+    level = data
+    n_written = 0
+    for l in range(max(1, int(num_levels))):
+        if l > 0:
+            level = level[..., ::2, ::2]                       # nearest-neighbour x2 (Scaler.nearest)
+            if level.shape[-1] < 1 or level.shape[-2] < 1:
+                break
+        _write_level(os.path.join(path, str(l)), level, chunks, compressor)
+        n_written += 1
+    _dump(os.path.join(path, ".zattrs"),
+          _group_attrs(name or os.path.basename(path).replace(".ome.zarr", ""), n_written, pixel_size_um, dz_um,
+                       channel_names, channel_colors, data.dtype))
+    return path
+
+
+def write_ome_zarr_chunked(path: str, chunked: np.ndarray, shape, chunk_hw, *, pixel_size_um: float, dz_um: float = 1.0,
+                           channel_names: Sequence[str], channel_colors: Sequence[int], name: Optional[str] = None) -> str:
+    """Level 0 only, from the library's SB_LAYOUT_CHUNKED buffer: ``chunked`` is
+    ``(C * Z, ncy, ncx, chunk_h, chunk_w)`` -- each chunk contiguous, edge chunks already zero-padded --
+    and ``shape`` the logical ``(C, Z, Hc, Wc)``.  No re-tiling pass on the host: one write per chunk."""
+    C, Z, H, W = (int(v) for v in shape)
+    ch_y, ch_x = int(chunk_hw[0]), int(chunk_hw[1])
+    ncy, ncx = -(-H // ch_y), -(-W // ch_x)
+    buf = np.asarray(chunked).reshape(C * Z, ncy, ncx, ch_y, ch_x)
+    os.makedirs(os.path.join(path, "0"), exist_ok=True)
+    _dump(os.path.join(path, ".zgroup"), {"zarr_format": 2})
+    _dump(os.path.join(path, "0", ".zarray"), _zarray((1, C, Z, H, W), (1, 1, 1, ch_y, ch_x), buf.dtype, None))
+    for c in range(C):
+        for z in range(Z):
+            for iy in range(ncy):
+                for ix in range(ncx):
+                    _write_chunk(os.path.join(path, "0"), (0, c, z, iy, ix), buf[c * Z + z, iy, ix], None)
+    _dump(os.path.join(path, ".zattrs"),
+          _group_attrs(name or os.path.basename(path).replace(".ome.zarr", ""), 1, pixel_size_um, dz_um,
+                       channel_names, channel_colors, buf.dtype))
+    return path
+
+
+def read_ome_zarr_level(path: str, level: int = 0) -> np.ndarray:
+    """Read one level back into a dense array (used by the tests; zarr itself is not installed)."""
+    ldir = os.path.join(path, str(level))
+    with open(os.path.join(ldir, ".zarray")) as fh:
+        za = json.load(fh)
+    shape, chunks = za["shape"], za["chunks"]
+    dtype = np.dtype(za["dtype"])
+    out = np.zeros(shape, dtype=dtype)
+    grid = [-(-s // c) for s, c in zip(shape, chunks)]
+    for idx in np.ndindex(*grid):
+        p = os.path.join(ldir, *[str(i) for i in idx])
+        if not os.path.exists(p):
+            continue
+        with open(p, "rb") as fh:
+            raw = fh.read()
+        if za["compressor"]:
+            raw = zlib.decompress(raw)
+        blk = np.frombuffer(raw, dtype=dtype).reshape(chunks)
+        sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, shape))
+        out[sl] = blk[tuple(slice(0, s.stop - s.start) for s in sl)]
+    return out

@@ -1,0 +1,505 @@
+"""``StitcherProcess`` -- host-side mirror of the reference's orchestrator for the hot path.
+
+Same class name, constructor, queue protocol and method names as the reference's
+``stitcher_process.StitcherProcess`` (stitcher_process.py:61-2037), so code written against the
+reference (its CLI/GUI, ``save_region_test.py``-style harnesses that inject state by attribute
+assignment) drives this class unchanged.  The L1 methods -- ``normalize_image``,
+``calculate_horizontal_shift`` / ``calculate_vertical_shift`` / ``calculate_shifts``,
+``apply_flatfield_correction``, ``stitch_region`` -- call libstitchb200 through ``_ffi``; there is
+no NumPy fallback (no CUDA device -> RuntimeError).  Everything else here is host glue written
+from the reference's *behaviour* (file layout, ordering and rounding rules are cited inline).
+
+Out of scope: BaSiC flat-field *fitting*, OME-TIFF / bioio / aicsimageio /
+pyvips writers, pyramid merges, HCS plate merges.  ``get_flatfields`` uses BaSiCPy when it is
+installed and otherwise asks for ``set_flatfields``; ``.ome.zarr`` output goes through the minimal
+NGFF writer in ``ome_zarr_writer``.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import sys
+import time
+from multiprocessing import Process
+from queue import Empty
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _ffi
+from . import geometry as geo
+from .stitcher_parameters import StitchingParameters
+
+IMAGE_SUFFIXES = (".bmp", ".tiff", "tif", "jpg", "jpeg", "png")     # as written in the reference (:285)
+CHANNEL_COLORS = (("405", 0x0000FF), ("488", 0x00FF00), ("561", 0xFFCF00), ("638", 0xFF0000), ("730", 0x770000),
+                  ("_B", 0x0000FF), ("_G", 0x00FF00), ("_R", 0xFF0000))
+
+
+def read_image(path: str) -> np.ndarray:
+    """Decode one tile (what ``dask_imread(path)[0]`` yields in the reference, :338/:731/:913)."""
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if img is None:
+        raise FileNotFoundError(path)
+    if img.ndim == 3 and img.shape[2] == 3:
+        img = img[:, :, ::-1]          # OpenCV decodes BGR; the reference's readers give RGB
+    return np.ascontiguousarray(img)
+
+
+class StitcherProcess(Process):
+    def __init__(self, params: StitchingParameters, progress_queue, status_queue, complete_queue, stop_event):
+        super().__init__()
+        self.progress_queue, self.status_queue = progress_queue, status_queue
+        self.complete_queue, self.stop_event = complete_queue, stop_event
+        self.params = params
+        self.input_folder = params.input_folder
+        self.output_folder = params.stitched_folder
+        self.output_format = params.output_format
+        self.merge_timepoints = getattr(params, "merge_timepoints", False)
+        self.merge_hcs_regions = getattr(params, "merge_hcs_regions", False)
+        self.per_timepoint_region_output_template = os.path.join(
+            self.output_folder, "{timepoint}_stitched", "{region}_stitched" + self.output_format)
+        self.apply_flatfield = params.apply_flatfield
+        self.use_registration = params.use_registration
+        self.registration_channel = params.registration_channel if self.use_registration else ""
+        self.registration_z_level = params.registration_z_level if self.use_registration else 0
+        self.dynamic_registration = getattr(params, "dynamic_registration", False)
+        self.scan_pattern = params.scan_pattern
+        self.blend_mode = getattr(params, "blend_mode", "paste")
+        self.upsample_factor = int(getattr(params, "upsample_factor", 10))
+        self.registration_precision = getattr(params, "registration_precision", "auto")
+        self.device = int(getattr(params, "device", 0))
+        self._ctx: Optional[_ffi.Context] = None
+        self._flat_dirty = True
+        self.init_stitching_parameters()
+
+    # ------------------------------------------------------------------ state / IPC (reference :146-230)
+    def init_stitching_parameters(self):
+        self.pixel_size_um = None
+        self.acquisition_params = None
+        self.timepoints: List[str] = []
+        self.regions: List[str] = []
+        self.channel_names: List[str] = []
+        self.monochrome_channels: List[str] = []
+        self.monochrome_colors: List[int] = []
+        self.num_z = self.num_c = self.num_t = 1
+        self.input_height = self.input_width = 0
+        self.num_pyramid_levels = 5
+        self.flatfields: Dict[int, np.ndarray] = {}
+        self.acquisition_metadata: Dict[tuple, dict] = {}
+        self.dtype = np.uint16
+        self.chunks = (1, 1, 1, 2048, 2048)
+        self.h_shift = (0, 0)
+        if self.scan_pattern == "S-Pattern":
+            self.h_shift_rev = (0, 0)
+            self.h_shift_rev_odd = 0
+        self.v_shift = (0, 0)
+        self.x_positions = set()
+        self.y_positions = set()
+        self.pixel_binning = 1
+
+    def emit_progress(self, current: int, total: int):
+        if self.progress_queue is None:
+            print(f"PROGRESS: {(current, total)}")
+        else:
+            self.progress_queue.put(("progress", (current, total)))
+
+    def emit_status(self, status: str, is_saving: bool = False):
+        if self.status_queue is None:
+            print(f"STATUS: {status}")
+        else:
+            self.status_queue.put(("status", (status, is_saving)))
+
+    def emit_complete(self, output_path: str, dtype):
+        if self.complete_queue is None:
+            print("COMPLETE:")
+        else:
+            self.complete_queue.put(("complete", (output_path, dtype)))
+
+    def check_stop(self):
+        """Cooperative stop, polled per region (the reference polls per tile; a region is one kernel launch)."""
+        if self.stop_event is not None and self.stop_event.is_set():
+            print("Stop event detected, terminating process...")
+            self.cleanup()
+            sys.exit(0)
+
+    def cleanup(self):
+        for q in (self.progress_queue, self.status_queue, self.complete_queue):
+            if q is None:
+                continue
+            try:
+                while not q.empty():
+                    q.get_nowait()
+            except (Empty, OSError):
+                pass
+        if self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None
+        self.emit_status("Process Stopped...")
+
+    # ------------------------------------------------------------------ CUDA context (lazy: created in the worker)
+    @property
+    def ctx(self) -> _ffi.Context:
+        if self._ctx is None:
+            self._ctx = _ffi.Context(self.device)        # raises without a CUDA device: no CPU fallback
+            self._flat_dirty = True
+        return self._ctx
+
+    def set_flatfields(self, flatfields: Dict[int, np.ndarray]):
+        """Install per-channel-index flatfields (what ``get_flatfields`` produces, :524)."""
+        self.flatfields = dict(flatfields)
+        self._flat_dirty = True
+
+    def _sync_fields(self):
+        if self._flat_dirty:
+            self.ctx.clear_fields()
+            for c, ff in self.flatfields.items():
+                self.ctx.set_flatfield(int(c), np.asarray(ff))
+            self._flat_dirty = False
+
+    # ------------------------------------------------------------------ metadata (reference :232-421)
+    def get_timepoints(self):
+        self.timepoints = sorted((d for d in os.listdir(self.input_folder)
+                                  if d.isdigit() and os.path.isdir(os.path.join(self.input_folder, d))), key=int)
+        return self.timepoints
+
+    def extract_acquisition_parameters(self):
+        with open(os.path.join(self.input_folder, "acquisition parameters.json")) as fh:
+            self.acquisition_params = json.load(fh)
+
+    def get_pixel_size(self):
+        p = self.acquisition_params
+        self.pixel_binning = p.get("pixel_binning", 1)
+        obj_focal_length_mm = p["objective"]["tube_lens_f_mm"] / p["objective"]["magnification"]
+        self.pixel_size_um = p["sensor_pixel_size_um"] / (p["tube_lens_mm"] / obj_focal_length_mm)
+
+    def parse_acquisition_metadata(self):
+        """File names ``<region>_<fov>_<z>_<channel>.<ext>`` matched to coordinates.csv rows (:261-371).
+        Dict insertion order == sorted file names: it is the paste order of ``stitch_region``."""
+        import pandas as pd
+        self.acquisition_metadata = {}
+        regions, channels = set(), set()
+        max_z = max_fov = 0
+        for timepoint in self.timepoints:
+            folder = os.path.join(self.input_folder, str(timepoint))
+            try:
+                df = pd.read_csv(os.path.join(folder, "coordinates.csv"))
+            except FileNotFoundError:
+                print(f"Warning: coordinates.csv not found for timepoint {timepoint}")
+                continue
+            cols = list(df.columns)
+            ix, iy, iz = cols.index("x (mm)"), cols.index("y (mm)"), cols.index("z (um)")
+            rows = {(str(r[cols.index("region")]), int(r[cols.index("fov")]), int(r[cols.index("z_level")])): r
+                    for r in reversed(list(df.itertuples(index=False, name=None)))}     # first match wins (:303)
+            files = sorted(f for f in os.listdir(folder)
+                           if f.endswith(IMAGE_SUFFIXES) and not f.startswith(".") and "focus_camera" not in f)
+            for name in files:
+                parts = name.split("_", 3)
+                region, fov, z_level = parts[0], int(parts[1]), int(parts[2])
+                channel = os.path.splitext(parts[3])[0].replace("_", " ").replace("full ", "full_")
+                row = rows.get((region, fov, z_level))
+                if row is None:
+                    print(f"Warning: No coordinates for {name}")
+                    continue
+                self.acquisition_metadata[(int(timepoint), region, fov, z_level, channel)] = {
+                    "filepath": os.path.join(folder, name), "x": row[ix], "y": row[iy], "z": row[iz],
+                    "channel": channel, "z_level": z_level, "region": region, "fov_idx": fov, "t": int(timepoint)}
+                regions.add(region)
+                channels.add(channel)
+                max_z, max_fov = max(max_z, z_level), max(max_fov, fov)
+        self.regions, self.channel_names = sorted(regions), sorted(channels)
+        self.num_t, self.num_z, self.num_fovs_per_region = len(self.timepoints), max_z + 1, max_fov + 1
+        first_key = next(iter(self.acquisition_metadata))
+        first = read_image(self.acquisition_metadata[first_key]["filepath"])
+        self.dtype = first.dtype
+        self.input_height, self.input_width = first.shape[:2]
+        self.monochrome_channels = []
+        t0, r0, f0, z0, _ = first_key
+        for channel in self.channel_names:
+            img = read_image(self.acquisition_metadata[(t0, r0, f0, z0, channel)]["filepath"])
+            if img.ndim == 3 and img.shape[2] == 3:
+                base = channel.split("_")[0]
+                self.monochrome_channels += [f"{base}_R", f"{base}_G", f"{base}_B"]
+            else:
+                self.monochrome_channels.append(channel)
+        self.num_c = len(self.monochrome_channels)
+        self.monochrome_colors = [self.get_channel_color(n) for n in self.monochrome_channels]
+
+    def get_region_data(self, t, region):
+        t = int(t)
+        data = {k: v for k, v in self.acquisition_metadata.items() if k[0] == t and k[1] == region}
+        if not data:
+            raise ValueError(f"No data found for timepoint {t}, region {region}")
+        return data
+
+    def get_channel_color(self, channel_name):
+        for key, color in CHANNEL_COLORS:
+            if key in channel_name:
+                return color
+        return 0xFFFFFF
+
+    def get_rows_and_columns(self):
+        return sorted({r[0] for r in self.regions}), sorted({r[1:] for r in self.regions})
+
+    # ------------------------------------------------------------------ geometry (reference :423-503)
+    def _lattice(self) -> Optional[geo.Lattice]:
+        if not self.use_registration:
+            return None
+        s = self.scan_pattern == "S-Pattern"
+        return geo.Lattice(tuple(self.h_shift), tuple(self.v_shift), tuple(getattr(self, "h_shift_rev", (0, 0))),
+                           int(getattr(self, "h_shift_rev_odd", 0)), s)
+
+    def calculate_output_dimensions(self, timepoint, region):
+        data = self.get_region_data(int(timepoint), region)
+        self.x_positions = sorted({v["x"] for v in data.values()})
+        self.y_positions = sorted({v["y"] for v in data.values()})
+        width, height = geo.canvas_size(self.input_width, self.input_height, self.x_positions, self.y_positions,
+                                        self.pixel_size_um, self._lattice())
+        max_dim = 1
+        if len(self.regions) > 1:
+            rows, cols = self.get_rows_and_columns()
+            max_dim = max(len(rows), len(cols))
+        self.num_pyramid_levels = geo.pyramid_levels(width, height, len(self.regions), max_dim)
+        return width, height
+
+    def init_output(self, timepoint, region):
+        """The reference returns a lazy zero canvas; here the canvas is produced whole by ``stitch_region``."""
+        width, height = self.calculate_output_dimensions(timepoint, region)
+        return np.zeros((1, self.num_c, self.num_z, height, width), dtype=self.dtype)
+
+    # ------------------------------------------------------------------ flat-field estimation (out of scope)
+    def get_flatfields(self):
+        try:
+            from basicpy import BaSiC      # noqa: F401
+        except ImportError as exc:
+            raise RuntimeError("flat-field *fitting* (BaSiCPy) is outside this package; install basicpy or provide "
+                               "the fields with set_flatfields({channel_index: HxW array})") from exc
+        import random
+        for channel in self.channel_names:
+            self.check_stop()
+            self.emit_status(f"Calculating Flatfield... ({channel})")
+            paths = [v["filepath"] for v in self.acquisition_metadata.values() if v["channel"] == channel]
+            random.shuffle(paths)
+            images = np.array([read_image(p) for p in paths[:48]])
+            basic = BaSiC(get_darkfield=False, smoothness_flatfield=1)
+            basic.fit(images)
+            self.flatfields[self.monochrome_channels.index(channel)] = basic.flatfield
+        self._flat_dirty = True
+
+    # ------------------------------------------------------------------ registration (reference :573-737, :844-855)
+    def normalize_image(self, img):
+        """Whole-tile min/max stretch in float64 with truncating cast (:844-855) -- ``sb_normalize``."""
+        return self.ctx.normalize(np.ascontiguousarray(img, dtype=np.uint16))
+
+    def _precision(self) -> int:
+        return {"auto": _ffi.SB_PREC_AUTO, "float32": _ffi.SB_PREC_F32, "float64": _ffi.SB_PREC_F64}[self.registration_precision]
+
+    def _register(self, pairs, max_x_overlap, max_y_overlap):
+        shape = pairs[0][0].shape
+        return self.ctx.register_pairs([(np.ascontiguousarray(a), np.ascontiguousarray(b), d) for a, b, d in pairs],
+                                       shape, max_x_overlap, max_y_overlap, upsample_factor=self.upsample_factor,
+                                       precision=self._precision())
+
+    def calculate_horizontal_shift(self, img_left, img_right, max_overlap):
+        """(:664-685) -> ``(round(shift[0]), round(shift[1] - strip_width))``."""
+        r = self._register([(img_left, img_right, _ffi.SB_DIR_HORIZONTAL)], max_overlap, max_overlap)[0]
+        return r["dy"], r["dx"]
+
+    def calculate_vertical_shift(self, img_top, img_bot, max_overlap):
+        """(:687-708) -> ``(round(shift[0] - strip_height), round(shift[1]))``."""
+        r = self._register([(img_top, img_bot, _ffi.SB_DIR_VERTICAL)], max_overlap, max_overlap)[0]
+        return r["dy"], r["dx"]
+
+    def get_tile(self, t, region, x, y, channel, z_level):
+        for value in self.get_region_data(int(t), str(region)).values():
+            if value["x"] == x and value["y"] == y and value["channel"] == channel and value["z_level"] == z_level:
+                try:
+                    return read_image(value["filepath"])
+                except FileNotFoundError:
+                    print(f"Warning: Tile file not found: {value['filepath']}")
+                    return None
+        print(f"Warning: No matching tile found for region {region}, x={x}, y={y}, channel={channel}, z={z_level}")
+        return None
+
+    def calculate_shifts(self, t, region):
+        """The 2 (3 for S-Pattern) centre pairs of the first region, one batched GPU call (:573-662)."""
+        self.h_shift = (0, 0)
+        self.v_shift = (0, 0)
+        if not self.registration_channel or self.registration_channel not in self.channel_names:
+            if self.registration_channel:
+                print(f"Warning: Registration channel '{self.registration_channel}' not found")
+            self.registration_channel = self.channel_names[0]
+        self.emit_status("Calculating Registration Shifts...")
+        self.calculate_output_dimensions(int(t), region)
+        xs, ys = list(self.x_positions), list(self.y_positions)
+        ov_x, ov_y = geo.strip_overlaps(self.input_width, self.input_height, xs, ys, self.pixel_size_um, self.pixel_binning)
+        s_pat = self.scan_pattern == "S-Pattern"
+        plan, rev_odd = geo.center_pairs(xs, ys, s_pat)
+        if self.dynamic_registration:
+            # extension behind the reference's declared-but-unused flag (stitcher_parameters.py:24): register EVERY
+            # adjacent pair of the region in one batch and keep the per-direction median (lower median, an observed value)
+            plan = []
+            for kind, (r0, c0), (r1, c1) in geo.grid_pairs(len(ys), len(xs)):
+                if kind == "h" and s_pat and r0 % 2 == int(rev_odd):
+                    kind = "h_rev"
+                plan.append((kind, (xs[c0], ys[r0]), (xs[c1], ys[r1])))
+        pairs, kinds = [], []
+        for kind, a_xy, b_xy in plan:
+            a = self.get_tile(t, region, a_xy[0], a_xy[1], self.registration_channel, self.registration_z_level)
+            b = self.get_tile(t, region, b_xy[0], b_xy[1], self.registration_channel, self.registration_z_level)
+            if a is None or b is None:
+                print(f"Warning: Missing tiles for {kind} shift calculation in region {region}.")
+                continue
+            pairs.append((a, b, _ffi.SB_DIR_VERTICAL if kind == "v" else _ffi.SB_DIR_HORIZONTAL))
+            kinds.append(kind)
+        if pairs:
+            found = {"h": [], "v": [], "h_rev": []}
+            for kind, r in zip(kinds, self._register(pairs, ov_x, ov_y)):
+                found[kind].append((r["dy"], r["dx"]))
+            self.registration_results = found
+
+            def pick(lst):
+                dys, dxs = sorted(p[0] for p in lst), sorted(p[1] for p in lst)
+                return dys[(len(dys) - 1) // 2], dxs[(len(dxs) - 1) // 2]
+            if found["h"]:
+                self.h_shift = pick(found["h"])
+            if found["v"]:
+                self.v_shift = pick(found["v"])
+            if found["h_rev"]:
+                self.h_shift_rev = pick(found["h_rev"])
+                self.h_shift_rev_odd = rev_odd
+        print(f"Calculated Shifts - Horizontal: {self.h_shift}, Vertical: {self.v_shift}")
+
+    # ------------------------------------------------------------------ fusion (reference :739-956)
+    def apply_flatfield_correction(self, tile, channel_idx):
+        """``(tile / flatfield).clip(0, max).astype(dtype)`` (:828-842) -- ``sb_flatfield_apply``."""
+        if channel_idx not in self.flatfields:
+            return tile
+        self._sync_fields()
+        return self.ctx.flatfield_apply(int(channel_idx), np.ascontiguousarray(tile, dtype=np.uint16))
+
+    def _tile_planes(self, tile: np.ndarray, channel: str):
+        """(:739-769): mono -> one plane; H x W x 3 -> <ch>_R/_G/_B planes; 1 x H x W -> squeezed."""
+        if tile.ndim == 2:
+            return [(self.monochrome_channels.index(channel), tile)]
+        if tile.ndim == 3 and tile.shape[2] == 3:
+            base = channel.split("_")[0]
+            return [(self.monochrome_channels.index(f"{base}_{c}"), np.ascontiguousarray(tile[:, :, i]))
+                    for i, c in enumerate("RGB")]
+        if tile.ndim == 3 and tile.shape[0] == 1:
+            return [(self.monochrome_channels.index(channel), tile[0])]
+        raise ValueError(f"Unexpected tile shape: {tile.shape}")
+
+    def stitch_region(self, timepoint, region):
+        """One region -> ``(1, C, Z, Hc, Wc)`` NumPy canvas, ONE ``sb_fuse_region`` call (:883-956)."""
+        start = time.time()
+        try:
+            data = self.get_region_data(int(timepoint), region)
+            width, height = self.calculate_output_dimensions(timepoint, region)
+            lattice = self._lattice()
+            xs, ys = list(self.x_positions), list(self.y_positions)
+            self.emit_status(f"Stitching... (Timepoint:{timepoint} Region:{region})")
+            self.check_stop()
+            job, keep = [], []
+            for key, info in data.items():                 # insertion order == sorted file names == paste order
+                try:
+                    tile = read_image(info["filepath"])
+                except Exception as exc:                   # the reference reports and skips (:912-916)
+                    self.emit_status(f"Error Loading Image {info['filepath']}: {exc}")
+                    continue
+                p = geo.place_tile(info["x"], info["y"], self.input_width, self.input_height, xs, ys,
+                                   self.pixel_size_um, lattice)
+                for c, plane in self._tile_planes(tile, key[4]):
+                    plane = np.ascontiguousarray(plane, dtype=np.uint16)
+                    keep.append(plane)
+                    job.append((plane, p.x, p.y, c, key[3], p.crop_t, p.crop_b, p.crop_l, p.crop_r))
+            out = np.empty((1, self.num_c, self.num_z, height, width), dtype=np.uint16)
+            if self.apply_flatfield:
+                self._sync_fields()
+            ov = geo.strip_overlaps(self.input_width, self.input_height, xs, ys, self.pixel_size_um, 2) \
+                if len(xs) > 1 and len(ys) > 1 else (0, 0)
+            blend = _ffi.BLEND_MODES[self.blend_mode]
+            if blend != _ffi.SB_BLEND_PASTE:               # blending needs the overlaps: no seam crops
+                job = [t[:5] + (0, 0, 0, 0) for t in job]
+            self.ctx.fuse_region(job, (self.input_height, self.input_width), (self.num_c, self.num_z, height, width),
+                                 out=out, apply_flatfield=self.apply_flatfield, blend=blend, blend_ov=ov)
+            self.emit_progress(len(data), len(data))
+            print(f"(Timepoint:{timepoint}, Region:{region}) Complete Stitching in {time.time() - start:.1f}s\n")
+            return out
+        except Exception as exc:
+            if self.status_queue is not None:
+                self.status_queue.put(("error", f"Error stitching region {region}: {exc}"))
+            raise
+
+    def place_single_channel_tile(self, stitched_region, tile, x_pixel, y_pixel, z_level, channel_idx, t):
+        """Per-tile form of the paste (:771-826), kept for callers that place tiles one by one.  The flat-field
+        division runs on the GPU; the slice assignment itself is a host copy into the caller's array."""
+        if stitched_region.ndim != 5:
+            raise ValueError(f"Unexpected stitched_region shape: {stitched_region.shape}. Expected 5D array (t, c, z, y, x).")
+        if self.apply_flatfield:
+            tile = self.apply_flatfield_correction(tile, channel_idx)
+        if self.use_registration:
+            # row_index / col_index are set by the caller, as in the reference's stitch_region (:920-921)
+            xs, ys = list(self.x_positions), list(self.y_positions)
+            p = geo.place_tile(xs[self.col_index], ys[self.row_index], self.input_width, self.input_height, xs, ys,
+                               self.pixel_size_um, self._lattice())
+            tile = tile[p.crop_t:tile.shape[0] - p.crop_b, p.crop_l:tile.shape[1] - p.crop_r]
+            x_pixel += p.crop_l
+            y_pixel += p.crop_t
+        y_end = min(y_pixel + tile.shape[0], stitched_region.shape[3])
+        x_end = min(x_pixel + tile.shape[1], stitched_region.shape[4])
+        stitched_region[0, channel_idx, z_level, y_pixel:y_end, x_pixel:x_end] = tile[:y_end - y_pixel, :x_end - x_pixel]
+
+    def place_tile(self, stitched_region, tile, x_pixel, y_pixel, z_level, channel, t):
+        for c, plane in self._tile_planes(tile, channel):
+            self.place_single_channel_tile(stitched_region, plane, x_pixel, y_pixel, z_level, c, 0)
+
+    # ------------------------------------------------------------------ output
+    def save_region_ome_zarr(self, timepoint, region, stitched_region):
+        from .ome_zarr_writer import write_ome_zarr
+        path = self.per_timepoint_region_output_template.format(timepoint=timepoint, region=region)
+        dz = self.acquisition_params.get("dz(um)", 1.0) if self.acquisition_params else 1.0
+        write_ome_zarr(path, np.asarray(stitched_region), pixel_size_um=self.pixel_size_um, dz_um=dz,
+                       channel_names=self.monochrome_channels, channel_colors=self.monochrome_colors,
+                       num_levels=self.num_pyramid_levels, chunks=self.chunks)
+        return path
+
+    def run(self):
+        """Same sequence as the reference's ``run`` (:1959-2037)."""
+        stime = time.time()
+        try:
+            self.emit_status("Extracting Acquisition Metadata...")
+            self.get_timepoints()
+            self.extract_acquisition_parameters()
+            self.get_pixel_size()
+            self.parse_acquisition_metadata()
+            os.makedirs(self.output_folder, exist_ok=True)
+            last_path = ""
+            if self.apply_flatfield and not self.flatfields:
+                self.get_flatfields()
+            if self.use_registration:
+                self.calculate_shifts(self.timepoints[0], self.regions[0])
+            for timepoint in self.timepoints:
+                self.check_stop()
+                os.makedirs(os.path.join(self.output_folder, f"{timepoint}_stitched"), exist_ok=True)
+                for region in self.regions:
+                    self.check_stop()
+                    stitched = self.stitch_region(timepoint, region)
+                    if not self.output_format.endswith(".zarr"):
+                        raise RuntimeError("OME-TIFF output relies on the reference's third-party writers "
+                                           "(out of scope, SURVEY.md section 2); use .ome.zarr")
+                    self.emit_status(f"Saving... (Timepoint:{timepoint} Region:{region})", is_saving=True)
+                    last_path = self.save_region_ome_zarr(timepoint, region, stitched)
+            self.check_stop()
+            self.emit_complete(last_path, self.dtype)
+            print(f"Processing complete. Total time: {time.time() - stime:.1f}s")
+        except Exception as exc:
+            print(f"Error in StitcherProcess: {exc}")
+            if self.status_queue is not None:
+                self.status_queue.put(("error", str(exc)))
+            raise
+        finally:
+            if self._ctx is not None:
+                self._ctx.close()
+                self._ctx = None

@@ -1,0 +1,203 @@
+"""CPU-side tests of the host mirror: parameters, Squid-layout parsing, placement geometry against the
+reference-generated goldens, the OME-Zarr writer, the CLI flag surface, and that the C-ABI library
+exports every symbol include/stitchb200.h declares (no compute calls: there is no GPU here)."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SMALL_GOLDENS, load_golden
+from image_stitcher_b200 import geometry as geo
+from image_stitcher_b200 import ome_zarr_writer as ozw
+from image_stitcher_b200.stitcher_parameters import StitchingParameters
+from oracle import synth
+
+
+# ------------------------------------------------------------------------------------------ C ABI
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "stitchb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_bound_exports():
+    from image_stitcher_b200 import _ffi
+    assert set(_header_functions()) == set(_ffi.EXPORTS)
+
+
+def test_library_loads_and_exports_every_header_symbol():
+    from image_stitcher_b200 import _ffi, build
+    lib_path = build.build(force=False)
+    lib = ctypes.CDLL(lib_path)
+    missing = [s for s in _header_functions() if not hasattr(lib, s)]
+    assert not missing, missing
+    h = _ffi.load_library()
+    assert h.sb_version() == 1
+    assert h.sb_canvas_pitch(3891) == 3904 and h.sb_canvas_pitch(64) == 64
+    assert h.sb_chunked_plane_elems(3891, 3891, 2048, 2048) == 4 * 2048 * 2048
+
+
+def test_struct_layouts_match_the_header():
+    """sizeof of the ctypes mirrors == what a C compiler gives for include/stitchb200.h."""
+    import subprocess
+    import tempfile
+    from image_stitcher_b200 import _ffi
+    code = ('#include "stitchb200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",sizeof(sb_tile),'
+            'sizeof(sb_fuse_job),sizeof(sb_pair),sizeof(sb_pair_result),sizeof(sb_register_job));return 0;}')
+    with tempfile.TemporaryDirectory() as tmp:
+        c = os.path.join(tmp, "s.c")
+        open(c, "w").write(code)
+        exe = os.path.join(tmp, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(v) for v in subprocess.check_output([exe]).split()]
+    mirrors = [_ffi.SbTile, _ffi.SbFuseJob, _ffi.SbPair, _ffi.SbPairResult, _ffi.SbRegisterJob]
+    assert sizes == [ctypes.sizeof(m) for m in mirrors]
+
+
+def test_no_device_means_loud_failure_not_a_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from image_stitcher_b200 import _ffi
+    with pytest.raises(RuntimeError, match="sb_create"):
+        _ffi.Context(0)
+
+
+# ------------------------------------------------------------------------------------------ parameters / CLI
+def test_parameters_roundtrip_and_validation(tmp_path):
+    p = StitchingParameters(input_folder=str(tmp_path), use_registration=True, registration_channel="x",
+                            apply_flatfield=True, scan_pattern="S-Pattern")
+    p.validate()
+    assert p.stitched_folder == p.stitched_folder            # stamp frozen (reference defect not copied)
+    assert p.stitched_folder.startswith(str(tmp_path) + "_stitched_")
+    j = tmp_path / "p.json"
+    p.to_json(str(j))
+    q = StitchingParameters.from_json(str(j))
+    assert q.to_dict() == p.to_dict()
+    assert StitchingParameters.from_dict({"input_folder": str(tmp_path), "unknown_key": 1}).output_format == ".ome.zarr"
+    for bad in (dict(output_format=".png"), dict(scan_pattern="zigzag"), dict(blend_mode="max"),
+                dict(use_registration=True, registration_z_level=-1), dict(upsample_factor=0)):
+        with pytest.raises(ValueError):
+            StitchingParameters(input_folder=str(tmp_path), **bad).validate()
+    with pytest.raises(ValueError):
+        StitchingParameters(input_folder=str(tmp_path / "missing")).validate()
+
+
+def test_cli_flag_surface_matches_reference(tmp_path):
+    from image_stitcher_b200 import stitcher_process_cli as cli
+    a = cli.parse_args(["-i", str(tmp_path), "-r", "-ff", "-rc", "Fluorescence 488 nm Ex", "-rz", "1", "-s", "S-Pattern",
+                        "-f", ".ome.zarr", "--dynamic-registration", "--merge-timepoints", "--merge-hcs-regions"])
+    p = cli.create_params(a)
+    assert (p.use_registration, p.apply_flatfield, p.registration_channel, p.registration_z_level) == \
+        (True, True, "Fluorescence 488 nm Ex", 1)
+    assert p.scan_pattern == "S-Pattern" and p.dynamic_registration and p.merge_timepoints and p.merge_hcs_regions
+    assert p.blend_mode == "paste" and p.upsample_factor == 10          # extension defaults = reference behaviour
+    pj = tmp_path / "params.json"
+    json.dump({"input_folder": str(tmp_path), "use_registration": True}, open(pj, "w"))
+    assert cli.create_params(cli.parse_args(["-i", "ignored", "--params-json", str(pj)])).use_registration
+
+
+# ------------------------------------------------------------------------------------------ Squid layout parsing
+def _stitcher(root, **params):
+    from image_stitcher_b200.stitcher_process import StitcherProcess
+    s = StitcherProcess(StitchingParameters(input_folder=root, **params), None, None, None, None)
+    s.get_timepoints()
+    s.extract_acquisition_parameters()
+    s.get_pixel_size()
+    s.parse_acquisition_metadata()
+    return s
+
+
+@pytest.mark.parametrize("name", SMALL_GOLDENS)
+def test_parse_squid_layout_and_geometry_match_reference_golden(name, tmp_path, capsys):
+    g, st, tiles, kw = load_golden(name)
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    s = _stitcher(root, use_registration=st.use_registration, apply_flatfield=st.apply_flatfield,
+                  scan_pattern=st.scan_pattern, registration_channel=st.registration_channel)
+    assert s.timepoints == ["0"] and s.regions == ["A1"]
+    assert s.monochrome_channels == [str(c) for c in g["monochrome_channels"]]
+    assert s.pixel_size_um == float(g["pixel_size_um"])
+    assert (s.input_height, s.input_width) == (kw["tile_h"], kw["tile_w"]) and s.dtype == np.uint16
+    assert s.num_z == kw.get("num_z", 1)
+    # paste order == sorted file names == the order the reference iterated (golden tile_names)
+    order = [os.path.basename(v["filepath"]) for v in s.get_region_data(0, "A1").values()]
+    assert order == [str(n) for n in g["tile_names"]]
+    # canvas size with the reference's registered shifts (incl. its height over-allocation quirk)
+    s.h_shift, s.v_shift = tuple(int(v) for v in g["h_shift"]), tuple(int(v) for v in g["v_shift"])
+    if st.scan_pattern == "S-Pattern":
+        s.h_shift_rev = tuple(int(v) for v in g["h_shift_rev"])
+        s.h_shift_rev_odd = int(g["h_shift_rev_odd"])
+    w, h = s.calculate_output_dimensions(0, "A1")
+    assert (1, s.num_c, s.num_z, h, w) == tuple(int(v) for v in g["canvas_shape"])
+
+
+def test_parse_skips_hidden_and_focus_camera_and_handles_fov_ge_10(tmp_path):
+    st, tiles, _ = synth.make_region(3, 4, 32, 32, seed=3, jitter=0, region="B2")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"B2": tiles})
+    import cv2
+    cv2.imwrite(os.path.join(root, "0", ".hidden_0_0_x.tiff"), tiles[0].pixels)
+    cv2.imwrite(os.path.join(root, "0", "B2_0_0_focus_camera.tiff"), tiles[0].pixels)
+    s = _stitcher(root)
+    names = [os.path.basename(v["filepath"]) for v in s.get_region_data(0, "B2").values()]
+    assert len(names) == 12 and names == sorted(names)
+    assert names.index("B2_10_0_Fluorescence_488_nm_Ex.tiff") < names.index("B2_2_0_Fluorescence_488_nm_Ex.tiff")
+    with pytest.raises(ValueError):
+        s.get_region_data(0, "nope")
+
+
+def test_strip_overlap_rule_and_center_pairs():
+    px = synth.pixel_size_um()
+    xs = [10.0 + c * 1843 * px / 1000 for c in range(3)]
+    ys = [20.0 + r * 1843 * px / 1000 for r in range(3)]
+    assert geo.strip_overlaps(2048, 2048, xs, ys, px, 2) == (214, 214)      # round(205*1.05)//2*2
+    assert geo.strip_overlaps(2048, 2048, xs, ys, px, 1) == (107, 107)      # the reference's binning-1 regime
+    plan, rev_odd = geo.center_pairs(xs, ys, True)
+    assert [k for k, _, _ in plan] == ["h", "v", "h_rev"] and rev_odd is False
+    assert plan[0][1] == (xs[1], ys[1]) and plan[0][2] == (xs[2], ys[1]) and plan[1][2] == (xs[1], ys[2])
+    assert len(geo.grid_pairs(3, 3)) == 12 and len(geo.grid_pairs(20, 20)) == 760
+
+
+# ------------------------------------------------------------------------------------------ OME-Zarr writer
+@pytest.mark.parametrize("compressor", [None, "zlib"])
+def test_ome_zarr_roundtrip_and_metadata(tmp_path, compressor):
+    rng = np.random.default_rng(0)
+    data = rng.integers(0, 65535, (1, 2, 3, 150, 201), dtype=np.uint16)
+    path = str(tmp_path / "A1_stitched.ome.zarr")
+    ozw.write_ome_zarr(path, data, pixel_size_um=0.752, dz_um=1.5, channel_names=["a 405", "b 488"],
+                       channel_colors=[0x0000FF, 0x00FF00], num_levels=3, chunks=(1, 1, 1, 64, 64), compressor=compressor)
+    for l in range(3):
+        assert np.array_equal(ozw.read_ome_zarr_level(path, l), data[..., ::2 ** l, ::2 ** l])
+    attrs = json.load(open(os.path.join(path, ".zattrs")))
+    ms = attrs["multiscales"][0]
+    assert [a["name"] for a in ms["axes"]] == list("tczyx") and ms["version"] == "0.4"
+    assert ms["datasets"][2]["coordinateTransformations"][0]["scale"] == [1, 1, 1.5, 0.752 * 4, 0.752 * 4]
+    assert [c["color"] for c in attrs["omero"]["channels"]] == ["0000FF", "00FF00"]
+    assert attrs["omero"]["channels"][0]["window"]["end"] == 65535
+    za = json.load(open(os.path.join(path, "0", ".zarray")))
+    assert za["chunks"] == [1, 1, 1, 64, 64] and za["dtype"] == "<u2" and za["dimension_separator"] == "/"
+    # edge chunks are stored full size, zero padded (zarr v2)
+    edge = os.path.join(path, "0", "0", "0", "0", "2", "3")
+    if compressor is None:
+        assert os.path.getsize(edge) == 64 * 64 * 2
+
+
+def test_ome_zarr_from_chunk_ordered_buffer(tmp_path):
+    rng = np.random.default_rng(1)
+    C, Z, H, W, ch = 2, 1, 100, 130, 64
+    dense = rng.integers(0, 65535, (C, Z, H, W), dtype=np.uint16)
+    ncy, ncx = 2, 3
+    buf = np.zeros((C * Z, ncy, ncx, ch, ch), np.uint16)
+    for p in range(C * Z):
+        for iy in range(ncy):
+            for ix in range(ncx):
+                blk = dense[p // Z, p % Z, iy * ch:(iy + 1) * ch, ix * ch:(ix + 1) * ch]
+                buf[p, iy, ix, :blk.shape[0], :blk.shape[1]] = blk
+    path = str(tmp_path / "c.ome.zarr")
+    ozw.write_ome_zarr_chunked(path, buf, (C, Z, H, W), (ch, ch), pixel_size_um=1.0, channel_names=["a", "b"],
+                               channel_colors=[1, 2])
+    assert np.array_equal(ozw.read_ome_zarr_level(path, 0)[0], dense)

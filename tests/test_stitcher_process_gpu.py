@@ -1,0 +1,171 @@
+"""GPU parity of the reference-facing class: ``StitcherProcess`` of this package, driven the way the
+reference's own harness drives its class (construct with queues, call the methods in ``run`` order,
+inject flatfields by attribute) on the SAME on-disk Squid acquisitions that produced the goldens
+(tests/golden/make_golden.py ran the unmodified reference on them).  Bit-exact shifts and canvases."""
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+from conftest import SMALL_GOLDENS, load_golden
+from image_stitcher_b200 import ome_zarr_writer as ozw
+from image_stitcher_b200.stitcher_parameters import StitchingParameters
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(root, st, **extra):
+    from image_stitcher_b200.stitcher_process import StitcherProcess
+    p = StitchingParameters(input_folder=root, use_registration=st.use_registration, apply_flatfield=st.apply_flatfield,
+                            scan_pattern=st.scan_pattern, registration_channel=st.registration_channel, **extra)
+    return StitcherProcess(p, mp.Queue(), mp.Queue(), mp.Queue(), mp.Event())
+
+
+def _drain(q):
+    from queue import Empty
+    out = []
+    while True:
+        try:
+            out.append(q.get(timeout=0.5))
+        except Empty:
+            return out
+
+
+def _prepare(s):
+    s.get_timepoints()
+    s.extract_acquisition_parameters()
+    s.get_pixel_size()
+    s.parse_acquisition_metadata()
+
+
+@pytest.mark.parametrize("name", SMALL_GOLDENS)
+def test_methods_in_run_order_match_reference_golden(name, tmp_path):
+    g, st, tiles, kw = load_golden(name)
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    s = _make(root, st)
+    try:
+        _prepare(s)
+        if st.apply_flatfield:
+            s.set_flatfields(st.flatfields)
+        if st.use_registration:
+            s.calculate_shifts(s.timepoints[0], s.regions[0])
+            assert tuple(s.h_shift) == tuple(int(v) for v in g["h_shift"])
+            assert tuple(s.v_shift) == tuple(int(v) for v in g["v_shift"])
+            if st.scan_pattern == "S-Pattern":
+                assert tuple(s.h_shift_rev) == tuple(int(v) for v in g["h_shift_rev"])
+                assert int(s.h_shift_rev_odd) == int(g["h_shift_rev_odd"])
+        out = s.stitch_region(0, "A1")
+        assert out.shape == tuple(int(v) for v in g["canvas_shape"]) and out.dtype == np.uint16
+        assert np.array_equal(out, g["canvas"])
+        assert "progress" in [m[0] for m in _drain(s.progress_queue)]
+    finally:
+        s.cleanup()
+
+
+def test_single_tile_methods_match_oracle(tmp_path):
+    """normalize_image / calculate_*_shift / apply_flatfield_correction / place_tile one call at a time."""
+    from oracle import stitch_ref as sr
+    g, st, tiles, kw = load_golden("reg_3x3_spattern_flat")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    s = _make(root, st)
+    try:
+        _prepare(s)
+        s.set_flatfields(st.flatfields)
+        a, b = tiles[0].pixels, tiles[1].pixels
+        assert np.array_equal(s.normalize_image(a), sr.normalize_image(a))
+        assert s.calculate_horizontal_shift(a, b, 14) == sr.calculate_horizontal_shift(a, b, 14)
+        assert s.calculate_vertical_shift(a, b, 18) == sr.calculate_vertical_shift(a, b, 18)
+        assert np.array_equal(s.apply_flatfield_correction(a, 1), sr.apply_flatfield_correction(st, a, 1))
+        assert s.apply_flatfield_correction(a, 7) is a                       # no field for that channel: passthrough
+        # per-tile placement API reproduces the batched canvas
+        s.calculate_shifts(0, "A1")
+        ref = s.stitch_region(0, "A1")
+        canvas = s.init_output(0, "A1")
+        xs, ys = list(s.x_positions), list(s.y_positions)
+        from image_stitcher_b200 import geometry as geo
+        for key, info in s.get_region_data(0, "A1").items():
+            s.col_index, s.row_index = xs.index(info["x"]), ys.index(info["y"])
+            p = geo.place_tile(info["x"], info["y"], s.input_width, s.input_height, xs, ys, s.pixel_size_um, s._lattice())
+            from image_stitcher_b200.stitcher_process import read_image
+            s.place_tile(canvas, read_image(info["filepath"]), p.x, p.y, key[3], key[4], 0)
+        assert np.array_equal(canvas, ref)
+    finally:
+        s.cleanup()
+
+
+def test_run_end_to_end_writes_ome_zarr(tmp_path):
+    """BASELINE.json configs[0] in small: 2x2 grid, registration + stitch to OME-Zarr, through ``run()``."""
+    g, st, tiles, kw = load_golden("reg_2x2_mono")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    s = _make(root, st)
+    s.run()                                   # synchronously, like stitcher_cli.py:112
+    kind, (path, dtype) = s.complete_queue.get(timeout=5)
+    assert kind == "complete" and path.endswith("A1_stitched.ome.zarr") and os.path.isdir(path)
+    assert np.array_equal(ozw.read_ome_zarr_level(path, 0), g["canvas"])
+    import json
+    levels = json.load(open(os.path.join(path, ".zattrs")))["multiscales"][0]["datasets"]
+    assert len(levels) == s.num_pyramid_levels          # a7: max(1, ceil(log2(max(Wc, Hc) / 1024)))
+    msgs = [m[1][0] for m in _drain(s.status_queue) if m[0] == "status"]
+    assert any("Registration" in m for m in msgs) and any("Stitching" in m for m in msgs) and any("Saving" in m for m in msgs)
+
+
+def test_dynamic_registration_all_pairs_median(tmp_path):
+    """Extension behind the reference's unused flag: every adjacent pair in one batch, lower median per direction.
+    Each pair's shift must equal the oracle's calculate_*_shift for that pair; the medians follow from them."""
+    from image_stitcher_b200 import geometry as geo
+    from oracle import stitch_ref as sr
+    g, st, tiles, kw = load_golden("reg_2x3_negdrift")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    s = _make(root, st, dynamic_registration=True)
+    try:
+        _prepare(s)
+        s.calculate_shifts(0, "A1")
+        xs, ys = list(s.x_positions), list(s.y_positions)
+        ovx, ovy = geo.strip_overlaps(s.input_width, s.input_height, xs, ys, s.pixel_size_um, s.pixel_binning)
+        by_pos = {(t.x_mm, t.y_mm): t.pixels for t in tiles}
+        exp = {"h": [], "v": []}
+        for kind, (r0, c0), (r1, c1) in geo.grid_pairs(len(ys), len(xs)):
+            a, b = by_pos[(xs[c0], ys[r0])], by_pos[(xs[c1], ys[r1])]
+            exp[kind].append(sr.calculate_horizontal_shift(a, b, ovx) if kind == "h" else sr.calculate_vertical_shift(a, b, ovy))
+        assert s.registration_results["h"] == exp["h"] and s.registration_results["v"] == exp["v"]
+        assert len(exp["h"]) == 4 and len(exp["v"]) == 3
+
+        def lower_median(lst, k):
+            v = sorted(p[k] for p in lst)
+            return v[(len(v) - 1) // 2]
+        assert tuple(s.h_shift) == (lower_median(exp["h"], 0), lower_median(exp["h"], 1))
+        assert tuple(s.v_shift) == (lower_median(exp["v"], 0), lower_median(exp["v"], 1))
+    finally:
+        s.cleanup()
+
+
+def test_errors_flow_to_the_status_queue(tmp_path):
+    g, st, tiles, kw = load_golden("coord_2x2_plain")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    s = _make(root, st)
+    try:
+        _prepare(s)
+        with pytest.raises(ValueError):
+            s.stitch_region(0, "Z9")
+        errors = [m[1] for m in _drain(s.status_queue) if m[0] == "error"]
+        assert errors and "Z9" in errors[0]
+    finally:
+        s.cleanup()
+
+
+def test_stop_event_terminates_before_the_next_region(tmp_path):
+    g, st, tiles, kw = load_golden("coord_2x2_plain")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    s = _make(root, st)
+    _prepare(s)
+    s.stop_event.set()
+    with pytest.raises(SystemExit):
+        s.stitch_region(0, "A1")
