@@ -46,9 +46,10 @@ def parse_args():
     ap.add_argument("--no-flatfield", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the host-buffer leg (default min(steps, 2))")
     ap.add_argument("--host-wells", type=int, default=6, help="distinct wells kept in pinned host memory for e2e")
+    ap.add_argument("--fuse-lanes", type=int, default=3, help="library lanes (streams) the per-well fusion launches rotate over")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-wells", type=int, default=1)
+    ap.add_argument("--cpu-sample-wells", type=int, default=0, help="wells in the CPU sample (0 = one per host core)")
     return ap.parse_args()
 
 
@@ -147,9 +148,43 @@ def cpu_sample(spec, plate_tiles_host, flat_host, n_wells, use_flat, workers=Non
     return pairs, px, t_reg, t_fuse
 
 
+_POOL_STATE = {}
+
+
+def _pool_task(i):
+    """One well of the CPU sample in a forked worker (arrays inherited, nothing pickled but the timings)."""
+    st = _POOL_STATE
+    tiles = st["tiles"]
+    return cpu_sample(st["spec"], tiles[i % len(tiles)][None], st["flat"], 1, st["use_flat"])
+
+
+def cpu_pool_sample(spec, tiles, flat, use_flat, n_tasks, procs):
+    """`n_tasks` wells (cycling over the distinct wells in `tiles`) over `procs` forked worker processes.
+    Returns (pairs, px, wall_seconds, cpu_seconds_registration, cpu_seconds_fusion)."""
+    import multiprocessing as mp
+    _POOL_STATE.update(spec=spec, tiles=tiles, flat=flat, use_flat=use_flat)
+    t0 = time.perf_counter()
+    if procs <= 1:
+        res = [_pool_task(i) for i in range(n_tasks)]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_pool_task, range(n_tasks), chunksize=1)
+    wall = time.perf_counter() - t0
+    return (sum(r[0] for r in res), sum(r[1] for r in res), wall, sum(r[2] for r in res), sum(r[3] for r in res))
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python
-    reference itself cannot travel to the GPU box and its third-party stack is not installed)."""
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores.  The Python
+    reference cannot travel to the GPU box and its third-party stack is not installed, so this is the oracle port
+    (oracle/stitch_ref.py + oracle/pcc_ref.py, validated against the reference itself by tests/golden), one well
+    per worker process over all host cores.  Each step is a bounded sample: `cores` wells of the named plate."""
     if rank != 0:
         return
     from image_stitcher_b200.plate import PlateSpec
@@ -157,11 +192,12 @@ def run_reference(args, rank, world):
     spec = PlateSpec(wells=args.wells, rows=args.grid, cols=args.grid, tile_h=args.tile, tile_w=args.tile,
                      channels=args.channels)
     use_flat = not args.no_flatfield
-    n = args.cpu_sample_wells
-    rng = np.random.default_rng(0)
-    # bounded sample: n wells generated on the host with the oracle's own generator
-    tiles = np.empty((n, spec.rows, spec.cols, spec.channels, 1, spec.tile_h, spec.tile_w), np.uint16)
-    for w in range(n):
+    cores = host_cores()
+    n_tasks = args.cpu_sample_wells if args.cpu_sample_wells > 0 else cores
+    distinct = min(2, n_tasks)
+    # bounded sample: wells generated on the host with the oracle's own generator, reused round-robin by the tasks
+    tiles = np.empty((distinct, spec.rows, spec.cols, spec.channels, 1, spec.tile_h, spec.tile_w), np.uint16)
+    for w in range(distinct):
         st, recs, _ = synth.make_region(spec.rows, spec.cols, spec.tile_h, spec.tile_w, seed=w, jitter=3)
         for t in recs:
             r, c = divmod(t.fov, spec.cols)
@@ -170,26 +206,24 @@ def run_reference(args, rank, world):
     flat = np.stack([synth.vignette(spec.tile_h, spec.tile_w, 0.35, (0.04 * (c + 1), -0.03 * (c + 1)))
                      for c in range(spec.channels)])
     for _ in range(min(args.warmup, 1)):
-        cpu_sample(spec, tiles, flat, 1, use_flat)
-    t0 = time.perf_counter()
+        cpu_pool_sample(spec, tiles, flat, use_flat, min(n_tasks, cores), cores)
     pairs = px = 0
-    t_reg = t_fuse = 0.0
+    wall = t_reg = t_fuse = 0.0
     for _ in range(args.steps):
-        p, x, a, b = cpu_sample(spec, tiles, flat, n, use_flat)
-        pairs += p; px += x; t_reg += a; t_fuse += b
-    total = time.perf_counter() - t0
-    val = px / 1e6 / (t_reg + t_fuse)
+        p, x, w_s, a, b = cpu_pool_sample(spec, tiles, flat, use_flat, n_tasks, cores)
+        pairs += p; px += x; wall += w_s; t_reg += a; t_fuse += b
+    val = px / 1e6 / wall
+    share_reg = t_reg / (t_reg + t_fuse)
+    sample = (f"{n_tasks} of {spec.wells} wells per step ({pairs // args.steps} pairs, {px // args.steps / 1e6:.0f} Mpx), "
+              f"one well per worker process over {cores} cores, arrays in RAM; NumPy/SciPy oracle port of the reference")
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpx/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16 (f64 registration)",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16 pixels; f64 registration",
         "data": "synthetic",
-        "config": {"workload": workload_name(spec, use_flat, args.blend), "sample": f"{n} well(s) per step"},
-        "tile_pairs_per_s": pairs / t_reg, "fusion_mpx_per_s": px / 1e6 / t_fuse,
-        "cpu_baseline": {"value": val, "unit": "Mpx/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{n} well(s) ({pairs // args.steps} pairs, {px // args.steps / 1e6:.0f} Mpx) per step; "
-                                   "NumPy/SciPy oracle port, scipy.fft default workers",
-                         "tile_pairs_per_s": pairs / t_reg, "fusion_mpx_per_s": px / 1e6 / t_fuse},
+        "config": {"workload": workload_name(spec, use_flat, args.blend), "sample": sample},
+        "tile_pairs_per_s": pairs / (wall * share_reg), "fusion_mpx_per_s": px / 1e6 / (wall * (1 - share_reg)),
+        "cpu_baseline": {"value": val, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
@@ -229,10 +263,15 @@ def run_b200(args, rank, world, local_rank):
     planes = spec.channels * spec.num_z
     canvases = torch.empty((spec.wells, planes, Hc, pitch), dtype=torch.int16, device=f"cuda:{local_rank}")
     ovx, ovy = spec.strip_overlaps()
-    # a real (non-default) stream: lane 0 launches on it and the timing events are recorded on it
-    stream = torch.cuda.Stream(device=local_rank)
+    # real (non-default) streams: the library's lanes launch on them and the timing events are recorded on them.
+    # Registration runs on lane 0; the independent per-well fusion launches rotate over `nl` lanes so that the tail
+    # of one persistent kernel overlaps the head of the next.  Lane 0's stream brackets everything (fork/join events).
+    nl = max(1, min(args.fuse_lanes, ctx.num_lanes))
+    streams = [torch.cuda.Stream(device=local_rank) for _ in range(nl)]
+    stream = streams[0]
     torch.cuda.synchronize()
-    ctx.set_lane_stream(0, stream.cuda_stream)
+    for i, st_ in enumerate(streams):
+        ctx.set_lane_stream(i, st_.cuda_stream)
 
     def dev_ptr(w):
         return lambda r, c, ch, z: plate.pool[w, r, c, ch, z].data_ptr()
@@ -256,8 +295,14 @@ def run_b200(args, rank, world, local_rank):
         e0.record(stream)
         last_reg = ctx.register_pairs(all_pairs, (spec.tile_h, spec.tile_w), ovx, ovy, mem=_ffi.SB_MEM_DEVICE, lane=0)
         e1.record(stream)
-        for p in plans:
-            p.run(0)
+        for st_ in streams[1:]:
+            st_.wait_event(e1)                           # fork: the other lanes start after registration
+        for i, p in enumerate(plans):
+            p.run(i % nl)
+        for st_ in streams[1:]:                          # join: lane 0 waits for the other lanes' last launch
+            j = torch.cuda.Event()
+            j.record(st_)
+            stream.wait_event(j)
         e2.record(stream)
         if record is not None:
             record.append((e0, e1, e2))
@@ -309,6 +354,12 @@ def run_b200(args, rank, world, local_rank):
             peaks = json.load(f)
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "fusion_traffic.json")
+    if os.path.exists(tpath) and args.blend == "paste" and use_flat and (args.tile, args.grid, args.channels) == (2048, 3, 4):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
     n_fuse = spec.wells * args.steps
     fuse_launch_ms = fuse_sum / n_fuse
     if args.blend == "paste":
@@ -329,7 +380,8 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": workload_name(spec, use_flat, args.blend), "plates": world,
                    "pairs_per_step": n_pairs * world, "canvas": [planes, Hc, Wc], "strip": [Sh_h, Sw_h],
                    "l2": "inputs (29 GB) and outputs (25 GB) per step exceed L2 (126 MB); no flush needed",
-                   "timing": "CUDA events on the launching stream, max over ranks"},
+                   "timing": "CUDA events on the launching stream (lane 0 brackets the other lanes with fork/join events), max over ranks",
+                   "fuse_lanes": nl},
         "tile_pairs_per_s": n_pairs * args.steps * world / (reg_sum * 1e-3),
         "fusion_mpx_per_s": px_per_step * args.steps * world / 1e6 / (fuse_sum * 1e-3),
         "registration_ms_per_step": reg_sum / args.steps, "fusion_ms_per_step": fuse_sum / args.steps,
@@ -338,8 +390,9 @@ def run_b200(args, rank, world, local_rank):
         "registration_f64_redo_pairs": int(sum(r["precision"] == 1 for r in last_reg)),
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "fuse_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+        "roofline": {"kernel": "fuse_paste_kernel<1>" if (args.blend == "paste" and use_flat) else ("fuse_paste_kernel<0>" if args.blend == "paste" else "fuse_kernel"), "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": "profiles/fusion_traffic.json (ncu --set full, per launch)" if traffic else None,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fuse_launch_ms,
                      "frac_of_spec_8000": achieved / 8000.0},
         "roofline_registration": {"bound": "hbm", "achieved": reg_achieved, "peak": peak_gbs, "unit": "GB/s",
@@ -357,7 +410,8 @@ def run_b200(args, rank, world, local_rank):
             host_tiles[i][...] = plate.pool[i].cpu().numpy().view(np.uint16)
         host_out = [ctx.pinned_empty((1, spec.channels, spec.num_z, Hc, Wc), np.uint16) for _ in range(pipe.depth)]
         e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(1, min(args.steps, 2))
-        ctx.set_lane_stream(0, None)
+        for i in range(nl):
+            ctx.set_lane_stream(i, None)
 
         def e2e_step():
             results = []
@@ -396,15 +450,19 @@ def run_b200(args, rank, world, local_rank):
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = max(1, args.cpu_sample_wells)
-        tiles = plate.pool[:n].cpu().numpy().view(np.uint16)
+        cores = host_cores()
+        n = args.cpu_sample_wells if args.cpu_sample_wells > 0 else cores
+        distinct = max(1, min(n, 4))
+        tiles = plate.pool[:distinct].cpu().numpy().view(np.uint16)
         flat = plate.flat.cpu().numpy()
-        p, x, a, b = cpu_sample(spec, tiles, flat, n, use_flat)
-        out["cpu_baseline"] = {"value": x / 1e6 / (a + b), "unit": "Mpx/s", "cores": os.cpu_count(), "kind": "port",
-                               "sample": f"{n} of {spec.wells} wells ({p} pairs, {x / 1e6:.0f} Mpx), arrays in RAM; "
-                                         "NumPy/SciPy oracle port of the reference, scipy.fft default workers",
-                               "tile_pairs_per_s": p / a, "fusion_mpx_per_s": x / 1e6 / b,
-                               "seconds": a + b}
+        p, x, wall_s, a, b = cpu_pool_sample(spec, tiles, flat, use_flat, n, cores)
+        share = a / (a + b)
+        out["cpu_baseline"] = {"value": x / 1e6 / wall_s, "unit": "Mpx/s", "cores": cores, "kind": "port",
+                               "sample": f"{n} of {spec.wells} wells ({p} pairs, {x / 1e6:.0f} Mpx), one well per worker "
+                                         f"process over {cores} cores, arrays in RAM; NumPy/SciPy oracle port of the "
+                                         "reference (validated against the reference by tests/golden)",
+                               "tile_pairs_per_s": p / (wall_s * share), "fusion_mpx_per_s": x / 1e6 / (wall_s * (1 - share)),
+                               "seconds": wall_s, "cpu_seconds": a + b}
     if rank == 0:
         print(json.dumps(out), flush=True)
     ctx.close()

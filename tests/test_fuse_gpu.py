@@ -166,3 +166,31 @@ def test_errors_are_reported(ctx):
     with pytest.raises(RuntimeError, match="negative"):
         ctx.fuse_region([(np.zeros((8, 8), np.uint16), -4, 0, 0, 0, 0, 0, 0, 0)], (8, 8), (1, 1, 16, 16),
                         out=np.zeros((1, 1, 1, 16, 16), np.uint16))
+
+
+def test_band_sharded_fusion_equals_whole_canvas(ctx):
+    """Multi-GPU partitioning of one big mosaic (shard.fusion_units_for_rank / tiles_for_band): fusing every
+    (plane, chunk-row) band separately -- as ranks would -- reproduces the single-call canvas bit for bit."""
+    from image_stitcher_b200 import shard
+    rng = np.random.default_rng(11)
+    th, tw, C, Z, Hc, Wc = 96, 136, 2, 1, 400, 517
+    job = random_job(rng, 19, th, tw, C, Z, Hc, Wc)
+    flat = rng.uniform(0.6, 1.4, (th, tw)).astype(np.float32)
+    ctx.clear_fields()
+    ctx.set_flatfield(1, flat)
+    whole = np.zeros((1, C, Z, Hc, Wc), np.uint16)
+    ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=whole, apply_flatfield=True)
+    parts = np.full_like(whole, 0x5555)
+    world = 3
+    for rank in range(world):
+        for plane, y0, y1 in shard.fusion_units_for_rank(C * Z, Hc, 128, world, rank):
+            c, z = divmod(plane, Z)
+            sub = [t for t in job if t[3] == c and t[4] == z]
+            band = [(t[0], t[1], t[2], 0, 0, *t[5:]) for t in shard.tiles_for_band(sub, th, y0, y1)]
+            out = np.zeros((1, 1, 1, y1 - y0, Wc), np.uint16)
+            ctx.clear_fields()
+            if c == 1:
+                ctx.set_flatfield(0, flat)
+            ctx.fuse_region(band, (th, tw), (1, 1, y1 - y0, Wc), out=out, apply_flatfield=True)
+            parts[0, c, z, y0:y1] = out[0, 0, 0]
+    assert np.array_equal(parts, whole)
