@@ -433,6 +433,10 @@ def run_b200(args, rank, world, local_rank):
             t = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
+        # parity inside the e2e leg: every well's asynchronously delivered shifts equal the generator's ground truth
+        kinds_ = well_pairs(spec, lambda *a: 0)[1]
+        e2e_reg_ok = sum(all((r["dy"], r["dx"]) == plate.truth[w % hw][k] for r, k in zip(res[w].get(), kinds_))
+                         for w in range(spec.wells))
         # check one well against the device-resident result of the same well
         got = host_out[(spec.wells - 1) % pipe.depth][0].reshape(planes, Hc, Wc)
         src_w = (spec.wells - 1) % hw
@@ -442,8 +446,9 @@ def run_b200(args, rank, world, local_rank):
                       "d2h_bytes_per_step": int(px_per_step * 2), "steps": e2e_steps,
                       "ms_per_step": e2e_s / e2e_steps * 1e3,
                       "tile_pairs_per_s": n_pairs * e2e_steps * world / e2e_s,
-                      "api": "WellPipeline.submit(host tiles) -> host canvas (sb_memcpy_async + sb_register_pairs "
-                             "+ sb_fuse_region over 3 lanes)",
+                      "api": "WellPipeline.submit(pinned host tiles) -> host canvas + shifts (sb_memcpy_async + "
+                             "sb_register_pairs_async + sb_fuse_region, rotating over 3 lanes)",
+                      "registration_truth_wells_ok": f"{e2e_reg_ok}/{spec.wells}",
                       "host_wells_distinct": hw, "matches_device_result": bool(np.array_equal(got, exp))}
     else:
         out["e2e"] = None

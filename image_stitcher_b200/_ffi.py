@@ -28,8 +28,8 @@ EXPORTS = [
     "sb_version", "sb_create", "sb_destroy", "sb_last_error", "sb_kernel_launches", "sb_num_lanes",
     "sb_device_sm_count", "sb_host_alloc", "sb_host_free", "sb_device_alloc", "sb_device_free",
     "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_memcpy_async", "sb_set_flatfield", "sb_set_darkfield", "sb_clear_fields",
-    "sb_flatfield_apply", "sb_fuse_region", "sb_sync", "sb_set_lane_stream", "sb_canvas_pitch",
-    "sb_chunked_plane_elems", "sb_register_pairs", "sb_normalize",
+    "sb_flatfield_apply", "sb_fuse_region", "sb_sync", "sb_lane_mark", "sb_lane_wait_mark", "sb_set_lane_stream", "sb_canvas_pitch",
+    "sb_chunked_plane_elems", "sb_register_pairs", "sb_register_pairs_async", "sb_normalize",
 ]
 
 
@@ -106,11 +106,14 @@ def load_library(path: Optional[str] = None):
     lib.sb_fuse_region.argtypes = [vp, C.POINTER(SbFuseJob), i32]
     lib.sb_sync.argtypes = [vp, i32]
     lib.sb_set_lane_stream.argtypes = [vp, i32, vp]
+    lib.sb_lane_mark.argtypes = [vp, i32]
+    lib.sb_lane_wait_mark.argtypes = [vp, i32, i32]
     lib.sb_canvas_pitch.argtypes = [C.c_int32]
     lib.sb_canvas_pitch.restype = i64
     lib.sb_chunked_plane_elems.argtypes = [C.c_int32] * 4
     lib.sb_chunked_plane_elems.restype = i64
     lib.sb_register_pairs.argtypes = [vp, C.POINTER(SbRegisterJob), C.POINTER(SbPairResult)]
+    lib.sb_register_pairs_async.argtypes = [vp, C.POINTER(SbRegisterJob), C.POINTER(SbPairResult)]
     lib.sb_normalize.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32]
     if path == LIB_PATH:
         _lib = lib
@@ -192,6 +195,12 @@ class Context:
     def sync(self, lane: int = -1):
         self._check(self.lib.sb_sync(self.handle, lane), "sb_sync")
 
+    def lane_mark(self, lane: int):
+        self._check(self.lib.sb_lane_mark(self.handle, lane), "sb_lane_mark")
+
+    def lane_wait_mark(self, lane: int, other: int):
+        self._check(self.lib.sb_lane_wait_mark(self.handle, lane, other), "sb_lane_wait_mark")
+
     def set_lane_stream(self, lane: int, stream_ptr: Optional[int]):
         self._check(self.lib.sb_set_lane_stream(self.handle, lane, C.c_void_p(stream_ptr or 0)), "sb_set_lane_stream")
 
@@ -263,26 +272,43 @@ class Context:
         self._check(self.lib.sb_memcpy_async(self.handle, lane, _ptr(dst), _ptr(src), int(nbytes), kind),
                     "sb_memcpy_async")
 
-    def register_pairs(self, pairs: Sequence[tuple], tile_shape, max_overlap_x: int, max_overlap_y: int, *,
-                       mem=SB_MEM_HOST, upsample_factor: int = 10, precision: int = SB_PREC_AUTO, lane: int = 0):
-        """``pairs``: sequence of ``(ref, mov, dir)``.  Returns a list of dicts (see ``sb_pair_result``)."""
+    @staticmethod
+    def _pair_dicts(res):
+        return [{"dy": r.dy, "dx": r.dx, "shift": (r.shift[0], r.shift[1]),
+                 "coarse": (r.coarse[0], r.coarse[1]), "fine": (r.fine[0], r.fine[1]), "peak": r.peak,
+                 "runner_up": r.runner_up, "fine_peak": r.fine_peak, "ref_minmax": (r.ref_min, r.ref_max),
+                 "mov_minmax": (r.mov_min, r.mov_max), "precision": r.precision} for r in res]
+
+    def _register_job(self, pairs, tile_shape, max_overlap_x, max_overlap_y, mem, upsample_factor, precision, lane):
         n = len(pairs)
-        if n == 0:
-            return []
         arr = (SbPair * n)()
         for i, (ref, mov, d) in enumerate(pairs):
             arr[i] = SbPair(_ptr(ref), _ptr(mov), int(d), 0)
         res = (SbPairResult * n)()
         job = SbRegisterJob(arr, n, int(tile_shape[0]), int(tile_shape[1]), SB_U16, mem, int(max_overlap_x),
                             int(max_overlap_y), int(upsample_factor), int(precision), int(lane))
+        return arr, res, job
+
+    def register_pairs(self, pairs: Sequence[tuple], tile_shape, max_overlap_x: int, max_overlap_y: int, *,
+                       mem=SB_MEM_HOST, upsample_factor: int = 10, precision: int = SB_PREC_AUTO, lane: int = 0):
+        """``pairs``: sequence of ``(ref, mov, dir)``.  Returns a list of dicts (see ``sb_pair_result``)."""
+        if len(pairs) == 0:
+            return []
+        arr, res, job = self._register_job(pairs, tile_shape, max_overlap_x, max_overlap_y, mem, upsample_factor,
+                                           precision, lane)
         self._check(self.lib.sb_register_pairs(self.handle, C.byref(job), res), "sb_register_pairs")
-        out = []
-        for r in res:
-            out.append({"dy": r.dy, "dx": r.dx, "shift": (r.shift[0], r.shift[1]),
-                        "coarse": (r.coarse[0], r.coarse[1]), "fine": (r.fine[0], r.fine[1]), "peak": r.peak,
-                        "runner_up": r.runner_up, "fine_peak": r.fine_peak, "ref_minmax": (r.ref_min, r.ref_max),
-                        "mov_minmax": (r.mov_min, r.mov_max), "precision": r.precision})
-        return out
+        return self._pair_dicts(res)
+
+    def register_pairs_async(self, pairs: Sequence[tuple], tile_shape, max_overlap_x: int, max_overlap_y: int, *,
+                             mem=SB_MEM_HOST, upsample_factor: int = 10, precision: int = SB_PREC_AUTO, lane: int = 0):
+        """Enqueue on ``lane`` and return a :class:`PendingRegistration`; its ``get()`` is valid after ``sync(lane)``
+        (``sb_register_pairs_async``).  The tiles must stay valid until then."""
+        if len(pairs) == 0:
+            return PendingRegistration(self, lane, None, None, None, list(pairs))
+        arr, res, job = self._register_job(pairs, tile_shape, max_overlap_x, max_overlap_y, mem, upsample_factor,
+                                           precision, lane)
+        self._check(self.lib.sb_register_pairs_async(self.handle, C.byref(job), res), "sb_register_pairs_async")
+        return PendingRegistration(self, lane, arr, res, job, list(pairs))
 
     def normalize(self, tiles: np.ndarray) -> np.ndarray:
         tiles = np.ascontiguousarray(tiles)
@@ -292,6 +318,26 @@ class Context:
         self._check(self.lib.sb_normalize(self.handle, _ptr(t3), _ptr(out), t3.shape[0], t3.shape[1], t3.shape[2],
                                           SB_U16, SB_MEM_HOST), "sb_normalize")
         return out.reshape(tiles.shape)
+
+
+class PendingRegistration:
+    """Results of ``register_pairs_async``: the ctypes buffers stay alive here until they are read."""
+
+    def __init__(self, ctx, lane, arr, res, job, keep):
+        self.ctx, self.lane, self._arr, self._res, self._job, self._keep = ctx, lane, arr, res, job, keep
+        self._done = res is None
+
+    def get(self):
+        """Waits for the lane (``sb_sync``) if that has not happened yet and returns the list of result dicts."""
+        if self._res is None:
+            return []
+        if not self._done:
+            self.ctx.sync(self.lane)
+            self._done = True
+        return Context._pair_dicts(self._res)
+
+    def mark_synced(self):
+        self._done = True
 
 
 def canvas_pitch(width: int) -> int:

@@ -118,15 +118,15 @@ void sb_destroy(sb_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i < SB_NUM_LANES; ++i) {
         Lane& l = ctx->lanes[i];
-        for (DevBuf* b : {&l.tiles, &l.canvas, &l.meta, &l.work})
+        sb_register_discard(ctx, i);
+        for (DevBuf* b : {&l.tiles, &l.canvas, &l.meta, &l.work, &l.reg_tiles, &l.reg_work, &l.reg_meta})
             if (b->p) cudaFree(b->p);
         if (l.meta_host) cudaFreeHost(l.meta_host);
+        if (l.reg_host) cudaFreeHost(l.reg_host);
         if (l.meta_free) cudaEventDestroy(l.meta_free);
+        if (l.mark) cudaEventDestroy(l.mark);
         if (l.own) cudaStreamDestroy(l.own);
     }
-    for (DevBuf* b : {&ctx->reg_tiles, &ctx->reg_work, &ctx->reg_meta})
-        if (b->p) cudaFree(b->p);
-    if (ctx->reg_meta_host) cudaFreeHost(ctx->reg_meta_host);
     for (auto& kv : ctx->twiddle_cache)
         if (kv.second.p) cudaFree(kv.second.p);
     free_field(ctx->flat);
@@ -263,7 +263,28 @@ int sb_sync(sb_ctx* ctx, int lane) {
     if (!ctx) return SB_ERR_INVALID;
     if (lane >= SB_NUM_LANES) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
     for (int i = 0; i < SB_NUM_LANES; ++i)
-        if (lane < 0 || lane == i) SB_CUDA(ctx, cudaStreamSynchronize(ctx->lanes[i].stream));
+        if (lane < 0 || lane == i) {
+            SB_CUDA(ctx, cudaStreamSynchronize(ctx->lanes[i].stream));
+            const int rc = sb_register_complete(ctx, i);   // results of a parked sb_register_pairs_async land now
+            if (rc) return rc;
+        }
+    return SB_OK;
+}
+
+int sb_lane_mark(sb_ctx* ctx, int lane) {
+    Lane* l = sb_lane(ctx, lane);
+    if (!l) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
+    if (!l->mark) SB_CUDA(ctx, cudaEventCreateWithFlags(&l->mark, cudaEventDisableTiming));
+    SB_CUDA(ctx, cudaEventRecord(l->mark, l->stream));
+    l->marked = true;
+    return SB_OK;
+}
+
+int sb_lane_wait_mark(sb_ctx* ctx, int lane, int other) {
+    Lane* l = sb_lane(ctx, lane);
+    Lane* o = sb_lane(ctx, other);
+    if (!l || !o) return sb_fail(ctx, SB_ERR_INVALID, "lane %d / %d out of range", lane, other);
+    if (o->marked && l != o) SB_CUDA(ctx, cudaStreamWaitEvent(l->stream, o->mark, 0));
     return SB_OK;
 }
 
@@ -283,7 +304,12 @@ int sb_flatfield_apply(sb_ctx* ctx, int channel, const void* tiles, void* out, i
 
 int sb_register_pairs(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out) {
     if (!ctx) return SB_ERR_INVALID;
-    return sb_register_pairs_impl(ctx, job, out);
+    return sb_register_pairs_impl(ctx, job, out, false);
+}
+
+int sb_register_pairs_async(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out) {
+    if (!ctx) return SB_ERR_INVALID;
+    return sb_register_pairs_impl(ctx, job, out, true);
 }
 
 int sb_normalize(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int dtype, int mem) {

@@ -25,6 +25,7 @@ struct FftPlan {
     int n;
     int nfac;
     int fac[16];
+    int gemm_radix;   // odd radix handled by pass_odd_gemm (needs its cos/sin table in shared memory); 0 = none
 };
 
 template <typename T> struct Vec2;
@@ -269,11 +270,154 @@ __device__ __forceinline__ void pass_odd_sym(T2* __restrict__ a, T2* __restrict_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Large odd radix (e.g. 107 of 214 = 2 * 107) as a register-tiled real matrix product on packed f32x2.
+//
+// Same conjugate-symmetric formulation as pass_odd_sym -- for q = 1..h
+//     Ce[q] = sum_r e_r cos(2 pi q r / R),   So[q] = sum_r o_r sin(2 pi q r / R)        (e, o complex)
+// i.e. two real (h x h) matrices applied to 2 * (lines * M) real columns -- but organised as a GEMM:
+//   * step 1 folds the inputs and TRANSPOSES them into the other buffer as T[r][j][line] (line fastest), so the
+//     four lines a thread owns are 32 contiguous bytes: two 128-bit loads per operand instead of four 64-bit ones;
+//   * cos / sin come from a dedicated table ctab[2][h][QP] (QP = h rounded up to 4) in shared memory: one 128-bit
+//     broadcast load gives the 4 outputs q of a thread, no per-term index arithmetic;
+//   * a thread owns 4 (q) x 4 (lines) complex accumulators for Ce and for So; a complex value IS a packed f32x2,
+//     so every term is one FFMA2 (fma.rn.f32x2) with the duplicated cos / sin: 32 FFMA2 per 6 LDS.128.
+// The result is written back to the INPUT buffer in the standard [line][index] layout.
+__device__ __forceinline__ unsigned long long fx2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long fx2_dup(float v) {
+    unsigned long long d;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(v));
+    return d;
+}
+__device__ __forceinline__ float2 fx2_unpack(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
+__device__ __forceinline__ void pass_odd_gemm(float2* __restrict__ a, float2* __restrict__ b, const float2* __restrict__ tw,
+                                              const float* __restrict__ ctab, int N, int Ns, int R, int nlines, bool inverse) {
+    const int M = N / R;
+    const int h = (R - 1) / 2;
+    const int QP = (h + 3) & ~3;
+    const int tstep = N / (Ns * R);
+    // ---- step 1: (pre-twiddle,) fold, transpose.  T[(r * M + j) * nlines + line]; r = 0 holds y_0.
+    for (int it = threadIdx.x; it < M * nlines; it += blockDim.x) {
+        const int j = it / nlines, line = it - j * nlines;
+        b[it] = a[(size_t)line * N + j];
+    }
+    for (int it = threadIdx.x; it < h * M * nlines; it += blockDim.x) {
+        const int rem = it / nlines, line = it - rem * nlines;
+        const int r = rem / M + 1, j = rem - (r - 1) * M;
+        float2 y1 = a[(size_t)line * N + r * M + j], y2 = a[(size_t)line * N + (R - r) * M + j];
+        if (Ns > 1) {
+            const int k = j % Ns;
+            float2 w1 = tw[(int)(((long long)r * k * tstep) % N)], w2 = tw[(int)(((long long)(R - r) * k * tstep) % N)];
+            if (inverse) { w1.y = -w1.y; w2.y = -w2.y; }
+            y1 = cmul(y1, w1);
+            y2 = cmul(y2, w2);
+        }
+        b[(size_t)(r * M + j) * nlines + line] = make_float2(y1.x + y2.x, y1.y + y2.y);
+        b[(size_t)((R - r) * M + j) * nlines + line] = make_float2(y1.x - y2.x, y1.y - y2.y);
+    }
+    __syncthreads();
+    // ---- step 2: the GEMM.  item = (q tile of 4, column group = (j, 4 lines)); lanes run over column groups.
+    const int lgs = nlines >> 2;
+    const int ncg = M * lgs;
+    const int nqt = QP >> 2;
+    const float* cosb = ctab;
+    const float* sinb = ctab + h * QP;
+    const int es = (M * nlines) >> 1;                      // ulonglong2 stride of one r step in T
+    for (int it = threadIdx.x; it < nqt * ncg; it += blockDim.x) {
+        const int qt = it / ncg, cg = it - qt * ncg;
+        const int j = cg / lgs, lg = cg - j * lgs;
+        const ulonglong2* ep = reinterpret_cast<const ulonglong2*>(b + (size_t)(M + j) * nlines + lg * 4);
+        const ulonglong2* op = reinterpret_cast<const ulonglong2*>(b + (size_t)((R - 1) * M + j) * nlines + lg * 4);
+        const float4* cp = reinterpret_cast<const float4*>(cosb + qt * 4);
+        const float4* sp = reinterpret_cast<const float4*>(sinb + qt * 4);
+        unsigned long long ce[4][4], so[4][4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int l = 0; l < 4; ++l) ce[t][l] = so[t][l] = 0ull;
+#pragma unroll 2
+        for (int r = 1; r <= h; ++r) {
+            const float4 c = *cp, s = *sp;
+            const ulonglong2 e01 = ep[0], e23 = ep[1], o01 = op[0], o23 = op[1];
+            cp += QP >> 2;
+            sp += QP >> 2;
+            ep += es;
+            op -= es;
+            const unsigned long long e[4] = {e01.x, e01.y, e23.x, e23.y}, o[4] = {o01.x, o01.y, o23.x, o23.y};
+            const float cv[4] = {c.x, c.y, c.z, c.w}, sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const unsigned long long cc = fx2_dup(cv[t]), ss = fx2_dup(sv[t]);
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    ce[t][l] = fx2_fma(e[l], cc, ce[t][l]);
+                    so[t][l] = fx2_fma(o[l], ss, so[t][l]);
+                }
+            }
+        }
+        const int k = j % Ns;
+        const int dst0 = (j / Ns) * Ns * R + k;
+        const float2* y0p = b + (size_t)j * nlines + lg * 4;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const float2 y0 = y0p[l];
+            float2* out = a + (size_t)(lg * 4 + l) * N + dst0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int q = qt * 4 + t + 1;
+                if (q <= h) {
+                    const float2 cev = fx2_unpack(ce[t][l]), sov = fx2_unpack(so[t][l]);
+                    const float bx = y0.x + cev.x, by = y0.y + cev.y;
+                    // forward: X[q] = base - i So, X[R-q] = base + i So ; inverse: swapped
+                    const float2 lo = make_float2(bx + sov.y, by - sov.x), hi = make_float2(bx - sov.y, by + sov.x);
+                    out[(size_t)q * Ns] = inverse ? hi : lo;
+                    out[(size_t)(R - q) * Ns] = inverse ? lo : hi;
+                }
+            }
+        }
+    }
+    // ---- X[0] = y_0 + sum_r e_r
+    for (int it = threadIdx.x; it < M * nlines; it += blockDim.x) {
+        const int j = it / nlines, line = it - j * nlines;
+        float2 acc = b[it];
+        for (int r = 1; r <= h; ++r) {
+            const float2 e = b[(size_t)(r * M + j) * nlines + line];
+            acc.x += e.x;
+            acc.y += e.y;
+        }
+        a[(size_t)line * N + (j / Ns) * Ns * R + (j % Ns)] = acc;
+    }
+}
+
+template <typename T2>
+struct OddGemm {      // float64 lines have no packed-FMA path: fall through to pass_odd_sym
+    static __device__ __forceinline__ bool run(T2*, T2*, const T2*, const float*, int, int, int, int, bool) { return false; }
+};
+template <>
+struct OddGemm<float2> {
+    static __device__ __forceinline__ bool run(float2* a, float2* b, const float2* tw, const float* ctab, int N, int Ns, int R,
+                                               int nlines, bool inverse) {
+        pass_odd_gemm(a, b, tw, ctab, N, Ns, R, nlines, inverse);
+        return true;
+    }
+};
+
 // In-place (ping-pong) FFT of `nlines` lines of length plan.n held in shared memory, line stride
 // plan.n.  nlines must be a multiple of LB.  Returns the buffer that holds the result.  All
 // threads of the block must call; ends with a __syncthreads().
 template <typename T2, int LB>
-__device__ T2* fft_lines(T2* buf0, T2* buf1, const T2* __restrict__ tw, const FftPlan& plan, int nlines, bool inverse) {
+__device__ T2* fft_lines(T2* buf0, T2* buf1, const T2* __restrict__ tw, const FftPlan& plan, int nlines, bool inverse,
+                         const float* __restrict__ ctab = nullptr) {
     // NOTE: odd-radix passes fold their inputs in place, so the input buffer is clobbered.
     const int N = plan.n;
     T2* a = buf0;
@@ -282,14 +426,19 @@ __device__ T2* fft_lines(T2* buf0, T2* buf1, const T2* __restrict__ tw, const Ff
     const int groups = nlines / LB;
     for (int f = 0; f < plan.nfac; ++f) {
         const int R = plan.fac[f];
+        bool in_place = false;
         if (R == 4) pass_radix4<T2, LB>(a, b, tw, N, Ns, groups, inverse);
         else if (R == 2) pass_radix2<T2, LB>(a, b, tw, N, Ns, groups, inverse);
+        else if (ctab != nullptr && R == plan.gemm_radix && (nlines & 3) == 0 &&
+                 OddGemm<T2>::run(a, b, tw, ctab, N, Ns, R, nlines, inverse)) in_place = true;
         else if (R & 1) pass_odd_sym<T2, LB, (sizeof(T2) == 8 ? (LB >= 4 ? 4 : 8) : (LB >= 4 ? 2 : 4))>(a, b, tw, N, Ns, R, groups, inverse);
         else pass_generic<T2, LB, (LB >= 4 ? 4 : 8)>(a, b, tw, N, Ns, R, groups, inverse);
         __syncthreads();
-        T2* t = a;
-        a = b;
-        b = t;
+        if (!in_place) {                     // pass_odd_gemm leaves its result in the input buffer
+            T2* t = a;
+            a = b;
+            b = t;
+        }
         Ns *= R;
     }
     return a;

@@ -109,17 +109,30 @@ __global__ void __launch_bounds__(256) normalize_kernel(const uint16_t* __restri
         o[i] = (uint16_t)stretch_px(t[i], m.x, m.y);
 }
 
+// cos/sin table of the big odd radix (fft.cuh: pass_odd_gemm): global -> shared, right after the twiddles.
+// All threads call; visibility is covered by the __syncthreads every kernel has before its first FFT pass.
+template <typename T2>
+__device__ __forceinline__ float* stage_ctab(T2* after_tw, const float* __restrict__ ctab_g, int ctab_n) {
+    if (ctab_n == 0) return nullptr;
+    float* dst = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(after_tw) + 15) & ~(uintptr_t)15);
+    const float4* src = reinterpret_cast<const float4*>(ctab_g);
+    for (int i = threadIdx.x; i < ctab_n / 4; i += blockDim.x) reinterpret_cast<float4*>(dst)[i] = __ldg(src + i);
+    return dst;
+}
+
 // ------------------------------------------------------------------------------------------ K1
 template <typename T, int LB>
-__global__ void __launch_bounds__(256) rows_fwd_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm,
+__global__ void __launch_bounds__(256, 2) rows_fwd_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm,
                                                        int tile_w, int Sh, int Sw, int lpb, int nrb,
                                                        const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
+                                                       const float* __restrict__ ctab_g, int ctab_n,
                                                        typename Vec2<T>::type* __restrict__ Z, int* __restrict__ nonzero) {
     using T2 = typename Vec2<T>::type;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     T2* buf0 = reinterpret_cast<T2*>(smem_raw);
     T2* buf1 = buf0 + (size_t)lpb * Sw;
     T2* tw = buf1 + (size_t)lpb * Sw;
+    float* ctab = stage_ctab(tw + Sw, ctab_g, ctab_n);
     const int p = blockIdx.x / nrb, rb = blockIdx.x - p * nrb;
     const int y0 = rb * lpb;
     const PairDesc pd = pairs[p];
@@ -160,19 +173,22 @@ __global__ void __launch_bounds__(256) rows_fwd_kernel(const PairDesc* __restric
     // the packed transform only gets it to rounding noise, so record the fact instead.
     const int any_a = __syncthreads_or(seen & 1), any_b = __syncthreads_or(seen & 2);   // predicate OR, not bitwise
     if (threadIdx.x == 0 && (any_a || any_b)) atomicOr(&nonzero[p], (any_a ? 1 : 0) | (any_b ? 2 : 0));
-    T2* res = fft_lines<T2, LB>(buf0, buf1, tw, plan, lpb, false);
+    T2* res = fft_lines<T2, LB>(buf0, buf1, tw, plan, lpb, false, ctab);
+    // Z is kept TRANSPOSED (Zt[kx][y], y fastest) so that the column pass reads and writes whole contiguous lines;
+    // here the lpb rows of this block are lpb consecutive y of every kx: runs of 8 * lpb contiguous bytes.
     T2* zp = Z + (size_t)p * Sh * Sw;
     for (int i = threadIdx.x; i < lpb * Sw; i += blockDim.x) {
-        const int l = i / Sw;
-        if (y0 + l < Sh) zp[(size_t)y0 * Sw + i] = res[i];
+        const int x = i / lpb, l = i - x * lpb;
+        if (y0 + l < Sh) zp[(size_t)x * Sh + y0 + l] = res[(size_t)l * Sw + x];
     }
 }
 
 // ------------------------------------------------------------------------------------------ K2
 // One block owns G columns kx and their mirrors (Sw - kx) % Sw: 2G lines of length Sh.
 template <typename T, int G>
-__global__ void __launch_bounds__(256) cols_xpower_kernel(int Sh, int Sw, int ncg,
+__global__ void __launch_bounds__(256, 2) cols_xpower_kernel(int Sh, int Sw, int ncg,
                                                           const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
+                                                          const float* __restrict__ ctab_g, int ctab_n,
                                                           typename Vec2<T>::type* __restrict__ Z,
                                                           typename Vec2<T>::type* __restrict__ Rbuf) {
     using T2 = typename Vec2<T>::type;
@@ -181,6 +197,7 @@ __global__ void __launch_bounds__(256) cols_xpower_kernel(int Sh, int Sw, int nc
     T2* buf0 = reinterpret_cast<T2*>(smem_raw);
     T2* buf1 = buf0 + (size_t)NL * Sh;
     T2* tw = buf1 + (size_t)NL * Sh;
+    float* ctab = stage_ctab(tw + Sh, ctab_g, ctab_n);
     const int p = blockIdx.x / ncg, cg = blockIdx.x - p * ncg;
     T2* zp = Z + (size_t)p * Sh * Sw;
     T2* rp = Rbuf + (size_t)p * Sh * Sw;
@@ -188,19 +205,19 @@ __global__ void __launch_bounds__(256) cols_xpower_kernel(int Sh, int Sw, int nc
     for (int i = threadIdx.x; i < Sh; i += blockDim.x) tw[i] = tw_g[i];
     // line l < G: column kx = cg*G + l ; line G + l: its mirror (unused when the column is self-mirrored)
     for (int i = threadIdx.x; i < NL * Sh; i += blockDim.x) {
-        const int y = i / NL, l = i - y * NL;   // l fastest: neighbouring columns are adjacent in memory
+        const int l = i / Sh, y = i - l * Sh;   // y fastest: a column of the strip is a contiguous line of Zt
         const int kx = cg * G + (l % G);
         T2 z = mk2<T2, T>(0, 0);
         if (kx <= half) {
             const int kxm = (Sw - kx) % Sw;
-            if (l < G) z = zp[(size_t)y * Sw + kx];
-            else if (kxm != kx) z = zp[(size_t)y * Sw + kxm];
+            if (l < G) z = zp[(size_t)kx * Sh + y];
+            else if (kxm != kx) z = zp[(size_t)kxm * Sh + y];
         }
-        buf0[(size_t)l * Sh + y] = z;
+        buf0[i] = z;
     }
     __syncthreads();
     constexpr int CLB = NL >= 4 ? 4 : NL;
-    T2* f = fft_lines<T2, CLB>(buf0, buf1, tw, plan, NL, false);
+    T2* f = fft_lines<T2, CLB>(buf0, buf1, tw, plan, NL, false, ctab);
     // unpack A = FFT(a), B = FFT(b) from Z = FFT(a + i b); R = A conj(B) / max(|A conj(B)|, clamp)
     for (int i = threadIdx.x; i < G * Sh; i += blockDim.x) {
         const int l = i / Sh, ky = i - l * Sh;
@@ -223,19 +240,19 @@ __global__ void __launch_bounds__(256) cols_xpower_kernel(int Sh, int Sw, int nc
         if (self && ky == kym) py = 0;          // self-conjugate bin: exactly real
         l1[ky] = mk2<T2, T>(px, py);
         l2[kym] = mk2<T2, T>(px, -py);
-        rp[(size_t)ky * Sw + kx] = mk2<T2, T>(px, py);
-        rp[(size_t)kym * Sw + kxm] = mk2<T2, T>(px, -py);
+        rp[(size_t)kx * Sh + ky] = mk2<T2, T>(px, py);          // R is kept transposed as well (Rt[kx][ky])
+        rp[(size_t)kxm * Sh + kym] = mk2<T2, T>(px, -py);
     }
     __syncthreads();
     T2* other = (f == buf0) ? buf1 : buf0;
-    T2* y = fft_lines<T2, CLB>(f, other, tw, plan, NL, true);
+    T2* y = fft_lines<T2, CLB>(f, other, tw, plan, NL, true, ctab);
     for (int i = threadIdx.x; i < NL * Sh; i += blockDim.x) {
-        const int yy = i / NL, l = i - yy * NL;
+        const int l = i / Sh, yy = i - l * Sh;
         const int kx = cg * G + (l % G);
         if (kx > half) continue;
         const int kxm = (Sw - kx) % Sw;
-        if (l < G) zp[(size_t)yy * Sw + kx] = y[(size_t)l * Sh + yy];
-        else if (kxm != kx) zp[(size_t)yy * Sw + kxm] = y[(size_t)l * Sh + yy];
+        if (l < G) zp[(size_t)kx * Sh + yy] = y[i];
+        else if (kxm != kx) zp[(size_t)kxm * Sh + yy] = y[i];
     }
 }
 
@@ -246,8 +263,9 @@ __device__ __forceinline__ void best_update(V& bv, int& bi, V v, int i) {
 }
 
 template <typename T, int LB>
-__global__ void __launch_bounds__(256) rows_inv_argmax_kernel(int Sh, int Sw, int lpb, int nrb,
+__global__ void __launch_bounds__(256, 2) rows_inv_argmax_kernel(int Sh, int Sw, int lpb, int nrb,
                                                               const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
+                                                              const float* __restrict__ ctab_g, int ctab_n,
                                                               const typename Vec2<T>::type* __restrict__ Y,
                                                               CtaBest* __restrict__ best) {
     using T2 = typename Vec2<T>::type;
@@ -255,27 +273,28 @@ __global__ void __launch_bounds__(256) rows_inv_argmax_kernel(int Sh, int Sw, in
     T2* buf0 = reinterpret_cast<T2*>(smem_raw);
     T2* buf1 = buf0 + (size_t)lpb * Sw;
     T2* tw = buf1 + (size_t)lpb * Sw;
+    float* ctab = stage_ctab(tw + Sw, ctab_g, ctab_n);
     const int p = blockIdx.x / nrb, rb = blockIdx.x - p * nrb;
     const int l0 = rb * lpb;                                 // first packed line of this block
     const T2* yp = Y + (size_t)p * Sh * Sw;
     for (int i = threadIdx.x; i < Sw; i += blockDim.x) tw[i] = tw_g[i];
     for (int i = threadIdx.x; i < lpb * Sw; i += blockDim.x) {
-        const int l = i / Sw, x = i - l * Sw;
+        const int x = i / lpb, l = i - x * lpb;              // l fastest: 2 * lpb consecutive y of one x are contiguous in Yt
         const int y1 = 2 * (l0 + l), y2 = y1 + 1;
         T2 v = mk2<T2, T>(0, 0);
         if (y1 < Sh) {
-            const T2 r1 = yp[(size_t)y1 * Sw + x];
+            const T2 r1 = yp[(size_t)x * Sh + y1];
             v = r1;
             if (y2 < Sh) {                                   // + i * row y2
-                const T2 r2 = yp[(size_t)y2 * Sw + x];
+                const T2 r2 = yp[(size_t)x * Sh + y2];
                 v.x -= r2.y;
                 v.y += r2.x;
             }
         }
-        buf0[i] = v;
+        buf0[(size_t)l * Sw + x] = v;
     }
     __syncthreads();
-    const T2* res = fft_lines<T2, LB>(buf0, buf1, tw, plan, lpb, true);
+    const T2* res = fft_lines<T2, LB>(buf0, buf1, tw, plan, lpb, true, ctab);
     T bv = (T)-1;
     int bi = 0x7fffffff;
     for (int i = threadIdx.x; i < lpb * Sw; i += blockDim.x) {
@@ -374,62 +393,67 @@ __global__ void __launch_bounds__(256) updft_twiddle_kernel(const PeakOut* __res
     }
 }
 
-// T[u][y] = sum_x conj(R[y][x]) Ex[u][x].  A block owns 16 rows (two per warp); the twiddle rows
-// Ex[u][x0 .. x0+XC) of a u tile are staged in shared memory once per block and reused by all 16 rows.
-template <typename T>
-__global__ void __launch_bounds__(256) updft_rows_kernel(int Sh, int Sw, int rs, int nrb,
+// T[u][y] = sum_x conj(R[y][x]) Ex[u][x] with R stored transposed (Rt[x][y]).  A block owns YT = 64 rows y and the
+// whole x range, split over 256 / YT = 4 interleaved x slices; a thread keeps all rs (<= UMAX) outputs of its y in
+// registers.  Lanes run over y, so every load of Rt is a contiguous 256-byte warp access; the twiddles Ex[.][x] are
+// staged in shared memory in chunks of XC and read as broadcasts.  Slices are reduced through shared memory.
+template <typename T, int UMAX>
+__global__ void __launch_bounds__(256) updft_rows_kernel(int Sh, int Sw, int rs, int u0, int nyb,
                                                          const typename Vec2<T>::type* __restrict__ Rbuf,
                                                          const typename Vec2<T>::type* __restrict__ Ex,
                                                          typename Vec2<T>::type* __restrict__ Tm) {
     using T2 = typename Vec2<T>::type;
-    constexpr int UT = 8;                       // u tile held in registers: 2 rows x 8 accumulators
-    constexpr int XC = 256;                     // x chunk staged in shared memory
-    __shared__ __align__(16) unsigned char ex_raw[UT * XC * sizeof(T2)];
+    constexpr int YT = 64, NS = 256 / YT;
+    constexpr int XC = 128;                      // x chunk staged in shared memory
+    static_assert(YT <= XC, "the reduction buffer [UMAX][YT] reuses the twiddle staging area [XC][UMAX]");
+    __shared__ __align__(16) unsigned char ex_raw[UMAX * XC * sizeof(T2)];
     T2* exs = reinterpret_cast<T2*>(ex_raw);
-    const int p = blockIdx.x / nrb, rb = blockIdx.x - p * nrb;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x / nyb, yb = blockIdx.x - p * nyb;
+    const int ys = threadIdx.x % YT, xs = threadIdx.x / YT;
+    const int y = yb * YT + ys;
     const T2* rp = Rbuf + (size_t)p * Sh * Sw;
     const T2* ex = Ex + (size_t)p * rs * Sw;
-    T2* tp = Tm + (size_t)p * rs * Sh;
-    const int y0 = rb * 16 + warp * 2, y1 = y0 + 1;
-    for (int u0 = 0; u0 < rs; u0 += UT) {
-        T2 acc0[UT], acc1[UT];
+    T2 acc[UMAX];
 #pragma unroll
-        for (int u = 0; u < UT; ++u) { acc0[u].x = acc0[u].y = 0; acc1[u].x = acc1[u].y = 0; }
-        for (int xc = 0; xc < Sw; xc += XC) {
-            const int nx = min(XC, Sw - xc);
-            __syncthreads();
-            for (int i = threadIdx.x; i < UT * nx; i += blockDim.x) {
-                const int u = i / nx, x = i - u * nx;
-                exs[u * XC + x] = (u0 + u < rs) ? ex[(size_t)(u0 + u) * Sw + xc + x] : mk2<T2, T>(0, 0);
-            }
-            __syncthreads();
-            for (int x = lane; x < nx; x += 32) {
-                T2 r0 = mk2<T2, T>(0, 0), r1 = mk2<T2, T>(0, 0);
-                if (y0 < Sh) { r0 = rp[(size_t)y0 * Sw + xc + x]; r0.y = -r0.y; }
-                if (y1 < Sh) { r1 = rp[(size_t)y1 * Sw + xc + x]; r1.y = -r1.y; }
+    for (int u = 0; u < UMAX; ++u) acc[u].x = acc[u].y = 0;
+    for (int xc = 0; xc < Sw; xc += XC) {
+        const int nx = min(XC, Sw - xc);
+        __syncthreads();
+        for (int i = threadIdx.x; i < UMAX * nx; i += blockDim.x) {
+            const int u = i / nx, x = i - u * nx;
+            exs[x * UMAX + u] = (u0 + u < rs) ? ex[(size_t)(u0 + u) * Sw + xc + x] : mk2<T2, T>(0, 0);
+        }
+        __syncthreads();
+        if (y < Sh) {
+            for (int x = xs; x < nx; x += NS) {
+                T2 r = rp[(size_t)(xc + x) * Sh + y];
+                r.y = -r.y;
 #pragma unroll
-                for (int u = 0; u < UT; ++u) {
-                    const T2 w = exs[u * XC + x];
-                    cfma(acc0[u], r0, w);
-                    cfma(acc1[u], r1, w);
-                }
+                for (int u = 0; u < UMAX; ++u) cfma(acc[u], r, exs[x * UMAX + u]);
             }
         }
+    }
+    // reduce the NS x slices: slice k parks its sums in shared memory, slice 0 adds them
+    for (int k = 1; k < NS; ++k) {
+        __syncthreads();
+        if (xs == k) {
 #pragma unroll
-        for (int u = 0; u < UT; ++u) {
+            for (int u = 0; u < UMAX; ++u) exs[u * YT + ys] = acc[u];
+        }
+        __syncthreads();
+        if (xs == 0) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                acc0[u].x += __shfl_xor_sync(0xffffffffu, acc0[u].x, o);
-                acc0[u].y += __shfl_xor_sync(0xffffffffu, acc0[u].y, o);
-                acc1[u].x += __shfl_xor_sync(0xffffffffu, acc1[u].x, o);
-                acc1[u].y += __shfl_xor_sync(0xffffffffu, acc1[u].y, o);
-            }
-            if (lane == 0 && u0 + u < rs) {
-                if (y0 < Sh) tp[(size_t)(u0 + u) * Sh + y0] = acc0[u];
-                if (y1 < Sh) tp[(size_t)(u0 + u) * Sh + y1] = acc1[u];
+            for (int u = 0; u < UMAX; ++u) {
+                const T2 o = exs[u * YT + ys];
+                acc[u].x += o.x;
+                acc[u].y += o.y;
             }
         }
+    }
+    if (xs == 0 && y < Sh) {
+#pragma unroll
+        for (int u = 0; u < UMAX; ++u)
+            if (u0 + u < rs) Tm[(size_t)p * rs * Sh + (size_t)(u0 + u) * Sh + y] = acc[u];
     }
 }
 
@@ -494,8 +518,39 @@ FftPlan make_plan(int n) {
     FftPlan pl;
     pl.n = n;
     pl.nfac = 0;
+    pl.gemm_radix = 0;
     for (int v : f) pl.fac[pl.nfac++] = v;
     return pl;
+}
+
+// The largest radix, when it is a big odd one (107 of 214, 157 of 314): worth the register-tiled f32x2 pass.
+int big_odd_radix(const FftPlan& pl) { return (pl.nfac > 0 && (pl.fac[0] & 1) && pl.fac[0] >= 13) ? pl.fac[0] : 0; }
+
+// cos/sin table of pass_odd_gemm: [2][h][QP] floats, h = (R-1)/2, QP = h rounded up to 4 (zero padded);
+// entry [0][r-1][q-1] = cos(2 pi q r / R), [1][r-1][q-1] = sin(2 pi q r / R), computed in long double.
+int get_ctab(sb_ctx* ctx, int R, const float** out, int* n_floats) {
+    const int h = (R - 1) / 2, QP = (h + 3) & ~3;
+    const int n = 2 * h * QP;
+    const uint64_t key = ((uint64_t)1 << 40) | (uint64_t)R;
+    auto it = ctx->twiddle_cache.find(key);
+    if (it == ctx->twiddle_cache.end()) {
+        std::vector<float> t((size_t)n, 0.0f);
+        const long double tau = 6.283185307179586476925286766559L;
+        for (int r = 1; r <= h; ++r)
+            for (int q = 1; q <= h; ++q) {
+                const long double a = tau * (long double)(((long long)q * r) % R) / (long double)R;
+                t[(size_t)(r - 1) * QP + (q - 1)] = (float)cosl(a);
+                t[(size_t)h * QP + (size_t)(r - 1) * QP + (q - 1)] = (float)sinl(a);
+            }
+        DevBuf b;
+        int rc = sb_reserve(ctx, b, (size_t)n * sizeof(float));
+        if (rc) return rc;
+        SB_CUDA(ctx, cudaMemcpy(b.p, t.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+        it = ctx->twiddle_cache.emplace(key, b).first;
+    }
+    *out = reinterpret_cast<const float*>(it->second.p);
+    *n_floats = n;
+    return SB_OK;
 }
 
 template <typename T>
@@ -535,9 +590,12 @@ int pick_lines(int n, size_t elem, int lb, size_t budget) {
     return l;
 }
 
+// Enqueues the whole chain for one direction group on the lane's stream; the per-pair PeakOut records are copied to
+// `h_out` (pinned for asynchronous jobs).  With do_sync the call returns when they have arrived.
 template <typename T>
-int run_group(sb_ctx* ctx, cudaStream_t st, const std::vector<PairDesc>& pairs, const GroupGeom& g, int tile_w,
-              const int2* d_mm, int uf, std::vector<PeakOut>& results) {
+int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const GroupGeom& g, int tile_w,
+              const int2* d_mm, int uf, PeakOut* h_out, bool do_sync) {
+    cudaStream_t st = lane->stream;
     using T2 = typename Vec2<T>::type;
     const int n = (int)pairs.size();
     const int Sh = g.Sh, Sw = g.Sw;
@@ -557,26 +615,52 @@ int run_group(sb_ctx* ctx, cudaStream_t st, const std::vector<PairDesc>& pairs, 
     int B = (int)std::max<size_t>(1, (size_t)(64u << 20) / per_pair);
     B = std::min(B, n);
 
-    // launch geometry
-    constexpr size_t kBudget = 112 * 1024;    // two blocks per SM
-    int lbx = 4, lpbx = pick_lines(Sw, sizeof(T2), 4, kBudget);
-    if (lpbx < 4) { lbx = 1; lpbx = pick_lines(Sw, sizeof(T2), 1, 200 * 1024); }
+    // cos/sin tables of the big odd radices (float32 lines only)
+    FftPlan px_plan = plan_x, py_plan = plan_y;
+    const float *ctab_x = nullptr, *ctab_y = nullptr;
+    int ctab_xn = 0, ctab_yn = 0;
+    if (sizeof(T) == 4 && !getenv("SB_REG_NO_GEMM")) {
+        if (big_odd_radix(plan_x)) {
+            px_plan.gemm_radix = big_odd_radix(plan_x);
+            rc = get_ctab(ctx, px_plan.gemm_radix, &ctab_x, &ctab_xn);
+            if (rc) return rc;
+        }
+        if (big_odd_radix(plan_y)) {
+            py_plan.gemm_radix = big_odd_radix(plan_y);
+            rc = get_ctab(ctx, py_plan.gemm_radix, &ctab_y, &ctab_yn);
+            if (rc) return rc;
+        }
+    }
+    const size_t ctab_xb = ctab_xn ? (size_t)ctab_xn * 4 + 16 : 0, ctab_yb = ctab_yn ? (size_t)ctab_yn * 4 + 16 : 0;
+
+    // launch geometry: two blocks per SM wherever the lines + tables allow it
+    constexpr size_t kBudget = 113 * 1024;
+    int lbx = 4, lpbx = pick_lines(Sw, sizeof(T2), 4, kBudget - ctab_xb);
+    if (lpbx < 4) { lbx = 1; lpbx = pick_lines(Sw, sizeof(T2), 1, 200 * 1024 - ctab_xb); }
     if (lpbx < 1) return sb_fail(ctx, SB_ERR_UNSUPPORTED, "strip width %d too large for the shared-memory FFT", Sw);
-    const size_t smem_x = (size_t)(2 * lpbx + 1) * Sw * sizeof(T2);
-    // columns per block: short lines (e.g. 214 = 2 * 107) take 8 columns + 8 mirrors so that the prime-radix
-    // pass has enough independent work for 256 threads and global accesses are 64-byte segments
-    int G = 16;
-    auto smem_for = [&](int g) { return (size_t)(2 * 2 * g + 1) * Sh * sizeof(T2); };
-    while (G > 1 && smem_for(G) > 112 * 1024) G >>= 1;
+    if (lbx != 4) { px_plan.gemm_radix = 0; }                    // pass_odd_gemm needs a multiple of 4 lines
+    const size_t smem_x = (size_t)(2 * lpbx + 1) * Sw * sizeof(T2) + (px_plan.gemm_radix ? ctab_xb : 0);
+    // columns per block: short lines (e.g. 214 = 2 * 107) take up to 16 columns + 16 mirrors so that the prime-radix
+    // pass has enough independent work for 256 threads and global accesses are 64..128-byte segments
+    static const int kG[] = {16, 12, 8, 4, 2, 1};
+    auto smem_for = [&](int g) { return (size_t)(2 * 2 * g + 1) * Sh * sizeof(T2) + ctab_yb; };
+    int G = 1;
+    for (int g : kG)
+        if (smem_for(g) <= kBudget) { G = g; break; }
     if (G == 1 && smem_for(2) <= 200 * 1024) G = 2;
+    if (G < 2) py_plan.gemm_radix = 0;
     const size_t smem_y = smem_for(G);
     if (smem_y > 227 * 1024) return sb_fail(ctx, SB_ERR_UNSUPPORTED, "strip height %d too large for the shared-memory FFT", Sh);
     const int nrb_fwd = (Sh + lpbx - 1) / lpbx;
     const int nlines_inv = (Sh + 1) / 2;
     const int nrb_inv = (nlines_inv + lpbx - 1) / lpbx;
     const int ncg = (Sw / 2 + 1 + G - 1) / G;
-    const int rows_per_block = 16;    // two rows per warp
+    const int rows_per_block = 64;    // updft_rows_kernel: YT rows y per block
     const int nrb_up = (Sh + rows_per_block - 1) / rows_per_block;
+    const float* cx = px_plan.gemm_radix ? ctab_x : nullptr;
+    const int cxn = px_plan.gemm_radix ? ctab_xn : 0;
+    const float* cy = py_plan.gemm_radix ? ctab_y : nullptr;
+    const int cyn = py_plan.gemm_radix ? ctab_yn : 0;
 
     // workspace: Z | R | Ex | Ey | T | best | peaks | pair descriptors
     size_t off = 0;
@@ -591,9 +675,9 @@ int run_group(sb_ctx* ctx, cudaStream_t st, const std::vector<PairDesc>& pairs, 
     const size_t o_peaks = carve((size_t)n * sizeof(PeakOut));
     const size_t o_pairs = carve((size_t)n * sizeof(PairDesc));
     const size_t o_nz = carve((size_t)n * sizeof(int));
-    rc = sb_reserve(ctx, ctx->reg_work, off);
+    rc = sb_reserve(ctx, lane->reg_work, off);
     if (rc) return rc;
-    uint8_t* w = (uint8_t*)ctx->reg_work.p;
+    uint8_t* w = (uint8_t*)lane->reg_work.p;
     T2* Z = (T2*)(w + o_Z);
     T2* Rb = (T2*)(w + o_R);
     T2* Ex = (T2*)(w + o_Ex);
@@ -609,7 +693,12 @@ int run_group(sb_ctx* ctx, cudaStream_t st, const std::vector<PairDesc>& pairs, 
 
     auto k1 = lbx == 4 ? rows_fwd_kernel<T, 4> : rows_fwd_kernel<T, 1>;
     auto k3 = lbx == 4 ? rows_inv_argmax_kernel<T, 4> : rows_inv_argmax_kernel<T, 1>;
-    auto k2 = G == 16 ? cols_xpower_kernel<T, 16> : G == 8 ? cols_xpower_kernel<T, 8> : (G == 4 ? cols_xpower_kernel<T, 4> : (G == 2 ? cols_xpower_kernel<T, 2> : cols_xpower_kernel<T, 1>));
+    auto k2 = G == 16 ? cols_xpower_kernel<T, 16>
+              : G == 12 ? cols_xpower_kernel<T, 12>
+              : G == 8  ? cols_xpower_kernel<T, 8>
+              : G == 4  ? cols_xpower_kernel<T, 4>
+              : G == 2  ? cols_xpower_kernel<T, 2>
+                        : cols_xpower_kernel<T, 1>;
     SB_CUDA(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
     SB_CUDA(ctx, cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
     SB_CUDA(ctx, cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_y));
@@ -617,23 +706,25 @@ int run_group(sb_ctx* ctx, cudaStream_t st, const std::vector<PairDesc>& pairs, 
     const float inv_n = 1.0f / ((float)Sh * (float)Sw);
     for (int p0 = 0; p0 < n; p0 += B) {
         const int nb = std::min(B, n - p0);
-        k1<<<nb * nrb_fwd, 256, smem_x, st>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, tw_x, plan_x, Z, d_nz + p0);
-        k2<<<nb * ncg, 256, smem_y, st>>>(Sh, Sw, ncg, tw_y, plan_y, Z, Rb);
-        k3<<<nb * nrb_inv, 256, smem_x, st>>>(Sh, Sw, lpbx, nrb_inv, tw_x, plan_x, Z, best);
+        k1<<<nb * nrb_fwd, 256, smem_x, st>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, tw_x, px_plan, cx, cxn, Z, d_nz + p0);
+        k2<<<nb * ncg, 256, smem_y, st>>>(Sh, Sw, ncg, tw_y, py_plan, cy, cyn, Z, Rb);
+        k3<<<nb * nrb_inv, 256, smem_x, st>>>(Sh, Sw, lpbx, nrb_inv, tw_x, px_plan, cx, cxn, Z, best);
         peak_final_kernel<<<nb, 32, 0, st>>>(best, nrb_inv, Sw, d_nz + p0, peaks + p0);
         ctx->launches += 4;
         if (uf > 1) {
             updft_twiddle_kernel<T><<<dim3(8, nb), 256, 0, st>>>(peaks + p0, Sh, Sw, uf, rs, dftshift, Ex, Ey);
-            updft_rows_kernel<T><<<nb * nrb_up, 256, 0, st>>>(Sh, Sw, rs, nrb_up, Rb, Ex, Tm);
+            for (int u0 = 0; u0 < rs; u0 += 16) {            // rs = 15 for the reference's upsample_factor 10: one launch
+                updft_rows_kernel<T, 16><<<nb * nrb_up, 256, 0, st>>>(Sh, Sw, rs, u0, nrb_up, Rb, Ex, Tm);
+                ctx->launches++;
+            }
             updft_cols_kernel<T><<<nb * rs, 256, 0, st>>>(Sh, rs, Tm, Ey, mag2);
             updft_final_kernel<<<nb, 32, 0, st>>>(rs, mag2, inv_n, d_nz + p0, peaks + p0);
-            ctx->launches += 4;
+            ctx->launches += 3;
         }
         SB_CUDA(ctx, cudaGetLastError());
     }
-    results.resize(n);
-    SB_CUDA(ctx, cudaMemcpyAsync(results.data(), peaks, (size_t)n * sizeof(PeakOut), cudaMemcpyDeviceToHost, st));
-    SB_CUDA(ctx, cudaStreamSynchronize(st));
+    SB_CUDA(ctx, cudaMemcpyAsync(h_out, peaks, (size_t)n * sizeof(PeakOut), cudaMemcpyDeviceToHost, st));
+    if (do_sync) SB_CUDA(ctx, cudaStreamSynchronize(st));
     return SB_OK;
 }
 
@@ -681,8 +772,9 @@ struct TileSet {
     std::vector<const uint16_t*> dev;       // device address per tile index
 };
 
-int prepare_tiles(sb_ctx* ctx, cudaStream_t st, const std::vector<const void*>& ptrs, int H, int W, int mem, TileSet& ts,
-                  int2** d_mm_out, std::vector<int2>* h_mm) {
+int prepare_tiles(sb_ctx* ctx, Lane* lane, const std::vector<const void*>& ptrs, int H, int W, int mem, TileSet& ts,
+                  int2** d_mm_out, int2* h_mm) {
+    cudaStream_t st = lane->stream;
     for (const void* p : ptrs) {
         if (!p) return sb_fail(ctx, SB_ERR_INVALID, "NULL tile pointer");
         if (ts.index.emplace(p, (int)ts.index.size()).second) ts.dev.push_back(nullptr);
@@ -690,10 +782,10 @@ int prepare_tiles(sb_ctx* ctx, cudaStream_t st, const std::vector<const void*>& 
     const int nt = (int)ts.index.size();
     const size_t tile_bytes = (size_t)H * W * 2;
     if (mem == SB_MEM_HOST) {
-        int rc = sb_reserve(ctx, ctx->reg_tiles, tile_bytes * nt);
+        int rc = sb_reserve(ctx, lane->reg_tiles, tile_bytes * nt);
         if (rc) return rc;
         for (auto& kv : ts.index) {
-            uint8_t* d = (uint8_t*)ctx->reg_tiles.p + tile_bytes * kv.second;
+            uint8_t* d = (uint8_t*)lane->reg_tiles.p + tile_bytes * kv.second;
             SB_CUDA(ctx, cudaMemcpyAsync(d, kv.first, tile_bytes, cudaMemcpyHostToDevice, st));
             ts.dev[kv.second] = (const uint16_t*)d;
         }
@@ -702,38 +794,47 @@ int prepare_tiles(sb_ctx* ctx, cudaStream_t st, const std::vector<const void*>& 
     }
     // device table of tile pointers + min/max
     const size_t meta = round_up64((size_t)nt * sizeof(void*), 256) + (size_t)nt * sizeof(int2);
-    int rc = sb_reserve(ctx, ctx->reg_meta, meta);
+    int rc = sb_reserve(ctx, lane->reg_meta, meta);
     if (rc) return rc;
-    SB_CUDA(ctx, cudaMemcpyAsync(ctx->reg_meta.p, ts.dev.data(), (size_t)nt * sizeof(void*), cudaMemcpyHostToDevice, st));
-    int2* d_mm = (int2*)((uint8_t*)ctx->reg_meta.p + round_up64((size_t)nt * sizeof(void*), 256));
+    SB_CUDA(ctx, cudaMemcpyAsync(lane->reg_meta.p, ts.dev.data(), (size_t)nt * sizeof(void*), cudaMemcpyHostToDevice, st));
+    int2* d_mm = (int2*)((uint8_t*)lane->reg_meta.p + round_up64((size_t)nt * sizeof(void*), 256));
     minmax_init_kernel<<<(nt + 255) / 256, 256, 0, st>>>(d_mm, nt);
     const int bpt = std::max(1, std::min(64, (ctx->sm_count * 8 + nt - 1) / nt));
-    tile_minmax_kernel<<<dim3(bpt, nt), 256, 0, st>>>((const uint16_t* const*)ctx->reg_meta.p, (int64_t)H * W, d_mm);
+    tile_minmax_kernel<<<dim3(bpt, nt), 256, 0, st>>>((const uint16_t* const*)lane->reg_meta.p, (int64_t)H * W, d_mm);
     ctx->launches += 2;
     SB_CUDA(ctx, cudaGetLastError());
-    if (h_mm) {
-        h_mm->resize(nt);
-        SB_CUDA(ctx, cudaMemcpyAsync(h_mm->data(), d_mm, (size_t)nt * sizeof(int2), cudaMemcpyDeviceToHost, st));
-    }
+    if (h_mm) SB_CUDA(ctx, cudaMemcpyAsync(h_mm, d_mm, (size_t)nt * sizeof(int2), cudaMemcpyDeviceToHost, st));
     *d_mm_out = d_mm;
     return SB_OK;
 }
 
 }  // namespace
 
-int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out) {
-    SB_CHECK(ctx, job && out, "job/out is NULL");
-    SB_CHECK(ctx, job->dtype == SB_U16, "only uint16 pixels are implemented");
-    SB_CHECK(ctx, job->n_pairs >= 0 && (job->n_pairs == 0 || job->pairs), "bad pair list");
-    SB_CHECK(ctx, job->upsample_factor >= 1 && job->upsample_factor <= 100, "upsample_factor %d out of range [1, 100]",
-             job->upsample_factor);
-    SB_CHECK(ctx, job->precision >= SB_PREC_F32 && job->precision <= SB_PREC_AUTO, "unknown precision %d", job->precision);
+// A registration job between its enqueue and its completion (asynchronous jobs park here until sb_sync(lane)).
+struct RegGroup {
+    int dir;
+    GroupGeom g;
+    std::vector<int> ids;          // indices into the job's pair list
+    std::vector<PairDesc> pd;
+    size_t first;                  // first PeakOut of the group in the pinned result block
+};
+struct RegPending {
+    sb_register_job job;           // scalars only; `pairs` points into `pairs_copy`
+    std::vector<sb_pair> pairs_copy;
+    sb_pair_result* out = nullptr;
+    std::vector<RegGroup> groups;
+    TileSet ts;
+    int2* d_mm = nullptr;
+    int2* h_mm = nullptr;          // pinned
+    PeakOut* h_peaks = nullptr;    // pinned
+};
+
+static int reg_enqueue(sb_ctx* ctx, Lane* lane, const sb_register_job* job, sb_pair_result* out, RegPending& pr) {
     const int H = job->tile_h, W = job->tile_w, n = job->n_pairs;
-    SB_CHECK(ctx, H > 0 && W > 0, "bad tile shape");
-    if (n == 0) return SB_OK;
-    Lane* lane = sb_lane(ctx, job->lane);
-    SB_CHECK(ctx, lane != nullptr, "lane %d out of range", job->lane);
-    cudaStream_t st = lane->stream;
+    pr.job = *job;
+    pr.pairs_copy.assign(job->pairs, job->pairs + n);
+    pr.job.pairs = pr.pairs_copy.data();
+    pr.out = out;
 
     std::vector<const void*> ptrs;
     for (int i = 0; i < n; ++i) {
@@ -741,18 +842,23 @@ int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_resu
         ptrs.push_back(job->pairs[i].ref);
         ptrs.push_back(job->pairs[i].mov);
     }
-    TileSet ts;
-    int2* d_mm = nullptr;
-    std::vector<int2> h_mm;
-    int rc = prepare_tiles(ctx, st, ptrs, H, W, job->mem, ts, &d_mm, &h_mm);
+    // pinned result block of the lane: [min/max of every unique tile | PeakOut of every pair]
+    const size_t mm_bytes = round_up64((size_t)2 * n * sizeof(int2), 64);
+    int rc = sb_reserve_pinned(ctx, &lane->reg_host, &lane->reg_host_cap, mm_bytes + (size_t)n * sizeof(PeakOut));
+    if (rc) return rc;
+    pr.h_mm = reinterpret_cast<int2*>(lane->reg_host);
+    pr.h_peaks = reinterpret_cast<PeakOut*>((uint8_t*)lane->reg_host + mm_bytes);
+    rc = prepare_tiles(ctx, lane, ptrs, H, W, job->mem, pr.ts, &pr.d_mm, pr.h_mm);
     if (rc) return rc;
 
+    size_t first = 0;
     for (int dir = 0; dir < 2; ++dir) {
-        std::vector<int> ids;
+        RegGroup grp;
+        grp.dir = dir;
         for (int i = 0; i < n; ++i)
-            if (job->pairs[i].dir == dir) ids.push_back(i);
-        if (ids.empty()) continue;
-        GroupGeom g;
+            if (job->pairs[i].dir == dir) grp.ids.push_back(i);
+        if (grp.ids.empty()) continue;
+        GroupGeom& g = grp.g;
         if (dir == SB_DIR_HORIZONTAL) {
             // img_left[margin:-margin, -ov:], img_right[margin:-margin, :ov]   (:677-679)
             const int margin = (int)((double)H * 0.25), ov = job->max_overlap_x;
@@ -766,21 +872,37 @@ int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_resu
             SB_CHECK(ctx, ov >= 1 && ov <= H, "max_overlap_y %d outside [1, %d]", ov, H);
             g = {ov, W - 2 * margin, H - ov, margin, 0, margin};
         }
-        std::vector<PairDesc> pd(ids.size());
-        for (size_t k = 0; k < ids.size(); ++k) {
-            const sb_pair& sp = job->pairs[ids[k]];
-            const int ia = ts.index[sp.ref], ib = ts.index[sp.mov];
-            pd[k].a = ts.dev[ia] + (size_t)g.a_y0 * W + g.a_x0;
-            pd[k].b = ts.dev[ib] + (size_t)g.b_y0 * W + g.b_x0;
-            pd[k].a_tile = ia;
-            pd[k].b_tile = ib;
+        grp.pd.resize(grp.ids.size());
+        for (size_t k = 0; k < grp.ids.size(); ++k) {
+            const sb_pair& sp = job->pairs[grp.ids[k]];
+            const int ia = pr.ts.index[sp.ref], ib = pr.ts.index[sp.mov];
+            grp.pd[k].a = pr.ts.dev[ia] + (size_t)g.a_y0 * W + g.a_x0;
+            grp.pd[k].b = pr.ts.dev[ib] + (size_t)g.b_y0 * W + g.b_x0;
+            grp.pd[k].a_tile = ia;
+            grp.pd[k].b_tile = ib;
         }
-        std::vector<PeakOut> res;
-        const int first_prec = job->precision == SB_PREC_F64 ? SB_PREC_F64 : SB_PREC_F32;
-        rc = first_prec == SB_PREC_F64 ? run_group<double>(ctx, st, pd, g, W, d_mm, job->upsample_factor, res)
-                                       : run_group<float>(ctx, st, pd, g, W, d_mm, job->upsample_factor, res);
+        grp.first = first;
+        first += grp.ids.size();
+        rc = job->precision == SB_PREC_F64
+                 ? run_group<double>(ctx, lane, grp.pd, g, W, pr.d_mm, job->upsample_factor, pr.h_peaks + grp.first, false)
+                 : run_group<float>(ctx, lane, grp.pd, g, W, pr.d_mm, job->upsample_factor, pr.h_peaks + grp.first, false);
         if (rc) return rc;
-        std::vector<int> prec(ids.size(), first_prec);
+        pr.groups.push_back(std::move(grp));
+    }
+    return SB_OK;
+}
+
+// Waits for the lane, redoes low-confidence pairs in float64 (SB_PREC_AUTO) and writes the caller's results.
+static int reg_complete(sb_ctx* ctx, Lane* lane, RegPending& pr) {
+    SB_CUDA(ctx, cudaStreamSynchronize(lane->stream));
+    const sb_register_job* job = &pr.job;
+    const int W = job->tile_w;
+    const int first_prec = job->precision == SB_PREC_F64 ? SB_PREC_F64 : SB_PREC_F32;
+    std::vector<int2> mm(pr.h_mm, pr.h_mm + pr.ts.index.size());      // the pinned block is reused by the redo below
+    for (RegGroup& grp : pr.groups) {
+        const GroupGeom& g = grp.g;
+        std::vector<PeakOut> res(pr.h_peaks + grp.first, pr.h_peaks + grp.first + grp.ids.size());
+        std::vector<int> prec(grp.ids.size(), first_prec);
         if (job->precision == SB_PREC_AUTO) {
             // A peak that does not stand clear of the correlation noise floor (rms 1/sqrt(N), expected
             // maximum ~ sqrt(2 ln N / N)) is an argmax among near-equal values: redo those in float64,
@@ -789,14 +911,14 @@ int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_resu
             const double floor_max = std::sqrt(2.0 * std::log(N) / N);
             std::vector<PairDesc> redo;
             std::vector<int> redo_k;
-            for (size_t k = 0; k < ids.size(); ++k)
+            for (size_t k = 0; k < grp.ids.size(); ++k)
                 if (!(res[k].peak > 4.0 * floor_max) || !(res[k].peak > 1.5f * res[k].runner_up)) {
-                    redo.push_back(pd[k]);
+                    redo.push_back(grp.pd[k]);
                     redo_k.push_back((int)k);
                 }
             if (!redo.empty()) {
-                std::vector<PeakOut> res2;
-                rc = run_group<double>(ctx, st, redo, g, W, d_mm, job->upsample_factor, res2);
+                std::vector<PeakOut> res2(redo.size());
+                int rc = run_group<double>(ctx, lane, redo, g, W, pr.d_mm, job->upsample_factor, res2.data(), true);
                 if (rc) return rc;
                 for (size_t j = 0; j < redo_k.size(); ++j) {
                     res[redo_k[j]] = res2[j];
@@ -804,17 +926,65 @@ int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_resu
                 }
             }
         }
-        for (size_t k = 0; k < ids.size(); ++k) {
-            sb_pair_result* r = &out[ids[k]];
+        for (size_t k = 0; k < grp.ids.size(); ++k) {
+            sb_pair_result* r = &pr.out[grp.ids[k]];
             memset(r, 0, sizeof(*r));
-            finish_pair(res[k], g, dir, job->upsample_factor, r);
-            const sb_pair& sp = job->pairs[ids[k]];
-            const int2 ma = h_mm[ts.index[sp.ref]], mb = h_mm[ts.index[sp.mov]];
+            finish_pair(res[k], g, grp.dir, job->upsample_factor, r);
+            const sb_pair& sp = job->pairs[grp.ids[k]];
+            const int2 ma = mm[pr.ts.index[sp.ref]], mb = mm[pr.ts.index[sp.mov]];
             r->ref_min = ma.x; r->ref_max = ma.y; r->mov_min = mb.x; r->mov_max = mb.y;
             r->precision = prec[k];
         }
     }
     return SB_OK;
+}
+
+// Completes the lane's parked asynchronous registration, if any (called from sb_sync and before new work on the lane).
+int sb_register_complete(sb_ctx* ctx, int lane_idx) {
+    Lane* lane = sb_lane(ctx, lane_idx);
+    if (!lane || !lane->reg_pending) return SB_OK;
+    RegPending* pr = static_cast<RegPending*>(lane->reg_pending);
+    lane->reg_pending = nullptr;
+    const int rc = reg_complete(ctx, lane, *pr);
+    delete pr;
+    return rc;
+}
+
+void sb_register_discard(sb_ctx* ctx, int lane_idx) {
+    Lane* lane = sb_lane(ctx, lane_idx);
+    if (lane && lane->reg_pending) {
+        delete static_cast<RegPending*>(lane->reg_pending);
+        lane->reg_pending = nullptr;
+    }
+}
+
+int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out, bool async) {
+    SB_CHECK(ctx, job && out, "job/out is NULL");
+    SB_CHECK(ctx, job->dtype == SB_U16, "only uint16 pixels are implemented");
+    SB_CHECK(ctx, job->n_pairs >= 0 && (job->n_pairs == 0 || job->pairs), "bad pair list");
+    SB_CHECK(ctx, job->upsample_factor >= 1 && job->upsample_factor <= 100, "upsample_factor %d out of range [1, 100]",
+             job->upsample_factor);
+    SB_CHECK(ctx, job->precision >= SB_PREC_F32 && job->precision <= SB_PREC_AUTO, "unknown precision %d", job->precision);
+    SB_CHECK(ctx, job->tile_h > 0 && job->tile_w > 0, "bad tile shape");
+    Lane* lane = sb_lane(ctx, job->lane);
+    SB_CHECK(ctx, lane != nullptr, "lane %d out of range", job->lane);
+    int rc = sb_register_complete(ctx, job->lane);        // one parked job per lane: finish the previous one first
+    if (rc) return rc;
+    if (job->n_pairs == 0) return SB_OK;
+    RegPending* pr = new RegPending();
+    rc = reg_enqueue(ctx, lane, job, out, *pr);
+    if (rc) {
+        cudaStreamSynchronize(lane->stream);              // nothing of the failed job may still use its buffers
+        delete pr;
+        return rc;
+    }
+    if (async) {
+        lane->reg_pending = pr;
+        return SB_OK;
+    }
+    rc = reg_complete(ctx, lane, *pr);
+    delete pr;
+    return rc;
 }
 
 int sb_normalize_impl(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int dtype, int mem) {
@@ -827,10 +997,12 @@ int sb_normalize_impl(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, in
     for (int i = 0; i < n_tiles; ++i) ptrs.push_back((const uint8_t*)tiles + i * px * 2);
     TileSet ts;
     int2* d_mm = nullptr;
-    int rc = prepare_tiles(ctx, st, ptrs, tile_h, tile_w, mem, ts, &d_mm, nullptr);
+    int rc = sb_register_complete(ctx, 0);
+    if (rc) return rc;
+    rc = prepare_tiles(ctx, lane, ptrs, tile_h, tile_w, mem, ts, &d_mm, nullptr);
     if (rc) return rc;
     // tiles were given contiguously, so tile i has index i and (host case) sits at reg_tiles + i * px
-    const uint16_t* d_in = mem == SB_MEM_HOST ? (const uint16_t*)ctx->reg_tiles.p : (const uint16_t*)tiles;
+    const uint16_t* d_in = mem == SB_MEM_HOST ? (const uint16_t*)lane->reg_tiles.p : (const uint16_t*)tiles;
     uint16_t* d_out = (uint16_t*)out;
     if (mem == SB_MEM_HOST) {
         rc = sb_reserve(ctx, lane->canvas, px * 2 * n_tiles);

@@ -39,6 +39,12 @@ struct Lane {
     void* meta_host = nullptr;      // pinned staging for per-job metadata
     size_t meta_host_cap = 0;
     cudaEvent_t meta_free = nullptr; // the previous job's metadata H2D has been consumed
+    cudaEvent_t mark = nullptr;      // sb_lane_mark / sb_lane_wait_mark
+    bool marked = false;
+    DevBuf reg_tiles, reg_work, reg_meta;   // registration workspace of this lane (grown on demand)
+    void* reg_host = nullptr;       // pinned block the registration results are copied into
+    size_t reg_host_cap = 0;
+    void* reg_pending = nullptr;    // parked asynchronous registration job (RegPending in reg.cu)
     std::vector<int32_t> perm;      // cached block-row order of the paste kernel (fuse.cu) ...
     uint64_t perm_sig = 0;          // ... and the geometry signature it was computed for
 };
@@ -54,10 +60,6 @@ struct sb_ctx {
     CUresult (*encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
-    // registration workspace (grown on demand)
-    DevBuf reg_tiles, reg_work, reg_meta;
-    void* reg_meta_host = nullptr;
-    size_t reg_meta_host_cap = 0;
     std::unordered_map<uint64_t, DevBuf> twiddle_cache;   // key: (n << 1 | is_double)
 };
 
@@ -85,7 +87,9 @@ static inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m 
 int sb_fuse_region_impl(sb_ctx* ctx, const sb_fuse_job* job, int lane);
 int sb_flatfield_apply_impl(sb_ctx* ctx, int channel, const void* tiles, void* out, int n_tiles, int tile_h,
                             int tile_w, int dtype, int mem);
-int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out);
+int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out, bool async);
+int sb_register_complete(sb_ctx* ctx, int lane);     // finish the lane's parked asynchronous registration, if any
+void sb_register_discard(sb_ctx* ctx, int lane);
 int sb_normalize_impl(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int dtype,
                       int mem);
 

@@ -31,6 +31,8 @@ class WellPipeline:
         self.canvas_shape = (spec.channels, spec.num_z, Hc, Wc)
         self.ov = spec.strip_overlaps()
         self.staging, self.plans, self.pairs = [], [], []
+        self.inflight = [None] * self.depth
+        self.last_lane = None
         shape = (spec.rows, spec.cols, spec.channels, spec.num_z)
         strides = np.array([spec.cols * spec.channels * spec.num_z, spec.channels * spec.num_z, spec.num_z, 1])
         for lane in range(self.depth):
@@ -47,27 +49,41 @@ class WellPipeline:
                                        blend_ov=self.ov))
             self.pairs.append(well_pairs(spec, ptr)[0])
 
-    def submit(self, host_tiles: np.ndarray, host_out: np.ndarray) -> List[dict]:
+    def submit(self, host_tiles: np.ndarray, host_out: np.ndarray):
         """``host_tiles``: uint16 [rows, cols, C, Z, H, W] (C-contiguous, ideally pinned).
-        ``host_out``: uint16 (1, C, Z, Hc, Wc).  Returns the pair results of this region (the call
-        returns once registration is done; fusion + download complete at the next sync of the lane)."""
+        ``host_out``: uint16 (1, C, Z, Hc, Wc).  Everything is enqueued on the next lane -- upload, registration
+        (``sb_register_pairs_async``), fusion, download -- and the call returns immediately, so the upload of the next
+        region overlaps this one's kernels and the previous one's download.  Returns a ``PendingRegistration`` whose
+        ``get()`` yields the pair results once the lane has been synchronised (next reuse of the lane, or ``drain``)."""
         assert host_tiles.dtype == np.uint16 and host_tiles.flags.c_contiguous
         assert host_out.shape[-4:] == self.canvas_shape and host_out.flags.c_contiguous
         lane = self.next
         self.next = (self.next + 1) % self.depth
-        self.ctx.sync(lane)
+        self.ctx.sync(lane)                                  # the lane's previous region is complete (results landed)
+        if self.inflight[lane] is not None:
+            self.inflight[lane].mark_synced()
+        # uploads of consecutive regions run back to back (this lane's upload waits for the previous lane's upload,
+        # not for its kernels or download), so the two bus directions stay busy at the same time
+        if self.last_lane is not None:
+            self.ctx.lane_wait_mark(lane, self.last_lane)
         self.ctx.memcpy_async(lane, self.staging[lane], host_tiles, self.well_bytes, 0)
-        res = []
+        self.ctx.lane_mark(lane)
+        self.last_lane = lane
+        pending = None
         if self.register:
-            res = self.ctx.register_pairs(self.pairs[lane], (self.spec.tile_h, self.spec.tile_w), self.ov[0], self.ov[1],
-                                          mem=_ffi.SB_MEM_DEVICE, lane=lane)
+            pending = self.ctx.register_pairs_async(self.pairs[lane], (self.spec.tile_h, self.spec.tile_w), self.ov[0],
+                                                    self.ov[1], mem=_ffi.SB_MEM_DEVICE, lane=lane)
+        self.inflight[lane] = pending
         plan = self.plans[lane]
         plan.job.out = host_out.ctypes.data
         plan.run(lane)
-        return res
+        return pending
 
     def drain(self):
         self.ctx.sync(-1)
+        for p in self.inflight:
+            if p is not None:
+                p.mark_synced()
 
     def close(self):
         self.drain()

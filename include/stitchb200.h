@@ -133,6 +133,12 @@ typedef struct sb_fuse_job {
  * lane's stream and return; sb_sync(lane) waits.  Buffers must stay valid until then. */
 int sb_fuse_region(sb_ctx* ctx, const sb_fuse_job* job, int lane);
 int sb_sync(sb_ctx* ctx, int lane);      /* lane < 0: all lanes */
+/* Cross-lane ordering for pipelines: sb_lane_mark records a marker at the current end of `lane`'s stream;
+ * sb_lane_wait_mark makes everything enqueued on `lane` afterwards wait for `other`'s latest marker (no host wait).
+ * WellPipeline uses it to keep the uploads of consecutive regions back to back on the bus while each region's
+ * kernels and download overlap the next upload. */
+int sb_lane_mark(sb_ctx* ctx, int lane);
+int sb_lane_wait_mark(sb_ctx* ctx, int lane, int other);
 /* Use the caller's stream (e.g. torch's current stream) for a lane; NULL restores the lane's own. */
 int sb_set_lane_stream(sb_ctx* ctx, int lane, void* cuda_stream);
 /* Device-canvas row pitch (elements) the library uses for a given width: round_up(width, 64). */
@@ -180,6 +186,10 @@ typedef struct sb_register_job {
 } sb_register_job;
 
 int sb_register_pairs(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out);
+/* Asynchronous form for pipelines (calculate_shifts of region i overlapping the upload of region i+1): enqueues the
+ * chain on job->lane and returns; `out` is filled when sb_sync(job->lane) returns (or when the next registration
+ * on that lane starts).  The pair list is copied; tiles and `out` must stay valid until then.  One parked job per lane. */
+int sb_register_pairs_async(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out);
 
 /* Standalone normalize_image(img) (:844-855) for n_tiles tiles (whole-tile min/max stretch,
  * float64 arithmetic, truncating cast). */

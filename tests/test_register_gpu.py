@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN_DIR, load_golden
+from oracle import synth
 
 pytestmark = pytest.mark.gpu
 
@@ -161,3 +162,69 @@ def test_device_memory_batch(ctx):
     for r, (a, b, d) in zip(res, host_job):
         exp_int, _, det = oracle_pair(a, b, 28, d)
         assert (r["dy"], r["dx"]) == exp_int and r["coarse"] == det["coarse"]
+
+
+def test_async_registration_matches_sync_and_overlaps_lanes(ctx):
+    """sb_register_pairs_async: results land at sb_sync(lane); three lanes in flight at once give the same
+    answers as the synchronous call (per-lane workspaces do not interfere)."""
+    from image_stitcher_b200 import _ffi
+    rng = np.random.default_rng(5)
+    H, W, ov = 256, 320, 34
+    jobs = []
+    for lane in range(3):
+        world = synth.make_world(H * 2 + 64, W * 2 + 64, rng)
+        a = np.clip(world[20:20 + H, 20:20 + W], 0, 65535).astype(np.uint16)
+        bh = np.clip(world[20 + lane:20 + lane + H, 20 + W - ov + 1:20 + 2 * W - ov + 1], 0, 65535).astype(np.uint16)
+        bv = np.clip(world[20 + H - ov - lane:20 + 2 * H - ov - lane, 22:22 + W], 0, 65535).astype(np.uint16)
+        jobs.append([(a, bh, _ffi.SB_DIR_HORIZONTAL), (a, bv, _ffi.SB_DIR_VERTICAL)])
+    sync_res = [ctx.register_pairs(j, (H, W), ov, ov, lane=0) for j in jobs]
+    pend = [ctx.register_pairs_async(j, (H, W), ov, ov, lane=lane) for lane, j in enumerate(jobs)]
+    got = [p.get() for p in pend]
+    for s, g in zip(sync_res, got):
+        assert [(r["dy"], r["dx"], r["coarse"], r["fine"]) for r in s] == [(r["dy"], r["dx"], r["coarse"], r["fine"]) for r in g]
+    # a second job on a lane with a parked one completes the parked one first
+    p0 = ctx.register_pairs_async(jobs[0], (H, W), ov, ov, lane=1)
+    again = ctx.register_pairs(jobs[1], (H, W), ov, ov, lane=1)
+    assert [(r["dy"], r["dx"]) for r in again] == [(r["dy"], r["dx"]) for r in sync_res[1]]
+    assert [(r["dy"], r["dx"]) for r in p0.get()] == [(r["dy"], r["dx"]) for r in sync_res[0]]
+    assert ctx.register_pairs_async([], (H, W), ov, ov).get() == []
+
+
+def test_well_pipeline_host_buffers_match_oracle(ctx):
+    """The end-to-end call the benchmark times (host tiles in -> shifts + host canvas out over 3 lanes)."""
+    import torch
+    from image_stitcher_b200 import _ffi
+    from image_stitcher_b200.pipeline import WellPipeline
+    from image_stitcher_b200.plate import PlateSpec, make_plate
+    from oracle import stitch_ref as sr
+    spec = PlateSpec(wells=5, rows=2, cols=2, tile_h=256, tile_w=256, channels=2, reg_channel=1, jitter=2, seed=3)
+    plate = make_plate(spec, device="cuda:0")
+    ctx.clear_fields()
+    for c in range(spec.channels):
+        ctx.set_flatfield(c, plate.flat[c], mem=_ffi.SB_MEM_DEVICE)
+    pipe = WellPipeline(ctx, spec, apply_flatfield=True)
+    Wc, Hc = spec.canvas_size()
+    host = [plate.pool[w].cpu().numpy().view(np.uint16).copy() for w in range(spec.wells)]
+    outs = [np.zeros((1, spec.channels, spec.num_z, Hc, Wc), np.uint16) for _ in range(spec.wells)]
+    pend = [pipe.submit(host[w], outs[w]) for w in range(spec.wells)]
+    pipe.drain()
+    names = [f"ch{c}" for c in range(spec.channels)]
+    xs, ys = spec.stage_positions()
+    from image_stitcher_b200.plate import well_pairs
+    ovx, ovy = spec.strip_overlaps()
+    for w in range(spec.wells):
+        hp, _ = well_pairs(spec, lambda r, c, ch, z: host[w][r, c, ch, z])
+        exp = [(sr.calculate_horizontal_shift(a, b, ovx) if d == 0 else sr.calculate_vertical_shift(a, b, ovy))
+               for a, b, d in hp]
+        assert [(r["dy"], r["dx"]) for r in pend[w].get()] == exp
+        st = sr.RegionState(tile_h=spec.tile_h, tile_w=spec.tile_w, pixel_size_um=spec.pixel_size_um,
+                            monochrome_channels=names, channel_names=names, apply_flatfield=True,
+                            flatfields={c: plate.flat[c].cpu().numpy() for c in range(spec.channels)})
+        recs = []
+        for fov in sorted(range(spec.rows * spec.cols), key=str):
+            r, c = divmod(fov, spec.cols)
+            for ch in range(spec.channels):
+                recs.append(sr.TileRec(x_mm=xs[c], y_mm=ys[r], z_level=0, channel=names[ch], pixels=host[w][r, c, ch, 0], fov=fov))
+        assert np.array_equal(outs[w], sr.stitch_region(st, recs))
+    pipe.close()
+    ctx.clear_fields()
