@@ -224,7 +224,9 @@ static int set_field(sb_ctx* ctx, FieldPool& pool, const char* what, int channel
         bool ok = true;
         for (size_t i = 0; i < (size_t)h * w && ok; ++i) {
             const float v = h_field[i];
-            ok = is_flat ? (v >= 9.5367431640625e-07f && v <= 1048576.0f) : (v >= -1048576.0f && v <= 1048576.0f);
+            // flat >= 2^-5 and |dark| <= 2^16 also keep |quotient| < 2^22, which the magic-number truncation of the
+            // paste kernel needs (fuse.cu: trunc_sat_pack); fields outside take the generic kernel
+            ok = is_flat ? (v >= 0.03125f && v <= 1048576.0f) : (v >= -65536.0f && v <= 65536.0f);
         }
         if (!ok) pool.fast_ok = false;
     } else {
