@@ -26,7 +26,15 @@ struct FftPlan {
     int nfac;
     int fac[16];
     int gemm_radix;   // odd radix handled by pass_odd_gemm (needs its cos/sin table in shared memory); 0 = none
+    // per-pass constants, filled by the host (make_plan): Ns = product of the radices already applied, M = n / radix,
+    // tstep = n / (Ns * radix), and multipliers for division by M and Ns without the integer-divide sequence
+    int Ns[16], M[16], tstep[16];
+    unsigned mM[16], mNs[16];
 };
+
+// n / d for 0 <= n, n * d < 2^32, with m = ceil(2^32 / d) precomputed (m == 0 encodes d == 1)
+__host__ __device__ inline unsigned fastdiv_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) + d - 1) / d); }
+__device__ __forceinline__ int fastdiv(int n, unsigned m) { return m ? (int)__umulhi((unsigned)n, m) : n; }
 
 template <typename T> struct Vec2;
 template <> struct Vec2<float> { using type = float2; };
@@ -58,16 +66,14 @@ __device__ __forceinline__ T2 cmul(const T2 a, const T2 w) {
 
 template <typename T2, int LB>
 __device__ __forceinline__ void pass_radix4(const T2* __restrict__ a, T2* __restrict__ b, const T2* __restrict__ tw, int N, int Ns,
-                                            int groups, bool inverse) {
-    const int M = N >> 2;
-    const int tstep = N / (Ns * 4);
+                                            int M, int tstep, unsigned mM, unsigned mNs, int groups, bool inverse) {
     const int items = M * groups;
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int g = it / M, j = it - g * M;
-        const int k = j % Ns;
+        const int g = fastdiv(it, mM), j = it - g * M;
+        const int jq = fastdiv(j, mNs), k = j - jq * Ns;
         T2 w1 = tw[k * tstep], w2 = tw[2 * k * tstep], w3 = tw[3 * k * tstep];
         if (inverse) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-        const int dst = (j / Ns) * Ns * 4 + k;
+        const int dst = jq * Ns * 4 + k;
 #pragma unroll
         for (int l = 0; l < LB; ++l) {
             const T2* in = a + (size_t)(g * LB + l) * N + j;
@@ -91,16 +97,14 @@ __device__ __forceinline__ void pass_radix4(const T2* __restrict__ a, T2* __rest
 
 template <typename T2, int LB>
 __device__ __forceinline__ void pass_radix2(const T2* __restrict__ a, T2* __restrict__ b, const T2* __restrict__ tw, int N, int Ns,
-                                            int groups, bool inverse) {
-    const int M = N >> 1;
-    const int tstep = N / (Ns * 2);
+                                            int M, int tstep, unsigned mM, unsigned mNs, int groups, bool inverse) {
     const int items = M * groups;
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int g = it / M, j = it - g * M;
-        const int k = j % Ns;
+        const int g = fastdiv(it, mM), j = it - g * M;
+        const int jq = fastdiv(j, mNs), k = j - jq * Ns;
         T2 w1 = tw[k * tstep];
         if (inverse) w1.y = -w1.y;
-        const int dst = (j / Ns) * Ns * 2 + k;
+        const int dst = jq * Ns * 2 + k;
 #pragma unroll
         for (int l = 0; l < LB; ++l) {
             const T2* in = a + (size_t)(g * LB + l) * N + j;
@@ -307,23 +311,29 @@ __device__ __forceinline__ void pass_odd_gemm(float2* __restrict__ a, float2* __
     const int QP = (h + 3) & ~3;
     const int tstep = N / (Ns * R);
     // ---- step 1: (pre-twiddle,) fold, transpose.  T[(r * M + j) * nlines + line]; r = 0 holds y_0.
-    for (int it = threadIdx.x; it < M * nlines; it += blockDim.x) {
-        const int j = it / nlines, line = it - j * nlines;
-        b[it] = a[(size_t)line * N + j];
-    }
-    for (int it = threadIdx.x; it < h * M * nlines; it += blockDim.x) {
-        const int rem = it / nlines, line = it - rem * nlines;
-        const int r = rem / M + 1, j = rem - (r - 1) * M;
-        float2 y1 = a[(size_t)line * N + r * M + j], y2 = a[(size_t)line * N + (R - r) * M + j];
-        if (Ns > 1) {
-            const int k = j % Ns;
-            float2 w1 = tw[(int)(((long long)r * k * tstep) % N)], w2 = tw[(int)(((long long)(R - r) * k * tstep) % N)];
-            if (inverse) { w1.y = -w1.y; w2.y = -w2.y; }
-            y1 = cmul(y1, w1);
-            y2 = cmul(y2, w2);
+    // Lanes run over lines (LP = lines rounded up to a power of two <= 32), the rest of the block over (r, j).
+    int lpl = 2;
+    while ((1 << lpl) < nlines && lpl < 5) ++lpl;
+    const int LP = 1 << lpl;
+    const int line0 = threadIdx.x & (LP - 1);
+    const int slot = threadIdx.x >> lpl, nslots = blockDim.x >> lpl;
+    for (int line = line0; line < nlines; line += LP) {
+        const float2* al = a + (size_t)line * N;
+        for (int idx = slot; idx < M; idx += nslots) b[(size_t)idx * nlines + line] = al[idx];
+        for (int r = 1 + slot; r <= h; r += nslots) {
+            for (int j = 0; j < M; ++j) {
+                float2 y1 = al[r * M + j], y2 = al[(R - r) * M + j];
+                if (Ns > 1) {
+                    const int k = j % Ns;
+                    float2 w1 = tw[(int)(((long long)r * k * tstep) % N)], w2 = tw[(int)(((long long)(R - r) * k * tstep) % N)];
+                    if (inverse) { w1.y = -w1.y; w2.y = -w2.y; }
+                    y1 = cmul(y1, w1);
+                    y2 = cmul(y2, w2);
+                }
+                b[(size_t)(r * M + j) * nlines + line] = make_float2(y1.x + y2.x, y1.y + y2.y);
+                b[(size_t)((R - r) * M + j) * nlines + line] = make_float2(y1.x - y2.x, y1.y - y2.y);
+            }
         }
-        b[(size_t)(r * M + j) * nlines + line] = make_float2(y1.x + y2.x, y1.y + y2.y);
-        b[(size_t)((R - r) * M + j) * nlines + line] = make_float2(y1.x - y2.x, y1.y - y2.y);
     }
     __syncthreads();
     // ---- step 2: the GEMM.  item = (q tile of 4, column group = (j, 4 lines)); lanes run over column groups.
@@ -387,16 +397,16 @@ __device__ __forceinline__ void pass_odd_gemm(float2* __restrict__ a, float2* __
         }
     }
     // ---- X[0] = y_0 + sum_r e_r
-    for (int it = threadIdx.x; it < M * nlines; it += blockDim.x) {
-        const int j = it / nlines, line = it - j * nlines;
-        float2 acc = b[it];
-        for (int r = 1; r <= h; ++r) {
-            const float2 e = b[(size_t)(r * M + j) * nlines + line];
-            acc.x += e.x;
-            acc.y += e.y;
+    for (int line = line0; line < nlines; line += LP)
+        for (int j = slot; j < M; j += nslots) {
+            float2 acc = b[(size_t)j * nlines + line];
+            for (int r = 1; r <= h; ++r) {
+                const float2 e = b[(size_t)(r * M + j) * nlines + line];
+                acc.x += e.x;
+                acc.y += e.y;
+            }
+            a[(size_t)line * N + (j / Ns) * Ns * R + (j % Ns)] = acc;
         }
-        a[(size_t)line * N + (j / Ns) * Ns * R + (j % Ns)] = acc;
-    }
 }
 
 template <typename T2>
@@ -427,8 +437,8 @@ __device__ T2* fft_lines(T2* buf0, T2* buf1, const T2* __restrict__ tw, const Ff
     for (int f = 0; f < plan.nfac; ++f) {
         const int R = plan.fac[f];
         bool in_place = false;
-        if (R == 4) pass_radix4<T2, LB>(a, b, tw, N, Ns, groups, inverse);
-        else if (R == 2) pass_radix2<T2, LB>(a, b, tw, N, Ns, groups, inverse);
+        if (R == 4) pass_radix4<T2, LB>(a, b, tw, N, Ns, plan.M[f], plan.tstep[f], plan.mM[f], plan.mNs[f], groups, inverse);
+        else if (R == 2) pass_radix2<T2, LB>(a, b, tw, N, Ns, plan.M[f], plan.tstep[f], plan.mM[f], plan.mNs[f], groups, inverse);
         else if (ctab != nullptr && R == plan.gemm_radix && (nlines & 3) == 0 &&
                  OddGemm<T2>::run(a, b, tw, ctab, N, Ns, R, nlines, inverse)) in_place = true;
         else if (R & 1) pass_odd_sym<T2, LB, (sizeof(T2) == 8 ? (LB >= 4 ? 4 : 8) : (LB >= 4 ? 2 : 4))>(a, b, tw, N, Ns, R, groups, inverse);

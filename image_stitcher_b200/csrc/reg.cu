@@ -94,10 +94,27 @@ __global__ void __launch_bounds__(256) tile_minmax_kernel(const uint16_t* const*
 }
 
 // normalize_image (:844-855): ((v - min) / (max - min)) * 65535 in float64, truncating cast.
-__device__ __forceinline__ int stretch_px(unsigned v, int mn, int mx) {
+__device__ __forceinline__ int stretch_px_f64(unsigned v, int mn, int mx) {
     if (mx <= mn) return 0;                       // 0/0 -> NaN -> undefined cast in the reference; defined as 0
     const double q = __ddiv_rn((double)((int)v - mn), (double)(mx - mn));
     return (int)(q * 65535.0);
+}
+
+// The same value without the float64 divide.  With a = v - min, b = max - min the exact quotient a * 65535 / b is
+// rational with denominator b <= 65535, so unless it is an integer it lies at least 1 / 65535 away from the next
+// one, while the float64 evaluation is off by at most 65535 * 2^-52: trunc() of both agree.  When b divides
+// a * 65535 the float64 result can land on either side of the integer -- only then the float64 sequence is run.
+// `inv` = 65535.0f / b (computed once per tile).
+__device__ __forceinline__ int stretch_px(unsigned v, int mn, int mx, float inv) {
+    if (mx <= mn) return 0;
+    const unsigned b = (unsigned)(mx - mn);
+    const unsigned num = (unsigned)((int)v - mn) * 65535u;                 // < 2^32
+    unsigned k = (unsigned)__float2int_rz(__uint2float_rn((unsigned)((int)v - mn)) * inv);
+    unsigned rem = num - k * b;                                            // k is off by at most one either way
+    if ((int)rem < 0) { --k; rem += b; }
+    else if (rem >= b) { ++k; rem -= b; }
+    if (rem == 0 && k != 0) return stretch_px_f64(v, mn, mx);              // exact quotient (rare): reproduce float64 rounding
+    return (int)k;
 }
 
 __global__ void __launch_bounds__(256) normalize_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
@@ -106,7 +123,7 @@ __global__ void __launch_bounds__(256) normalize_kernel(const uint16_t* __restri
     const uint16_t* t = in + (int64_t)blockIdx.y * px;
     uint16_t* o = out + (int64_t)blockIdx.y * px;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px; i += (int64_t)gridDim.x * blockDim.x)
-        o[i] = (uint16_t)stretch_px(t[i], m.x, m.y);
+        o[i] = (uint16_t)stretch_px_f64(t[i], m.x, m.y);
 }
 
 // cos/sin table of the big odd radix (fft.cuh: pass_odd_gemm): global -> shared, right after the twiddles.
@@ -138,35 +155,37 @@ __global__ void __launch_bounds__(256, 2) rows_fwd_kernel(const PairDesc* __rest
     const PairDesc pd = pairs[p];
     int seen = 0;                                // bit 0: strip a has a non-zero pixel, bit 1: strip b
     const int2 ma = mm[pd.a_tile], mb = mm[pd.b_tile];
+    const float inva = ma.y > ma.x ? 65535.0f / (float)(ma.y - ma.x) : 0.f;
+    const float invb = mb.y > mb.x ? 65535.0f / (float)(mb.y - mb.x) : 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int i = threadIdx.x; i < Sw; i += blockDim.x) tw[i] = tw_g[i];
-    // strip crop + stretch fused into the load; four independent pixel pairs in flight per thread
-    for (int i0 = threadIdx.x; i0 < lpb * Sw; i0 += 4 * blockDim.x) {
-        unsigned av[4], bv[4];
-        bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * blockDim.x;
-            const int l = i / Sw, x = i - l * Sw;
-            ok[u] = i < lpb * Sw && y0 + l < Sh;
-            av[u] = bv[u] = 0;
-            if (ok[u]) {
-                const size_t off = (size_t)(y0 + l) * tile_w + x;
-                av[u] = pd.a[off];
-                bv[u] = pd.b[off];
-            }
+    // strip crop + stretch fused into the load: a warp walks one strip row at a time (coalesced 64-byte reads of both
+    // strips), four independent pixel pairs in flight per lane; no integer divisions in the index arithmetic
+    for (int l = warp; l < lpb; l += nwarps) {
+        T2* row = buf0 + (size_t)l * Sw;
+        if (y0 + l >= Sh) {
+            for (int x = lane; x < Sw; x += 32) row[x] = mk2<T2, T>(0, 0);
+            continue;
         }
+        const uint16_t* pa = pd.a + (size_t)(y0 + l) * tile_w;
+        const uint16_t* pb = pd.b + (size_t)(y0 + l) * tile_w;
+        for (int x0 = lane; x0 < Sw; x0 += 128) {
+            unsigned av[4], bv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * blockDim.x;
-            if (i >= lpb * Sw) continue;
-            T2 z = mk2<T2, T>(0, 0);
-            if (ok[u]) {
-                const int na = stretch_px(av[u], ma.x, ma.y), nb = stretch_px(bv[u], mb.x, mb.y);
-                seen |= (na != 0 ? 1 : 0) | (nb != 0 ? 2 : 0);
-                z.x = (T)(na * kInScale);
-                z.y = (T)(nb * kInScale);
+            for (int u = 0; u < 4; ++u) {
+                const int x = x0 + 32 * u;
+                av[u] = x < Sw ? pa[x] : 0u;
+                bv[u] = x < Sw ? pb[x] : 0u;
             }
-            buf0[i] = z;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int x = x0 + 32 * u;
+                if (x < Sw) {
+                    const int na = stretch_px(av[u], ma.x, ma.y, inva), nb = stretch_px(bv[u], mb.x, mb.y, invb);
+                    seen |= (na != 0 ? 1 : 0) | (nb != 0 ? 2 : 0);
+                    row[x] = mk2<T2, T>((T)(na * kInScale), (T)(nb * kInScale));
+                }
+            }
         }
     }
     // An all-zero strip has an exactly zero spectrum in the reference (P == 0 -> cc == 0 -> argmax 0);
@@ -176,11 +195,15 @@ __global__ void __launch_bounds__(256, 2) rows_fwd_kernel(const PairDesc* __rest
     T2* res = fft_lines<T2, LB>(buf0, buf1, tw, plan, lpb, false, ctab);
     // Z is kept TRANSPOSED (Zt[kx][y], y fastest) so that the column pass reads and writes whole contiguous lines;
     // here the lpb rows of this block are lpb consecutive y of every kx: runs of 8 * lpb contiguous bytes.
+    // Lanes run over the rows (LP = lpb rounded up to a power of two), the rest of the block over kx.
     T2* zp = Z + (size_t)p * Sh * Sw;
-    for (int i = threadIdx.x; i < lpb * Sw; i += blockDim.x) {
-        const int x = i / lpb, l = i - x * lpb;
-        if (y0 + l < Sh) zp[(size_t)x * Sh + y0 + l] = res[(size_t)l * Sw + x];
-    }
+    int lpl = 0;
+    while ((1 << lpl) < lpb && lpl < 5) ++lpl;
+    const int l = threadIdx.x & ((1 << lpl) - 1);
+    const int xs = threadIdx.x >> lpl, nxs = blockDim.x >> lpl;
+    for (int l2 = l; l2 < lpb; l2 += (1 << lpl))
+        if (y0 + l2 < Sh)
+            for (int x = xs; x < Sw; x += nxs) zp[(size_t)x * Sh + y0 + l2] = res[(size_t)l2 * Sw + x];
 }
 
 // ------------------------------------------------------------------------------------------ K2
@@ -202,57 +225,60 @@ __global__ void __launch_bounds__(256, 2) cols_xpower_kernel(int Sh, int Sw, int
     T2* zp = Z + (size_t)p * Sh * Sw;
     T2* rp = Rbuf + (size_t)p * Sh * Sw;
     const int half = Sw / 2;                    // columns 0..half own their mirrors
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int i = threadIdx.x; i < Sh; i += blockDim.x) tw[i] = tw_g[i];
-    // line l < G: column kx = cg*G + l ; line G + l: its mirror (unused when the column is self-mirrored)
-    for (int i = threadIdx.x; i < NL * Sh; i += blockDim.x) {
-        const int l = i / Sh, y = i - l * Sh;   // y fastest: a column of the strip is a contiguous line of Zt
-        const int kx = cg * G + (l % G);
-        T2 z = mk2<T2, T>(0, 0);
-        if (kx <= half) {
-            const int kxm = (Sw - kx) % Sw;
-            if (l < G) z = zp[(size_t)kx * Sh + y];
-            else if (kxm != kx) z = zp[(size_t)kxm * Sh + y];
-        }
-        buf0[i] = z;
+    // line l < G: column kx = cg*G + l ; line G + l: its mirror (unused when the column is self-mirrored).
+    // A column of the strip is a contiguous line of Zt: one warp streams one line at a time.
+    for (int l = warp; l < NL; l += nwarps) {
+        const int kx = cg * G + (l < G ? l : l - G);
+        const int kxm = kx == 0 ? 0 : Sw - kx;
+        const bool live = kx <= half && (l < G || kxm != kx);
+        const T2* src = zp + (size_t)(l < G ? kx : kxm) * Sh;
+        T2* dst = buf0 + (size_t)l * Sh;
+        for (int y = lane; y < Sh; y += 32) dst[y] = live ? src[y] : mk2<T2, T>(0, 0);
     }
     __syncthreads();
     constexpr int CLB = NL >= 4 ? 4 : NL;
     T2* f = fft_lines<T2, CLB>(buf0, buf1, tw, plan, NL, false, ctab);
     // unpack A = FFT(a), B = FFT(b) from Z = FFT(a + i b); R = A conj(B) / max(|A conj(B)|, clamp)
-    for (int i = threadIdx.x; i < G * Sh; i += blockDim.x) {
-        const int l = i / Sh, ky = i - l * Sh;
+    for (int l = 0; l < G; ++l) {
         const int kx = cg * G + l;
-        if (kx > half) continue;
-        const int kxm = (Sw - kx) % Sw;
-        const int kym = (Sh - ky) % Sh;
+        if (kx > half) break;
+        const int kxm = kx == 0 ? 0 : Sw - kx;
         const bool self = (kxm == kx);
-        if (self && ky > kym) continue;         // the partner (kym, kx) lives in the same line: handle each pair once
         T2* l1 = f + (size_t)l * Sh;
         T2* l2 = self ? l1 : f + (size_t)(G + l) * Sh;
-        const T2 z1 = l1[ky], z2 = l2[kym];
-        const T ax = (T)0.5 * (z1.x + z2.x), ay = (T)0.5 * (z1.y - z2.y);
-        const T bx = (T)0.5 * (z1.y + z2.y), by = (T)-0.5 * (z1.x - z2.x);
-        T px = ax * bx + ay * by, py = ay * bx - ax * by;
-        const T mag = sqrt(px * px + py * py);
-        const T den = mag > (T)kClamp ? mag : (T)kClamp;
-        px /= den;
-        py /= den;
-        if (self && ky == kym) py = 0;          // self-conjugate bin: exactly real
-        l1[ky] = mk2<T2, T>(px, py);
-        l2[kym] = mk2<T2, T>(px, -py);
-        rp[(size_t)kx * Sh + ky] = mk2<T2, T>(px, py);          // R is kept transposed as well (Rt[kx][ky])
-        rp[(size_t)kxm * Sh + kym] = mk2<T2, T>(px, -py);
+        T2* r1 = rp + (size_t)kx * Sh;            // R is kept transposed as well (Rt[kx][ky])
+        T2* r2 = rp + (size_t)kxm * Sh;
+        for (int ky = threadIdx.x; ky < Sh; ky += blockDim.x) {
+            const int kym = ky == 0 ? 0 : Sh - ky;
+            if (self && ky > kym) continue;       // the partner (kym, kx) lives in the same line: handle each pair once
+            const T2 z1 = l1[ky], z2 = l2[kym];
+            const T ax = (T)0.5 * (z1.x + z2.x), ay = (T)0.5 * (z1.y - z2.y);
+            const T bx = (T)0.5 * (z1.y + z2.y), by = (T)-0.5 * (z1.x - z2.x);
+            T px = ax * bx + ay * by, py = ay * bx - ax * by;
+            const T mag = sqrt(px * px + py * py);
+            const T den = mag > (T)kClamp ? mag : (T)kClamp;
+            px /= den;
+            py /= den;
+            if (self && ky == kym) py = 0;        // self-conjugate bin: exactly real
+            l1[ky] = mk2<T2, T>(px, py);
+            l2[kym] = mk2<T2, T>(px, -py);
+            r1[ky] = mk2<T2, T>(px, py);
+            r2[kym] = mk2<T2, T>(px, -py);
+        }
     }
     __syncthreads();
     T2* other = (f == buf0) ? buf1 : buf0;
     T2* y = fft_lines<T2, CLB>(f, other, tw, plan, NL, true, ctab);
-    for (int i = threadIdx.x; i < NL * Sh; i += blockDim.x) {
-        const int l = i / Sh, yy = i - l * Sh;
-        const int kx = cg * G + (l % G);
+    for (int l = warp; l < NL; l += nwarps) {
+        const int kx = cg * G + (l < G ? l : l - G);
         if (kx > half) continue;
-        const int kxm = (Sw - kx) % Sw;
-        if (l < G) zp[(size_t)kx * Sh + yy] = y[i];
-        else if (kxm != kx) zp[(size_t)kxm * Sh + yy] = y[i];
+        const int kxm = kx == 0 ? 0 : Sw - kx;
+        if (l >= G && kxm == kx) continue;
+        T2* dst = zp + (size_t)(l < G ? kx : kxm) * Sh;
+        const T2* src = y + (size_t)l * Sh;
+        for (int yy = lane; yy < Sh; yy += 32) dst[yy] = src[yy];
     }
 }
 
@@ -277,31 +303,42 @@ __global__ void __launch_bounds__(256, 2) rows_inv_argmax_kernel(int Sh, int Sw,
     const int p = blockIdx.x / nrb, rb = blockIdx.x - p * nrb;
     const int l0 = rb * lpb;                                 // first packed line of this block
     const T2* yp = Y + (size_t)p * Sh * Sw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int i = threadIdx.x; i < Sw; i += blockDim.x) tw[i] = tw_g[i];
-    for (int i = threadIdx.x; i < lpb * Sw; i += blockDim.x) {
-        const int x = i / lpb, l = i - x * lpb;              // l fastest: 2 * lpb consecutive y of one x are contiguous in Yt
-        const int y1 = 2 * (l0 + l), y2 = y1 + 1;
-        T2 v = mk2<T2, T>(0, 0);
-        if (y1 < Sh) {
-            const T2 r1 = yp[(size_t)x * Sh + y1];
-            v = r1;
-            if (y2 < Sh) {                                   // + i * row y2
-                const T2 r2 = yp[(size_t)x * Sh + y2];
-                v.x -= r2.y;
-                v.y += r2.x;
+    {   // lanes over the packed lines (2 * lpb consecutive y of one x are contiguous in Yt), the rest of the block over x
+        int lpl = 0;
+        while ((1 << lpl) < lpb && lpl < 5) ++lpl;
+        const int lq = threadIdx.x & ((1 << lpl) - 1);
+        const int xs = threadIdx.x >> lpl, nxs = blockDim.x >> lpl;
+        for (int l = lq; l < lpb; l += (1 << lpl)) {
+            const int y1 = 2 * (l0 + l), y2 = y1 + 1;
+            for (int x = xs; x < Sw; x += nxs) {
+                T2 v = mk2<T2, T>(0, 0);
+                if (y1 < Sh) {
+                    v = yp[(size_t)x * Sh + y1];
+                    if (y2 < Sh) {                           // + i * row y2
+                        const T2 r2 = yp[(size_t)x * Sh + y2];
+                        v.x -= r2.y;
+                        v.y += r2.x;
+                    }
+                }
+                buf0[(size_t)l * Sw + x] = v;
             }
         }
-        buf0[(size_t)l * Sw + x] = v;
     }
     __syncthreads();
     const T2* res = fft_lines<T2, LB>(buf0, buf1, tw, plan, lpb, true, ctab);
     T bv = (T)-1;
     int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < lpb * Sw; i += blockDim.x) {
-        const int l = i / Sw, x = i - l * Sw;
+    for (int l = warp; l < lpb; l += nwarps) {
         const int y1 = 2 * (l0 + l), y2 = y1 + 1;
-        if (y1 < Sh) best_update<T>(bv, bi, fabs(res[i].x), y1 * Sw + x);
-        if (y2 < Sh) best_update<T>(bv, bi, fabs(res[i].y), y2 * Sw + x);
+        if (y1 >= Sh) break;
+        const T2* row = res + (size_t)l * Sw;
+        for (int x = lane; x < Sw; x += 32) {
+            const T2 v = row[x];
+            best_update<T>(bv, bi, fabs(v.x), y1 * Sw + x);
+            if (y2 < Sh) best_update<T>(bv, bi, fabs(v.y), y2 * Sw + x);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -520,6 +557,16 @@ FftPlan make_plan(int n) {
     pl.nfac = 0;
     pl.gemm_radix = 0;
     for (int v : f) pl.fac[pl.nfac++] = v;
+    int Ns = 1;
+    for (int i = 0; i < 16; ++i) {
+        const int R = i < pl.nfac ? pl.fac[i] : 1;
+        pl.Ns[i] = Ns;
+        pl.M[i] = n / R;
+        pl.tstep[i] = n / (Ns * R);
+        pl.mM[i] = fastdiv_magic((unsigned)pl.M[i]);
+        pl.mNs[i] = fastdiv_magic((unsigned)Ns);
+        if (i < pl.nfac) Ns *= R;
+    }
     return pl;
 }
 
