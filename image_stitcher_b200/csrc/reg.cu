@@ -140,7 +140,7 @@ __device__ __forceinline__ float* stage_ctab(T2* after_tw, const float* __restri
 // ------------------------------------------------------------------------------------------ K1
 template <typename T, int LB>
 __global__ void __launch_bounds__(256, 2) rows_fwd_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm,
-                                                       int tile_w, int Sh, int Sw, int lpb, int nrb,
+                                                       int tile_w, int Sh, int Sw, int lpb, int nrb, int swap,
                                                        const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
                                                        const float* __restrict__ ctab_g, int ctab_n,
                                                        typename Vec2<T>::type* __restrict__ Z, int* __restrict__ nonzero) {
@@ -159,31 +159,69 @@ __global__ void __launch_bounds__(256, 2) rows_fwd_kernel(const PairDesc* __rest
     const float invb = mb.y > mb.x ? 65535.0f / (float)(mb.y - mb.x) : 0.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int i = threadIdx.x; i < Sw; i += blockDim.x) tw[i] = tw_g[i];
-    // strip crop + stretch fused into the load: a warp walks one strip row at a time (coalesced 64-byte reads of both
-    // strips), four independent pixel pairs in flight per lane; no integer divisions in the index arithmetic
-    for (int l = warp; l < lpb; l += nwarps) {
-        T2* row = buf0 + (size_t)l * Sw;
-        if (y0 + l >= Sh) {
-            for (int x = lane; x < Sw; x += 32) row[x] = mk2<T2, T>(0, 0);
-            continue;
-        }
-        const uint16_t* pa = pd.a + (size_t)(y0 + l) * tile_w;
-        const uint16_t* pb = pd.b + (size_t)(y0 + l) * tile_w;
-        for (int x0 = lane; x0 < Sw; x0 += 128) {
-            unsigned av[4], bv[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int x = x0 + 32 * u;
-                av[u] = x < Sw ? pa[x] : 0u;
-                bv[u] = x < Sw ? pb[x] : 0u;
+    if (!swap) {
+        // strip crop + stretch fused into the load: a warp walks one strip row at a time (coalesced 64-byte reads of both
+        // strips), four independent pixel pairs in flight per lane; no integer divisions in the index arithmetic
+        for (int l = warp; l < lpb; l += nwarps) {
+            T2* row = buf0 + (size_t)l * Sw;
+            if (y0 + l >= Sh) {
+                for (int x = lane; x < Sw; x += 32) row[x] = mk2<T2, T>(0, 0);
+                continue;
             }
+            const uint16_t* pa = pd.a + (size_t)(y0 + l) * tile_w;
+            const uint16_t* pb = pd.b + (size_t)(y0 + l) * tile_w;
+            for (int x0 = lane; x0 < Sw; x0 += 128) {
+                unsigned av[4], bv[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int x = x0 + 32 * u;
-                if (x < Sw) {
-                    const int na = stretch_px(av[u], ma.x, ma.y, inva), nb = stretch_px(bv[u], mb.x, mb.y, invb);
-                    seen |= (na != 0 ? 1 : 0) | (nb != 0 ? 2 : 0);
-                    row[x] = mk2<T2, T>((T)(na * kInScale), (T)(nb * kInScale));
+                for (int u = 0; u < 4; ++u) {
+                    const int x = x0 + 32 * u;
+                    av[u] = x < Sw ? pa[x] : 0u;
+                    bv[u] = x < Sw ? pb[x] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int x = x0 + 32 * u;
+                    if (x < Sw) {
+                        const int na = stretch_px(av[u], ma.x, ma.y, inva), nb = stretch_px(bv[u], mb.x, mb.y, invb);
+                        seen |= (na != 0 ? 1 : 0) | (nb != 0 ? 2 : 0);
+                        row[x] = mk2<T2, T>((T)(na * kInScale), (T)(nb * kInScale));
+                    }
+                }
+            }
+        }
+    } else {
+        // Transposed frame (wide strips are processed as their transpose so that the long axis is the column pass):
+        // frame row l is image column y0 + l, frame column x is image row x.  Lanes run over the frame rows -- adjacent
+        // image columns, contiguous in memory -- and the rest of the block over the image rows.
+        int lpl = 0;
+        while ((1 << lpl) < lpb && lpl < 5) ++lpl;
+        const int l = threadIdx.x & ((1 << lpl) - 1);
+        const int xs = threadIdx.x >> lpl, nxs = blockDim.x >> lpl;
+        for (int l2 = l; l2 < lpb; l2 += (1 << lpl)) {
+            const bool live = y0 + l2 < Sh;
+            const uint16_t* pa = pd.a + (y0 + l2);
+            const uint16_t* pb = pd.b + (y0 + l2);
+            T2* row = buf0 + (size_t)l2 * Sw;
+            for (int x0 = xs; x0 < Sw; x0 += 4 * nxs) {
+                unsigned av[4], bv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int x = x0 + u * nxs;
+                    av[u] = (live && x < Sw) ? pa[(size_t)x * tile_w] : 0u;
+                    bv[u] = (live && x < Sw) ? pb[(size_t)x * tile_w] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int x = x0 + u * nxs;
+                    if (x < Sw) {
+                        int na = 0, nb = 0;
+                        if (live) {
+                            na = stretch_px(av[u], ma.x, ma.y, inva);
+                            nb = stretch_px(bv[u], mb.x, mb.y, invb);
+                            seen |= (na != 0 ? 1 : 0) | (nb != 0 ? 2 : 0);
+                        }
+                        row[x] = mk2<T2, T>((T)(na * kInScale), (T)(nb * kInScale));
+                    }
                 }
             }
         }
@@ -289,7 +327,7 @@ __device__ __forceinline__ void best_update(V& bv, int& bi, V v, int i) {
 }
 
 template <typename T, int LB>
-__global__ void __launch_bounds__(256, 2) rows_inv_argmax_kernel(int Sh, int Sw, int lpb, int nrb,
+__global__ void __launch_bounds__(256, 2) rows_inv_argmax_kernel(int Sh, int Sw, int lpb, int nrb, int swap,
                                                               const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
                                                               const float* __restrict__ ctab_g, int ctab_n,
                                                               const typename Vec2<T>::type* __restrict__ Y,
@@ -336,8 +374,9 @@ __global__ void __launch_bounds__(256, 2) rows_inv_argmax_kernel(int Sh, int Sw,
         const T2* row = res + (size_t)l * Sw;
         for (int x = lane; x < Sw; x += 32) {
             const T2 v = row[x];
-            best_update<T>(bv, bi, fabs(v.x), y1 * Sw + x);
-            if (y2 < Sh) best_update<T>(bv, bi, fabs(v.y), y2 * Sw + x);
+            // first maximum in the C order of the ORIGINAL strip: in a transposed frame (y, x) is (col, row) there
+            best_update<T>(bv, bi, fabs(v.x), swap ? x * Sh + y1 : y1 * Sw + x);
+            if (y2 < Sh) best_update<T>(bv, bi, fabs(v.y), swap ? x * Sh + y2 : y2 * Sw + x);
         }
     }
 #pragma unroll
@@ -359,7 +398,7 @@ __global__ void __launch_bounds__(256, 2) rows_inv_argmax_kernel(int Sh, int Sw,
 }
 
 // one warp per pair: global first-maximum and the best value found by any OTHER block
-__global__ void __launch_bounds__(32) peak_final_kernel(const CtaBest* __restrict__ best, int nrb, int Sw,
+__global__ void __launch_bounds__(32) peak_final_kernel(const CtaBest* __restrict__ best, int nrb, int Sh, int Sw, int swap,
                                                         const int* __restrict__ nonzero, PeakOut* out) {
     const int p = blockIdx.x;
     if (nonzero[p] != 3) {                       // a strip is identically zero: cc == 0 everywhere, first index wins
@@ -389,8 +428,9 @@ __global__ void __launch_bounds__(32) peak_final_kernel(const CtaBest* __restric
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ru = fmax(ru, __shfl_xor_sync(0xffffffffu, ru, o));
     if (threadIdx.x == 0) {
-        out[p].coarse_y = bi / Sw;
-        out[p].coarse_x = bi - (bi / Sw) * Sw;
+        // frame coordinates of the peak (the index was formed in the original strip's C order)
+        out[p].coarse_y = swap ? bi % Sh : bi / Sw;
+        out[p].coarse_x = swap ? bi / Sh : bi % Sw;
         out[p].peak = (float)bv;
         out[p].runner_up = (float)ru;
         out[p].fine_y = out[p].fine_x = -1;
@@ -516,7 +556,7 @@ __global__ void __launch_bounds__(256) updft_cols_kernel(int Sh, int rs, const t
 }
 
 // first maximum (C order) of the rs x rs window; one warp per pair
-__global__ void __launch_bounds__(32) updft_final_kernel(int rs, const double* __restrict__ mag2, float inv_n,
+__global__ void __launch_bounds__(32) updft_final_kernel(int rs, int swap, const double* __restrict__ mag2, float inv_n,
                                                          const int* __restrict__ nonzero, PeakOut* __restrict__ peaks) {
     const int p = blockIdx.x;
     if (nonzero[p] != 3) {                       // zero cross-power: the upsampled window is all zero -> index 0
@@ -525,7 +565,10 @@ __global__ void __launch_bounds__(32) updft_final_kernel(int rs, const double* _
     }
     double bv = -1.0;
     int bi = 0x7fffffff;
-    for (int o = threadIdx.x; o < rs * rs; o += 32) best_update<double>(bv, bi, mag2[(size_t)p * rs * rs + o], o);
+    for (int o = threadIdx.x; o < rs * rs; o += 32) {
+        const int v = o / rs, u = o - v * rs;            // mag2 is [v][u] in the frame; original order is [u][v] when swapped
+        best_update<double>(bv, bi, mag2[(size_t)p * rs * rs + o], swap ? u * rs + v : o);
+    }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, bv, s);
@@ -533,8 +576,8 @@ __global__ void __launch_bounds__(32) updft_final_kernel(int rs, const double* _
         best_update<double>(bv, bi, ov, oi);
     }
     if (threadIdx.x == 0) {
-        peaks[p].fine_y = bi / rs;
-        peaks[p].fine_x = bi - (bi / rs) * rs;
+        peaks[p].fine_y = swap ? bi % rs : bi / rs;      // frame coordinates again
+        peaks[p].fine_x = swap ? bi / rs : bi % rs;
         peaks[p].fine_peak = (float)(sqrt(bv) * (double)inv_n);
     }
 }
@@ -628,6 +671,11 @@ struct GroupGeom {          // strips of one direction
     int a_y0, a_x0, b_y0, b_x0;
 };
 
+bool group_swapped(const GroupGeom& g) {
+    static const bool off = getenv("SB_REG_NO_SWAP") != nullptr;
+    return g.Sw > g.Sh && !off;
+}
+
 // lines per block so that 2 buffers + the twiddle table fit comfortably in shared memory
 int pick_lines(int n, size_t elem, int lb, size_t budget) {
     if ((size_t)n * elem * 3 > budget) return 0;
@@ -645,7 +693,10 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     cudaStream_t st = lane->stream;
     using T2 = typename Vec2<T>::type;
     const int n = (int)pairs.size();
-    const int Sh = g.Sh, Sw = g.Sw;
+    // Wide strips (vertical pairs: 214 x 1024) run in a transposed frame so that the long axis is always the column pass
+    // and every group has the H-like shape the kernels are tuned for; indices are mapped back in finish_pair.
+    const int swap = group_swapped(g) ? 1 : 0;
+    const int Sh = swap ? g.Sw : g.Sh, Sw = swap ? g.Sh : g.Sw;
     const size_t strip = (size_t)Sh * Sw;
     const FftPlan plan_x = make_plan(Sw), plan_y = make_plan(Sh);
     const T2 *tw_x = nullptr, *tw_y = nullptr;
@@ -753,10 +804,10 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     const float inv_n = 1.0f / ((float)Sh * (float)Sw);
     for (int p0 = 0; p0 < n; p0 += B) {
         const int nb = std::min(B, n - p0);
-        k1<<<nb * nrb_fwd, 256, smem_x, st>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, tw_x, px_plan, cx, cxn, Z, d_nz + p0);
+        k1<<<nb * nrb_fwd, 256, smem_x, st>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, swap, tw_x, px_plan, cx, cxn, Z, d_nz + p0);
         k2<<<nb * ncg, 256, smem_y, st>>>(Sh, Sw, ncg, tw_y, py_plan, cy, cyn, Z, Rb);
-        k3<<<nb * nrb_inv, 256, smem_x, st>>>(Sh, Sw, lpbx, nrb_inv, tw_x, px_plan, cx, cxn, Z, best);
-        peak_final_kernel<<<nb, 32, 0, st>>>(best, nrb_inv, Sw, d_nz + p0, peaks + p0);
+        k3<<<nb * nrb_inv, 256, smem_x, st>>>(Sh, Sw, lpbx, nrb_inv, swap, tw_x, px_plan, cx, cxn, Z, best);
+        peak_final_kernel<<<nb, 32, 0, st>>>(best, nrb_inv, Sh, Sw, swap, d_nz + p0, peaks + p0);
         ctx->launches += 4;
         if (uf > 1) {
             updft_twiddle_kernel<T><<<dim3(8, nb), 256, 0, st>>>(peaks + p0, Sh, Sw, uf, rs, dftshift, Ex, Ey);
@@ -765,7 +816,7 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
                 ctx->launches++;
             }
             updft_cols_kernel<T><<<nb * rs, 256, 0, st>>>(Sh, rs, Tm, Ey, mag2);
-            updft_final_kernel<<<nb, 32, 0, st>>>(rs, mag2, inv_n, d_nz + p0, peaks + p0);
+            updft_final_kernel<<<nb, 32, 0, st>>>(rs, swap, mag2, inv_n, d_nz + p0, peaks + p0);
             ctx->launches += 3;
         }
         SB_CUDA(ctx, cudaGetLastError());
@@ -776,7 +827,12 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
 }
 
 // skimage's float64 shift from integer indices, then the reference's round() (half-to-even)
-void finish_pair(const PeakOut& pk, const GroupGeom& g, int dir, int uf, sb_pair_result* r) {
+void finish_pair(const PeakOut& pk_frame, const GroupGeom& g, int dir, int uf, sb_pair_result* r) {
+    PeakOut pk = pk_frame;
+    if (group_swapped(g)) {                      // the kernels worked on the transposed strip: map the indices back
+        std::swap(pk.coarse_y, pk.coarse_x);
+        std::swap(pk.fine_y, pk.fine_x);
+    }
     const int shape[2] = {g.Sh, g.Sw};
     const int coarse[2] = {pk.coarse_y, pk.coarse_x};
     const int fine[2] = {pk.fine_y, pk.fine_x};
