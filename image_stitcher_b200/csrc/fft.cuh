@@ -339,53 +339,58 @@ __device__ __forceinline__ void pass_odd_gemm(float2* __restrict__ a, float2* __
     // ---- step 2: the GEMM.  item = (q tile of 4, column group = (j, 4 lines)); lanes run over column groups.
     const int lgs = nlines >> 2;
     const int ncg = M * lgs;
-    const int nqt = QP >> 2;
+    const int nqt = h >> 2;                                // FULL tiles of 4 outputs q; the h & 3 leftover outputs go below
     const float* cosb = ctab;
     const float* sinb = ctab + h * QP;
     const int es = (M * nlines) >> 1;                      // ulonglong2 stride of one r step in T
-    for (int it = threadIdx.x; it < nqt * ncg; it += blockDim.x) {
-        const int qt = it / ncg, cg = it - qt * ncg;
-        const int j = cg / lgs, lg = cg - j * lgs;
-        const ulonglong2* ep = reinterpret_cast<const ulonglong2*>(b + (size_t)(M + j) * nlines + lg * 4);
-        const ulonglong2* op = reinterpret_cast<const ulonglong2*>(b + (size_t)((R - 1) * M + j) * nlines + lg * 4);
-        const float4* cp = reinterpret_cast<const float4*>(cosb + qt * 4);
-        const float4* sp = reinterpret_cast<const float4*>(sinb + qt * 4);
-        unsigned long long ce[4][4], so[4][4];
+    const int n_gemm = nqt * ncg;
+    // work list of the block: [GEMM items | leftover-q columns | X[0] columns]; the two cheap tails keep the threads
+    // busy that the GEMM items do not cover (214 = 2 * 107, 24 lines: 156 + 48 + 48 of 256 threads)
+    const int ncol = M * nlines;
+    const int nleft = (h & 3) ? ncol : 0;
+    for (int it = threadIdx.x; it < n_gemm + nleft + ncol; it += blockDim.x) {
+        if (it < n_gemm) {
+            const int qt = it / ncg, cg = it - qt * ncg;
+            const int j = cg / lgs, lg = cg - j * lgs;
+            const ulonglong2* ep = reinterpret_cast<const ulonglong2*>(b + (size_t)(M + j) * nlines + lg * 4);
+            const ulonglong2* op = reinterpret_cast<const ulonglong2*>(b + (size_t)((R - 1) * M + j) * nlines + lg * 4);
+            const float4* cp = reinterpret_cast<const float4*>(cosb + qt * 4);
+            const float4* sp = reinterpret_cast<const float4*>(sinb + qt * 4);
+            unsigned long long ce[4][4], so[4][4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
+            for (int t = 0; t < 4; ++t)
 #pragma unroll
-            for (int l = 0; l < 4; ++l) ce[t][l] = so[t][l] = 0ull;
+                for (int l = 0; l < 4; ++l) ce[t][l] = so[t][l] = 0ull;
 #pragma unroll 2
-        for (int r = 1; r <= h; ++r) {
-            const float4 c = *cp, s = *sp;
-            const ulonglong2 e01 = ep[0], e23 = ep[1], o01 = op[0], o23 = op[1];
-            cp += QP >> 2;
-            sp += QP >> 2;
-            ep += es;
-            op -= es;
-            const unsigned long long e[4] = {e01.x, e01.y, e23.x, e23.y}, o[4] = {o01.x, o01.y, o23.x, o23.y};
-            const float cv[4] = {c.x, c.y, c.z, c.w}, sv[4] = {s.x, s.y, s.z, s.w};
+            for (int r = 1; r <= h; ++r) {
+                const float4 c = *cp, s = *sp;
+                const ulonglong2 e01 = ep[0], e23 = ep[1], o01 = op[0], o23 = op[1];
+                cp += QP >> 2;
+                sp += QP >> 2;
+                ep += es;
+                op -= es;
+                const unsigned long long e[4] = {e01.x, e01.y, e23.x, e23.y}, o[4] = {o01.x, o01.y, o23.x, o23.y};
+                const float cv[4] = {c.x, c.y, c.z, c.w}, sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const unsigned long long cc = fx2_dup(cv[t]), ss = fx2_dup(sv[t]);
+                for (int t = 0; t < 4; ++t) {
+                    const unsigned long long cc = fx2_dup(cv[t]), ss = fx2_dup(sv[t]);
 #pragma unroll
-                for (int l = 0; l < 4; ++l) {
-                    ce[t][l] = fx2_fma(e[l], cc, ce[t][l]);
-                    so[t][l] = fx2_fma(o[l], ss, so[t][l]);
+                    for (int l = 0; l < 4; ++l) {
+                        ce[t][l] = fx2_fma(e[l], cc, ce[t][l]);
+                        so[t][l] = fx2_fma(o[l], ss, so[t][l]);
+                    }
                 }
             }
-        }
-        const int k = j % Ns;
-        const int dst0 = (j / Ns) * Ns * R + k;
-        const float2* y0p = b + (size_t)j * nlines + lg * 4;
+            const int k = j % Ns;
+            const int dst0 = (j / Ns) * Ns * R + k;
+            const float2* y0p = b + (size_t)j * nlines + lg * 4;
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            const float2 y0 = y0p[l];
-            float2* out = a + (size_t)(lg * 4 + l) * N + dst0;
+            for (int l = 0; l < 4; ++l) {
+                const float2 y0 = y0p[l];
+                float2* out = a + (size_t)(lg * 4 + l) * N + dst0;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int q = qt * 4 + t + 1;
-                if (q <= h) {
+                for (int t = 0; t < 4; ++t) {
+                    const int q = qt * 4 + t + 1;
                     const float2 cev = fx2_unpack(ce[t][l]), sov = fx2_unpack(so[t][l]);
                     const float bx = y0.x + cev.x, by = y0.y + cev.y;
                     // forward: X[q] = base - i So, X[R-q] = base + i So ; inverse: swapped
@@ -394,11 +399,45 @@ __device__ __forceinline__ void pass_odd_gemm(float2* __restrict__ a, float2* __
                     out[(size_t)(R - q) * Ns] = inverse ? lo : hi;
                 }
             }
-        }
-    }
-    // ---- X[0] = y_0 + sum_r e_r
-    for (int line = line0; line < nlines; line += LP)
-        for (int j = slot; j < M; j += nslots) {
+        } else if (it < n_gemm + nleft) {
+            // leftover outputs q = 4 * nqt + 1 .. h of one column (j, line)
+            const int col = it - n_gemm;
+            const int j = col / nlines, line = col - j * nlines;
+            const int nq = h & 3;
+            float2 ce[3], so[3];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) ce[t] = so[t] = make_float2(0.f, 0.f);
+            const float* cp = cosb + 4 * nqt;
+            const float* sp = sinb + 4 * nqt;
+            for (int r = 1; r <= h; ++r) {
+                const float2 e = b[(size_t)(r * M + j) * nlines + line], o = b[(size_t)((R - r) * M + j) * nlines + line];
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+                    if (t < nq) {
+                        const float c = cp[t], s = sp[t];
+                        ce[t].x = fmaf(e.x, c, ce[t].x);
+                        ce[t].y = fmaf(e.y, c, ce[t].y);
+                        so[t].x = fmaf(o.x, s, so[t].x);
+                        so[t].y = fmaf(o.y, s, so[t].y);
+                    }
+                cp += QP;
+                sp += QP;
+            }
+            const float2 y0 = b[(size_t)j * nlines + line];
+            float2* out = a + (size_t)line * N + (j / Ns) * Ns * R + (j % Ns);
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+                if (t < nq) {
+                    const int q = 4 * nqt + t + 1;
+                    const float bx = y0.x + ce[t].x, by = y0.y + ce[t].y;
+                    const float2 lo = make_float2(bx + so[t].y, by - so[t].x), hi = make_float2(bx - so[t].y, by + so[t].x);
+                    out[(size_t)q * Ns] = inverse ? hi : lo;
+                    out[(size_t)(R - q) * Ns] = inverse ? lo : hi;
+                }
+        } else {
+            // X[0] = y_0 + sum_r e_r of one column
+            const int col = it - n_gemm - nleft;
+            const int j = col / nlines, line = col - j * nlines;
             float2 acc = b[(size_t)j * nlines + line];
             for (int r = 1; r <= h; ++r) {
                 const float2 e = b[(size_t)(r * M + j) * nlines + line];
@@ -407,6 +446,7 @@ __device__ __forceinline__ void pass_odd_gemm(float2* __restrict__ a, float2* __
             }
             a[(size_t)line * N + (j / Ns) * Ns * R + (j % Ns)] = acc;
         }
+    }
 }
 
 template <typename T2>

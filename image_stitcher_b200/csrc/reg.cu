@@ -350,17 +350,21 @@ __global__ void __launch_bounds__(256, 2) rows_inv_argmax_kernel(int Sh, int Sw,
         const int xs = threadIdx.x >> lpl, nxs = blockDim.x >> lpl;
         for (int l = lq; l < lpb; l += (1 << lpl)) {
             const int y1 = 2 * (l0 + l), y2 = y1 + 1;
-            for (int x = xs; x < Sw; x += nxs) {
-                T2 v = mk2<T2, T>(0, 0);
-                if (y1 < Sh) {
-                    v = yp[(size_t)x * Sh + y1];
-                    if (y2 < Sh) {                           // + i * row y2
-                        const T2 r2 = yp[(size_t)x * Sh + y2];
-                        v.x -= r2.y;
-                        v.y += r2.x;
-                    }
+            const bool h1 = y1 < Sh, h2 = y2 < Sh;
+            // four x positions (eight independent loads) in flight per thread: this phase is pure L2 latency
+            for (int x0 = xs; x0 < Sw; x0 += 4 * nxs) {
+                T2 r1[4], r2[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int x = x0 + u * nxs;
+                    r1[u] = (h1 && x < Sw) ? yp[(size_t)x * Sh + y1] : mk2<T2, T>(0, 0);
+                    r2[u] = (h2 && x < Sw) ? yp[(size_t)x * Sh + y2] : mk2<T2, T>(0, 0);
                 }
-                buf0[(size_t)l * Sw + x] = v;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int x = x0 + u * nxs;
+                    if (x < Sw) buf0[(size_t)l * Sw + x] = mk2<T2, T>(r1[u].x - r2[u].y, r1[u].y + r2[u].x);   // row y1 + i * row y2
+                }
             }
         }
     }

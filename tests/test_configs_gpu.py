@@ -139,3 +139,52 @@ def test_config4_zstack_planes_and_chunked_output(ctx):
     dense = out.transpose(0, 1, 3, 2, 4).reshape(5, ncy * ch, ncx * ch)
     assert np.array_equal(dense[:, :height, :width], exp[0, 0])
     assert not dense[:, height:, :].any() and not dense[:, :, width:].any()      # edge chunks zero padded
+
+
+def test_config2_full_size_well_bit_exact_and_properties(ctx):
+    """One well of BASELINE.json configs[2] at FULL size (3x3 tiles of 2048^2, 4 channels, flat-field on, coordinate
+    placement -> (1, 4, 1, 5734, 5734)): bit-exact against the oracle, plus size-independent properties --
+    idempotence (fusing twice gives the same canvas), and with unit flat-fields the canvas is a pure copy: every
+    pixel equals the winning source pixel, so per-tile interiors hash to the same value as the inputs."""
+    import hashlib
+    from image_stitcher_b200 import _ffi
+    from image_stitcher_b200 import geometry as geo
+    chans = ("Fluorescence 405 nm Ex", "Fluorescence 488 nm Ex", "Fluorescence 561 nm Ex", "Fluorescence 638 nm Ex")
+    st, tiles, truth = synth.make_region(rows=3, cols=3, tile_h=2048, tile_w=2048, seed=81, jitter=0, channels=chans,
+                                         apply_flatfield=True)
+    exp = sr.stitch_region(st, tiles)
+    assert exp.shape == (1, 4, 1, 5734, 5734)
+    xs = sorted(set(t.x_mm for t in tiles))
+    ys = sorted(set(t.y_mm for t in tiles))
+    job, origin = [], {}
+    for t in tiles:
+        p = geo.place_tile(t.x_mm, t.y_mm, 2048, 2048, xs, ys, st.pixel_size_um, None)
+        c = st.monochrome_channels.index(t.channel)
+        job.append((t.pixels, p.x, p.y, c, 0, 0, 0, 0, 0))
+        origin[(t.fov, c)] = (p.x, p.y, t.pixels)
+    ctx.clear_fields()
+    for c, ff in st.flatfields.items():
+        ctx.set_flatfield(c, ff)
+    out = np.empty((1, 4, 1, 5734, 5734), np.uint16)
+    ctx.fuse_region(job, (2048, 2048), (4, 1, 5734, 5734), out=out, apply_flatfield=True)
+    assert np.array_equal(out, exp)
+    again = np.empty_like(out)
+    ctx.fuse_region(job, (2048, 2048), (4, 1, 5734, 5734), out=again, apply_flatfield=True)
+    assert hashlib.sha256(again.tobytes()).digest() == hashlib.sha256(out.tobytes()).digest()
+    # unit flat-field == no flat-field == copy of the winning pixels
+    ctx.clear_fields()
+    for c in range(4):
+        ctx.set_flatfield(c, np.ones((2048, 2048), np.float32))
+    unit = np.empty_like(out)
+    ctx.fuse_region(job, (2048, 2048), (4, 1, 5734, 5734), out=unit, apply_flatfield=True)
+    ctx.clear_fields()
+    plain = np.empty_like(out)
+    ctx.fuse_region(job, (2048, 2048), (4, 1, 5734, 5734), out=plain, apply_flatfield=False)
+    assert np.array_equal(unit, plain)
+    # the last tile in paste order (fov 8) is never overwritten: its whole footprint is a verbatim copy
+    for c in range(4):
+        x, y, px = origin[(8, c)]
+        assert np.array_equal(plain[0, c, 0, y:y + 2048, x:x + 2048], px)
+    # a tile's interior that no later tile touches (205-px overlaps) is a verbatim copy as well
+    x, y, px = origin[(0, 2)]
+    assert np.array_equal(plain[0, 2, 0, y:y + 1843, x:x + 1843], px[:1843, :1843])
