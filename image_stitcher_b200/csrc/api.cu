@@ -125,6 +125,11 @@ void sb_destroy(sb_ctx* ctx) {
         if (l.reg_host) cudaFreeHost(l.reg_host);
         if (l.meta_free) cudaEventDestroy(l.meta_free);
         if (l.mark) cudaEventDestroy(l.mark);
+        if (l.aux_fork) cudaEventDestroy(l.aux_fork);
+        for (int k = 0; k < 3; ++k) {
+            if (l.aux_join[k]) cudaEventDestroy(l.aux_join[k]);
+            if (l.aux[k]) cudaStreamDestroy(l.aux[k]);
+        }
         if (l.own) cudaStreamDestroy(l.own);
     }
     for (auto& kv : ctx->twiddle_cache)

@@ -712,10 +712,15 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     const int rs = (3 * uf + 1) / 2;            // ceil(1.5 * uf)
     const int dftshift = rs / 2;                // fix(rs / 2)
 
-    // sub-batches sized so that Z + R of a sub-batch stay L2 resident
+    // Sub-batches sized so that Z + R of the sub-batches in flight stay L2 resident.  Two sub-batches run
+    // concurrently (the lane's stream and its auxiliary stream, each with its own workspace half): the chain is a
+    // sequence of short dependent kernels, and the neighbour's blocks fill the tails and launch gaps.
+    static const int kWays = getenv("SB_REG_WAYS") ? std::max(1, std::min(4, atoi(getenv("SB_REG_WAYS")))) : 2;
     const size_t per_pair = 2 * strip * sizeof(T2);
     int B = (int)std::max<size_t>(1, (size_t)(64u << 20) / per_pair);
-    B = std::min(B, n);
+    int ways = 1;
+    while (ways < kWays && B / (ways + 1) >= 2 && n > B / (ways + 1)) ++ways;
+    B = std::min(std::max(1, B / ways), n);
 
     // cos/sin tables of the big odd radices (float32 lines only)
     FftPlan px_plan = plan_x, py_plan = plan_y;
@@ -774,6 +779,8 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     const size_t o_T = carve((size_t)B * rs * Sh * sizeof(T2));
     const size_t o_best = carve((size_t)B * nrb_inv * sizeof(CtaBest));
     const size_t o_mag = carve((size_t)B * rs * rs * sizeof(double));
+    const size_t way_bytes = off;                           // everything above exists once per concurrent sub-batch
+    off = way_bytes * ways;
     const size_t o_peaks = carve((size_t)n * sizeof(PeakOut));
     const size_t o_pairs = carve((size_t)n * sizeof(PairDesc));
     const size_t o_nz = carve((size_t)n * sizeof(int));
@@ -806,24 +813,48 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     SB_CUDA(ctx, cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_y));
 
     const float inv_n = 1.0f / ((float)Sh * (float)Sw);
-    for (int p0 = 0; p0 < n; p0 += B) {
+    cudaStream_t way_stream[4] = {st, st, st, st};
+    if (ways > 1) {
+        if (!lane->aux_fork) SB_CUDA(ctx, cudaEventCreateWithFlags(&lane->aux_fork, cudaEventDisableTiming));
+        SB_CUDA(ctx, cudaEventRecord(lane->aux_fork, st));            // pair descriptors, min/max, earlier lane work
+        for (int k = 1; k < ways; ++k) {
+            if (!lane->aux[k - 1]) {
+                SB_CUDA(ctx, cudaStreamCreateWithFlags(&lane->aux[k - 1], cudaStreamNonBlocking));
+                SB_CUDA(ctx, cudaEventCreateWithFlags(&lane->aux_join[k - 1], cudaEventDisableTiming));
+            }
+            way_stream[k] = lane->aux[k - 1];
+            SB_CUDA(ctx, cudaStreamWaitEvent(lane->aux[k - 1], lane->aux_fork, 0));
+        }
+    }
+    int way = 0;
+    for (int p0 = 0; p0 < n; p0 += B, way = (way + 1) % ways) {
         const int nb = std::min(B, n - p0);
-        k1<<<nb * nrb_fwd, 256, smem_x, st>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, swap, tw_x, px_plan, cx, cxn, Z, d_nz + p0);
-        k2<<<nb * ncg, 256, smem_y, st>>>(Sh, Sw, ncg, tw_y, py_plan, cy, cyn, Z, Rb);
-        k3<<<nb * nrb_inv, 256, smem_x, st>>>(Sh, Sw, lpbx, nrb_inv, swap, tw_x, px_plan, cx, cxn, Z, best);
-        peak_final_kernel<<<nb, 32, 0, st>>>(best, nrb_inv, Sh, Sw, swap, d_nz + p0, peaks + p0);
+        cudaStream_t ws = way_stream[way];
+        const size_t wo = way_bytes * way;
+        T2 *Zw = (T2*)((uint8_t*)Z + wo), *Rw = (T2*)((uint8_t*)Rb + wo), *Exw = (T2*)((uint8_t*)Ex + wo);
+        T2 *Eyw = (T2*)((uint8_t*)Ey + wo), *Tw = (T2*)((uint8_t*)Tm + wo);
+        CtaBest* bestw = (CtaBest*)((uint8_t*)best + wo);
+        double* magw = (double*)((uint8_t*)mag2 + wo);
+        k1<<<nb * nrb_fwd, 256, smem_x, ws>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, swap, tw_x, px_plan, cx, cxn, Zw, d_nz + p0);
+        k2<<<nb * ncg, 256, smem_y, ws>>>(Sh, Sw, ncg, tw_y, py_plan, cy, cyn, Zw, Rw);
+        k3<<<nb * nrb_inv, 256, smem_x, ws>>>(Sh, Sw, lpbx, nrb_inv, swap, tw_x, px_plan, cx, cxn, Zw, bestw);
+        peak_final_kernel<<<nb, 32, 0, ws>>>(bestw, nrb_inv, Sh, Sw, swap, d_nz + p0, peaks + p0);
         ctx->launches += 4;
         if (uf > 1) {
-            updft_twiddle_kernel<T><<<dim3(8, nb), 256, 0, st>>>(peaks + p0, Sh, Sw, uf, rs, dftshift, Ex, Ey);
+            updft_twiddle_kernel<T><<<dim3(8, nb), 256, 0, ws>>>(peaks + p0, Sh, Sw, uf, rs, dftshift, Exw, Eyw);
             for (int u0 = 0; u0 < rs; u0 += 16) {            // rs = 15 for the reference's upsample_factor 10: one launch
-                updft_rows_kernel<T, 16><<<nb * nrb_up, 256, 0, st>>>(Sh, Sw, rs, u0, nrb_up, Rb, Ex, Tm);
+                updft_rows_kernel<T, 16><<<nb * nrb_up, 256, 0, ws>>>(Sh, Sw, rs, u0, nrb_up, Rw, Exw, Tw);
                 ctx->launches++;
             }
-            updft_cols_kernel<T><<<nb * rs, 256, 0, st>>>(Sh, rs, Tm, Ey, mag2);
-            updft_final_kernel<<<nb, 32, 0, st>>>(rs, swap, mag2, inv_n, d_nz + p0, peaks + p0);
+            updft_cols_kernel<T><<<nb * rs, 256, 0, ws>>>(Sh, rs, Tw, Eyw, magw);
+            updft_final_kernel<<<nb, 32, 0, ws>>>(rs, swap, magw, inv_n, d_nz + p0, peaks + p0);
             ctx->launches += 3;
         }
         SB_CUDA(ctx, cudaGetLastError());
+    }
+    for (int k = 1; k < ways; ++k) {
+        SB_CUDA(ctx, cudaEventRecord(lane->aux_join[k - 1], lane->aux[k - 1]));
+        SB_CUDA(ctx, cudaStreamWaitEvent(st, lane->aux_join[k - 1], 0));
     }
     SB_CUDA(ctx, cudaMemcpyAsync(h_out, peaks, (size_t)n * sizeof(PeakOut), cudaMemcpyDeviceToHost, st));
     if (do_sync) SB_CUDA(ctx, cudaStreamSynchronize(st));

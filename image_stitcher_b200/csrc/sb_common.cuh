@@ -45,6 +45,8 @@ struct Lane {
     void* reg_host = nullptr;       // pinned block the registration results are copied into
     size_t reg_host_cap = 0;
     void* reg_pending = nullptr;    // parked asynchronous registration job (RegPending in reg.cu)
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // extra streams of the lane: registration sub-batches rotate over them
+    cudaEvent_t aux_fork = nullptr, aux_join[3] = {nullptr, nullptr, nullptr};
     std::vector<int32_t> perm;      // cached block-row order of the paste kernel (fuse.cu) ...
     uint64_t perm_sig = 0;          // ... and the geometry signature it was computed for
 };
