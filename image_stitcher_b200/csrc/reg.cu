@@ -506,11 +506,23 @@ __global__ void __launch_bounds__(256) updft_rows_kernel(int Sh, int Sw, int rs,
         }
         __syncthreads();
         if (y < Sh) {
-            for (int x = xs; x < nx; x += NS) {
-                T2 r = rp[(size_t)(xc + x) * Sh + y];
-                r.y = -r.y;
+            // four independent loads of Rt in flight per thread: this loop is L2-latency bound otherwise
+            for (int x0 = xs; x0 < nx; x0 += 4 * NS) {
+                T2 r[4];
 #pragma unroll
-                for (int u = 0; u < UMAX; ++u) cfma(acc[u], r, exs[x * UMAX + u]);
+                for (int k = 0; k < 4; ++k) {
+                    const int x = x0 + k * NS;
+                    r[k] = x < nx ? rp[(size_t)(xc + x) * Sh + y] : mk2<T2, T>(0, 0);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int x = x0 + k * NS;
+                    if (x < nx) {
+                        const T2 rc = mk2<T2, T>(r[k].x, -r[k].y);
+#pragma unroll
+                        for (int u = 0; u < UMAX; ++u) cfma(acc[u], rc, exs[x * UMAX + u]);
+                    }
+                }
             }
         }
     }

@@ -35,6 +35,8 @@ class StitchingParameters:
     upsample_factor: int = 10             # the reference hard-codes 10 (stitcher_process.py:684)
     registration_precision: str = "auto"
     device: int = 0
+    rank: int = 0                         # multi-GPU: this worker stitches regions rank, rank + world, ...
+    world: int = 1
 
     def __post_init__(self):
         self.input_folder = os.path.abspath(self.input_folder)

@@ -70,6 +70,10 @@ class StitcherProcess(Process):
         self.upsample_factor = int(getattr(params, "upsample_factor", 10))
         self.registration_precision = getattr(params, "registration_precision", "auto")
         self.device = int(getattr(params, "device", 0))
+        self.decode_threads = max(1, min(16, os.cpu_count() or 1))
+        # multi-GPU: worker `rank` of `world` stitches regions rank, rank + world, ... on its own device.  Every worker
+        # registers the same first region itself (2-3 pairs), so all of them hold the same lattice without any exchange.
+        self.rank, self.world = int(getattr(params, "rank", 0)), max(1, int(getattr(params, "world", 1)))
         self._ctx: Optional[_ffi.Context] = None
         self._flat_dirty = True
         self.init_stitching_parameters()
@@ -402,10 +406,20 @@ class StitcherProcess(Process):
             self.emit_status(f"Stitching... (Timepoint:{timepoint} Region:{region})")
             self.check_stop()
             job, keep = [], []
-            for key, info in data.items():                 # insertion order == sorted file names == paste order
+            # decode the tiles on a thread pool (cv2 releases the GIL); results are consumed in dict order, which is
+            # the sorted-file-name paste order of the reference (:283-288, :908)
+            from concurrent.futures import ThreadPoolExecutor
+
+            def _load(item):
+                key, info = item
                 try:
-                    tile = read_image(info["filepath"])
+                    return key, info, read_image(info["filepath"]), None
                 except Exception as exc:                   # the reference reports and skips (:912-916)
+                    return key, info, None, exc
+            with ThreadPoolExecutor(max_workers=self.decode_threads) as pool:
+                loaded = list(pool.map(_load, data.items()))
+            for key, info, tile, exc in loaded:
+                if tile is None:
                     self.emit_status(f"Error Loading Image {info['filepath']}: {exc}")
                     continue
                 p = geo.place_tile(info["x"], info["y"], self.input_width, self.input_height, xs, ys,
@@ -480,10 +494,12 @@ class StitcherProcess(Process):
                 self.get_flatfields()
             if self.use_registration:
                 self.calculate_shifts(self.timepoints[0], self.regions[0])
+            from .shard import wells_for_rank
+            my_regions = [self.regions[i] for i in wells_for_rank(len(self.regions), self.world, self.rank)]
             for timepoint in self.timepoints:
                 self.check_stop()
                 os.makedirs(os.path.join(self.output_folder, f"{timepoint}_stitched"), exist_ok=True)
-                for region in self.regions:
+                for region in my_regions:
                     self.check_stop()
                     stitched = self.stitch_region(timepoint, region)
                     if not self.output_format.endswith(".zarr"):

@@ -13,6 +13,7 @@ Extensions sit behind extra flags whose defaults reproduce the reference.
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import multiprocessing as mp
 import sys
 import time
@@ -40,6 +41,8 @@ def parse_args(argv=None) -> argparse.Namespace:
     p.add_argument("--upsample-factor", type=int, default=10)
     p.add_argument("--registration-precision", choices=["auto", "float32", "float64"], default="auto")
     p.add_argument("--device", type=int, default=0, help="CUDA device index")
+    p.add_argument("--devices", default="", help="comma-separated CUDA devices: one worker process per device, regions "
+                                                 "(wells) split round-robin, no inter-process exchange needed")
     return p.parse_args(argv)
 
 
@@ -97,11 +100,21 @@ def main(argv=None) -> int:
     params = create_params(args)
     params.validate()
     from .stitcher_process import StitcherProcess
-    progress_queue, status_queue, complete_queue = mp.Queue(), mp.Queue(), mp.Queue()
-    stop_event = mp.Event()
-    proc = StitcherProcess(params, progress_queue, status_queue, complete_queue, stop_event)
-    proc.start()
-    return monitor_process(proc, progress_queue, status_queue, complete_queue, stop_event)
+    devices = [int(d) for d in args.devices.split(",") if d.strip() != ""] or [params.device]
+    _ = params.stitched_folder                      # freeze the output folder stamp once for all workers
+    procs = []
+    for rank, dev in enumerate(devices):
+        p = dataclasses.replace(params, device=dev, rank=rank, world=len(devices))
+        p._stamp = params._stamp
+        queues = (mp.Queue(), mp.Queue(), mp.Queue())
+        stop_event = mp.Event()
+        proc = StitcherProcess(p, *queues, stop_event)
+        proc.start()
+        procs.append((proc, queues, stop_event))
+    rc = 0
+    for proc, queues, stop_event in procs:
+        rc = max(rc, monitor_process(proc, *queues, stop_event))
+    return rc
 
 
 if __name__ == "__main__":

@@ -201,3 +201,16 @@ def test_ome_zarr_from_chunk_ordered_buffer(tmp_path):
     ozw.write_ome_zarr_chunked(path, buf, (C, Z, H, W), (ch, ch), pixel_size_um=1.0, channel_names=["a", "b"],
                                channel_colors=[1, 2])
     assert np.array_equal(ozw.read_ome_zarr_level(path, 0)[0], dense)
+
+
+def test_multi_device_workers_split_regions_without_exchange(tmp_path):
+    """--devices 0,1: worker r of w stitches regions r, r + w, ...; both register the same first region."""
+    from image_stitcher_b200 import stitcher_process_cli as cli
+    from image_stitcher_b200.shard import wells_for_rank
+    a = cli.parse_args(["-i", str(tmp_path), "--devices", "0,1,3"])
+    assert [int(d) for d in a.devices.split(",")] == [0, 1, 3]
+    regions = [f"{r}{c}" for r in "ABCD" for c in range(1, 7)]
+    got = [[regions[i] for i in wells_for_rank(len(regions), 3, r)] for r in range(3)]
+    assert sorted(sum(got, [])) == sorted(regions) and got[1][:2] == ["A2", "A5"]
+    p = StitchingParameters(input_folder=str(tmp_path), rank=1, world=3, device=1)
+    assert StitchingParameters.from_dict(p.to_dict()).world == 3
