@@ -120,6 +120,18 @@ def load_library(path: Optional[str] = None):
     return lib
 
 
+def _pixel_dtype(a, default=SB_U16) -> int:
+    """SB_U8 / SB_U16 of a numpy array or torch tensor; raw addresses take ``default``."""
+    dt = str(getattr(a, "dtype", ""))
+    if dt.endswith("uint8"):
+        return SB_U8
+    if dt.endswith("uint16") or dt.endswith("int16"):
+        return SB_U16
+    if dt == "":
+        return default
+    raise TypeError(f"unsupported pixel dtype {dt} (uint8 and uint16 are implemented)")
+
+
 def _ptr(a) -> int:
     """Address of a numpy array's first element, a raw int address, or a torch tensor's data_ptr."""
     if isinstance(a, (int, np.integer)):
@@ -231,17 +243,16 @@ class Context:
 
     def flatfield_apply(self, channel: int, tiles: np.ndarray) -> np.ndarray:
         tiles = np.ascontiguousarray(tiles)
-        assert tiles.dtype == np.uint16
         t3 = tiles.reshape((-1,) + tiles.shape[-2:])
         out = np.empty_like(t3)
         self._check(self.lib.sb_flatfield_apply(self.handle, channel, _ptr(t3), _ptr(out), t3.shape[0], t3.shape[1],
-                                                t3.shape[2], SB_U16, SB_MEM_HOST), "sb_flatfield_apply")
+                                                t3.shape[2], _pixel_dtype(t3), SB_MEM_HOST), "sb_flatfield_apply")
         return out.reshape(tiles.shape)
 
     # ------------------------------------------------------------------ fusion
     def fuse_region(self, tiles: Sequence[tuple], tile_shape, canvas_shape, *, out, tile_mem=SB_MEM_HOST,
                     out_mem=SB_MEM_HOST, apply_flatfield=False, blend=SB_BLEND_PASTE, blend_ov=(0, 0),
-                    layout=SB_LAYOUT_ROWMAJOR, out_row_pitch=0, chunk=(0, 0), lane=-1, keepalive=None):
+                    layout=SB_LAYOUT_ROWMAJOR, out_row_pitch=0, chunk=(0, 0), lane=-1, keepalive=None, dtype=None):
         """``tiles``: sequence of ``(px, x, y, c, z, crop_t, crop_b, crop_l, crop_r)`` in paste order.
 
         ``canvas_shape`` = ``(num_c, num_z, height, width)``.  ``out`` is a numpy array / address / tensor.
@@ -251,7 +262,11 @@ class Context:
         for i, t in enumerate(tiles):
             px, x, y, c, z, ct, cb, cl, cr = t
             arr[i] = SbTile(_ptr(px), int(x), int(y), int(c), int(z), int(ct), int(cb), int(cl), int(cr))
-        job = SbFuseJob(arr, n, int(tile_shape[0]), int(tile_shape[1]), SB_U16, tile_mem,
+        if dtype is None:                      # pixel dtype: from the first tile (or the canvas) when they are arrays
+            dtype = _pixel_dtype(tiles[0][0] if n else out, _pixel_dtype(out))
+            if isinstance(out, np.ndarray) and _pixel_dtype(out) != dtype:
+                raise TypeError(f"canvas dtype {out.dtype} does not match the tile dtype (the canvas has the tile dtype)")
+        job = SbFuseJob(arr, n, int(tile_shape[0]), int(tile_shape[1]), int(dtype), tile_mem,
                         int(canvas_shape[0]), int(canvas_shape[1]), int(canvas_shape[2]), int(canvas_shape[3]),
                         int(bool(apply_flatfield)), int(blend), int(blend_ov[0]), int(blend_ov[1]),
                         _ptr(out), out_mem, layout, int(out_row_pitch), int(chunk[0]), int(chunk[1]))
@@ -279,44 +294,48 @@ class Context:
                  "runner_up": r.runner_up, "fine_peak": r.fine_peak, "ref_minmax": (r.ref_min, r.ref_max),
                  "mov_minmax": (r.mov_min, r.mov_max), "precision": r.precision} for r in res]
 
-    def _register_job(self, pairs, tile_shape, max_overlap_x, max_overlap_y, mem, upsample_factor, precision, lane):
+    def _register_job(self, pairs, tile_shape, max_overlap_x, max_overlap_y, mem, upsample_factor, precision, lane,
+                      dtype=None):
         n = len(pairs)
+        if dtype is None:
+            dtype = _pixel_dtype(pairs[0][0])
         arr = (SbPair * n)()
         for i, (ref, mov, d) in enumerate(pairs):
             arr[i] = SbPair(_ptr(ref), _ptr(mov), int(d), 0)
         res = (SbPairResult * n)()
-        job = SbRegisterJob(arr, n, int(tile_shape[0]), int(tile_shape[1]), SB_U16, mem, int(max_overlap_x),
+        job = SbRegisterJob(arr, n, int(tile_shape[0]), int(tile_shape[1]), int(dtype), mem, int(max_overlap_x),
                             int(max_overlap_y), int(upsample_factor), int(precision), int(lane))
         return arr, res, job
 
     def register_pairs(self, pairs: Sequence[tuple], tile_shape, max_overlap_x: int, max_overlap_y: int, *,
-                       mem=SB_MEM_HOST, upsample_factor: int = 10, precision: int = SB_PREC_AUTO, lane: int = 0):
+                       mem=SB_MEM_HOST, upsample_factor: int = 10, precision: int = SB_PREC_AUTO, lane: int = 0,
+                       dtype=None):
         """``pairs``: sequence of ``(ref, mov, dir)``.  Returns a list of dicts (see ``sb_pair_result``)."""
         if len(pairs) == 0:
             return []
         arr, res, job = self._register_job(pairs, tile_shape, max_overlap_x, max_overlap_y, mem, upsample_factor,
-                                           precision, lane)
+                                           precision, lane, dtype)
         self._check(self.lib.sb_register_pairs(self.handle, C.byref(job), res), "sb_register_pairs")
         return self._pair_dicts(res)
 
     def register_pairs_async(self, pairs: Sequence[tuple], tile_shape, max_overlap_x: int, max_overlap_y: int, *,
-                             mem=SB_MEM_HOST, upsample_factor: int = 10, precision: int = SB_PREC_AUTO, lane: int = 0):
+                             mem=SB_MEM_HOST, upsample_factor: int = 10, precision: int = SB_PREC_AUTO, lane: int = 0,
+                             dtype=None):
         """Enqueue on ``lane`` and return a :class:`PendingRegistration`; its ``get()`` is valid after ``sync(lane)``
         (``sb_register_pairs_async``).  The tiles must stay valid until then."""
         if len(pairs) == 0:
             return PendingRegistration(self, lane, None, None, None, list(pairs))
         arr, res, job = self._register_job(pairs, tile_shape, max_overlap_x, max_overlap_y, mem, upsample_factor,
-                                           precision, lane)
+                                           precision, lane, dtype)
         self._check(self.lib.sb_register_pairs_async(self.handle, C.byref(job), res), "sb_register_pairs_async")
         return PendingRegistration(self, lane, arr, res, job, list(pairs))
 
     def normalize(self, tiles: np.ndarray) -> np.ndarray:
         tiles = np.ascontiguousarray(tiles)
-        assert tiles.dtype == np.uint16
         t3 = tiles.reshape((-1,) + tiles.shape[-2:])
         out = np.empty_like(t3)
         self._check(self.lib.sb_normalize(self.handle, _ptr(t3), _ptr(out), t3.shape[0], t3.shape[1], t3.shape[2],
-                                          SB_U16, SB_MEM_HOST), "sb_normalize")
+                                          _pixel_dtype(t3), SB_MEM_HOST), "sb_normalize")
         return out.reshape(tiles.shape)
 
 

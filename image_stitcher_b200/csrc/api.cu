@@ -119,7 +119,8 @@ void sb_destroy(sb_ctx* ctx) {
     for (int i = 0; i < SB_NUM_LANES; ++i) {
         Lane& l = ctx->lanes[i];
         sb_register_discard(ctx, i);
-        for (DevBuf* b : {&l.tiles, &l.canvas, &l.meta, &l.work, &l.reg_tiles, &l.reg_work, &l.reg_meta})
+        for (DevBuf* b : {&l.tiles, &l.canvas, &l.meta, &l.work, &l.reg_tiles, &l.reg_work, &l.reg_meta, &l.u8_stage, &l.u8_tiles,
+                          &l.u8_canvas16, &l.u8_canvas8, &l.u8_reg_stage, &l.u8_reg_tiles})
             if (b->p) cudaFree(b->p);
         if (l.meta_host) cudaFreeHost(l.meta_host);
         if (l.reg_host) cudaFreeHost(l.reg_host);
@@ -263,6 +264,7 @@ int64_t sb_chunked_plane_elems(int32_t height, int32_t width, int32_t chunk_h, i
 int sb_fuse_region(sb_ctx* ctx, const sb_fuse_job* job, int lane) {
     if (!ctx) return SB_ERR_INVALID;
     if (lane >= SB_NUM_LANES) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
+    if (job && job->dtype == SB_U8) return sb_fuse_region_u8(ctx, job, lane);
     return sb_fuse_region_impl(ctx, job, lane);
 }
 
@@ -306,21 +308,25 @@ int sb_set_lane_stream(sb_ctx* ctx, int lane, void* cuda_stream) {
 int sb_flatfield_apply(sb_ctx* ctx, int channel, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w,
                        int dtype, int mem) {
     if (!ctx) return SB_ERR_INVALID;
+    if (dtype == SB_U8) return sb_flatfield_apply_u8(ctx, channel, tiles, out, n_tiles, tile_h, tile_w, mem);
     return sb_flatfield_apply_impl(ctx, channel, tiles, out, n_tiles, tile_h, tile_w, dtype, mem);
 }
 
 int sb_register_pairs(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out) {
     if (!ctx) return SB_ERR_INVALID;
+    if (job && job->dtype == SB_U8) return sb_register_pairs_u8(ctx, job, out, false);
     return sb_register_pairs_impl(ctx, job, out, false);
 }
 
 int sb_register_pairs_async(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out) {
     if (!ctx) return SB_ERR_INVALID;
+    if (job && job->dtype == SB_U8) return sb_register_pairs_u8(ctx, job, out, true);
     return sb_register_pairs_impl(ctx, job, out, true);
 }
 
 int sb_normalize(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int dtype, int mem) {
     if (!ctx) return SB_ERR_INVALID;
+    if (dtype == SB_U8) return sb_normalize_u8(ctx, tiles, out, n_tiles, tile_h, tile_w, mem);
     return sb_normalize_impl(ctx, tiles, out, n_tiles, tile_h, tile_w, dtype, mem);
 }
 

@@ -94,36 +94,37 @@ __global__ void __launch_bounds__(256) tile_minmax_kernel(const uint16_t* const*
 }
 
 // normalize_image (:844-855): ((v - min) / (max - min)) * 65535 in float64, truncating cast.
-__device__ __forceinline__ int stretch_px_f64(unsigned v, int mn, int mx) {
+// `maxval` = iinfo(dtype).max of the caller's pixels: 65535, or 255 for (widened) uint8 tiles (:854).
+__device__ __forceinline__ int stretch_px_f64(unsigned v, int mn, int mx, int maxval) {
     if (mx <= mn) return 0;                       // 0/0 -> NaN -> undefined cast in the reference; defined as 0
     const double q = __ddiv_rn((double)((int)v - mn), (double)(mx - mn));
-    return (int)(q * 65535.0);
+    return (int)(q * (double)maxval);
 }
 
 // The same value without the float64 divide.  With a = v - min, b = max - min the exact quotient a * 65535 / b is
 // rational with denominator b <= 65535, so unless it is an integer it lies at least 1 / 65535 away from the next
 // one, while the float64 evaluation is off by at most 65535 * 2^-52: trunc() of both agree.  When b divides
 // a * 65535 the float64 result can land on either side of the integer -- only then the float64 sequence is run.
-// `inv` = 65535.0f / b (computed once per tile).
-__device__ __forceinline__ int stretch_px(unsigned v, int mn, int mx, float inv) {
+// `inv` = maxval / b as float (computed once per tile).
+__device__ __forceinline__ int stretch_px(unsigned v, int mn, int mx, float inv, int maxval) {
     if (mx <= mn) return 0;
     const unsigned b = (unsigned)(mx - mn);
-    const unsigned num = (unsigned)((int)v - mn) * 65535u;                 // < 2^32
+    const unsigned num = (unsigned)((int)v - mn) * (unsigned)maxval;       // < 2^32
     unsigned k = (unsigned)__float2int_rz(__uint2float_rn((unsigned)((int)v - mn)) * inv);
     unsigned rem = num - k * b;                                            // k is off by at most one either way
     if ((int)rem < 0) { --k; rem += b; }
     else if (rem >= b) { ++k; rem -= b; }
-    if (rem == 0 && k != 0) return stretch_px_f64(v, mn, mx);              // exact quotient (rare): reproduce float64 rounding
+    if (rem == 0 && k != 0) return stretch_px_f64(v, mn, mx, maxval);      // exact quotient (rare): reproduce float64 rounding
     return (int)k;
 }
 
 __global__ void __launch_bounds__(256) normalize_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
-                                                        const int2* __restrict__ mm, int64_t px) {
+                                                        const int2* __restrict__ mm, int64_t px, int maxval) {
     const int2 m = mm[blockIdx.y];
     const uint16_t* t = in + (int64_t)blockIdx.y * px;
     uint16_t* o = out + (int64_t)blockIdx.y * px;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px; i += (int64_t)gridDim.x * blockDim.x)
-        o[i] = (uint16_t)stretch_px_f64(t[i], m.x, m.y);
+        o[i] = (uint16_t)stretch_px_f64(t[i], m.x, m.y, maxval);
 }
 
 // cos/sin table of the big odd radix (fft.cuh: pass_odd_gemm): global -> shared, right after the twiddles.
@@ -140,7 +141,7 @@ __device__ __forceinline__ float* stage_ctab(T2* after_tw, const float* __restri
 // ------------------------------------------------------------------------------------------ K1
 template <typename T, int LB>
 __global__ void __launch_bounds__(256, 2) rows_fwd_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm,
-                                                       int tile_w, int Sh, int Sw, int lpb, int nrb, int swap,
+                                                       int tile_w, int Sh, int Sw, int lpb, int nrb, int swap, int maxval,
                                                        const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
                                                        const float* __restrict__ ctab_g, int ctab_n,
                                                        typename Vec2<T>::type* __restrict__ Z, int* __restrict__ nonzero) {
@@ -155,8 +156,8 @@ __global__ void __launch_bounds__(256, 2) rows_fwd_kernel(const PairDesc* __rest
     const PairDesc pd = pairs[p];
     int seen = 0;                                // bit 0: strip a has a non-zero pixel, bit 1: strip b
     const int2 ma = mm[pd.a_tile], mb = mm[pd.b_tile];
-    const float inva = ma.y > ma.x ? 65535.0f / (float)(ma.y - ma.x) : 0.f;
-    const float invb = mb.y > mb.x ? 65535.0f / (float)(mb.y - mb.x) : 0.f;
+    const float inva = ma.y > ma.x ? (float)maxval / (float)(ma.y - ma.x) : 0.f;
+    const float invb = mb.y > mb.x ? (float)maxval / (float)(mb.y - mb.x) : 0.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int i = threadIdx.x; i < Sw; i += blockDim.x) tw[i] = tw_g[i];
     if (!swap) {
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(256, 2) rows_fwd_kernel(const PairDesc* __rest
                 for (int u = 0; u < 4; ++u) {
                     const int x = x0 + 32 * u;
                     if (x < Sw) {
-                        const int na = stretch_px(av[u], ma.x, ma.y, inva), nb = stretch_px(bv[u], mb.x, mb.y, invb);
+                        const int na = stretch_px(av[u], ma.x, ma.y, inva, maxval), nb = stretch_px(bv[u], mb.x, mb.y, invb, maxval);
                         seen |= (na != 0 ? 1 : 0) | (nb != 0 ? 2 : 0);
                         row[x] = mk2<T2, T>((T)(na * kInScale), (T)(nb * kInScale));
                     }
@@ -216,8 +217,8 @@ __global__ void __launch_bounds__(256, 2) rows_fwd_kernel(const PairDesc* __rest
                     if (x < Sw) {
                         int na = 0, nb = 0;
                         if (live) {
-                            na = stretch_px(av[u], ma.x, ma.y, inva);
-                            nb = stretch_px(bv[u], mb.x, mb.y, invb);
+                            na = stretch_px(av[u], ma.x, ma.y, inva, maxval);
+                            nb = stretch_px(bv[u], mb.x, mb.y, invb, maxval);
                             seen |= (na != 0 ? 1 : 0) | (nb != 0 ? 2 : 0);
                         }
                         row[x] = mk2<T2, T>((T)(na * kInScale), (T)(nb * kInScale));
@@ -705,7 +706,7 @@ int pick_lines(int n, size_t elem, int lb, size_t budget) {
 // `h_out` (pinned for asynchronous jobs).  With do_sync the call returns when they have arrived.
 template <typename T>
 int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const GroupGeom& g, int tile_w,
-              const int2* d_mm, int uf, PeakOut* h_out, bool do_sync) {
+              const int2* d_mm, int uf, int maxval, PeakOut* h_out, bool do_sync) {
     cudaStream_t st = lane->stream;
     using T2 = typename Vec2<T>::type;
     const int n = (int)pairs.size();
@@ -847,7 +848,7 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
         T2 *Eyw = (T2*)((uint8_t*)Ey + wo), *Tw = (T2*)((uint8_t*)Tm + wo);
         CtaBest* bestw = (CtaBest*)((uint8_t*)best + wo);
         double* magw = (double*)((uint8_t*)mag2 + wo);
-        k1<<<nb * nrb_fwd, 256, smem_x, ws>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, swap, tw_x, px_plan, cx, cxn, Zw, d_nz + p0);
+        k1<<<nb * nrb_fwd, 256, smem_x, ws>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, swap, maxval, tw_x, px_plan, cx, cxn, Zw, d_nz + p0);
         k2<<<nb * ncg, 256, smem_y, ws>>>(Sh, Sw, ncg, tw_y, py_plan, cy, cyn, Zw, Rw);
         k3<<<nb * nrb_inv, 256, smem_x, ws>>>(Sh, Sw, lpbx, nrb_inv, swap, tw_x, px_plan, cx, cxn, Zw, bestw);
         peak_final_kernel<<<nb, 32, 0, ws>>>(bestw, nrb_inv, Sh, Sw, swap, d_nz + p0, peaks + p0);
@@ -972,6 +973,7 @@ struct RegPending {
     sb_register_job job;           // scalars only; `pairs` points into `pairs_copy`
     std::vector<sb_pair> pairs_copy;
     sb_pair_result* out = nullptr;
+    int maxval = 65535;
     std::vector<RegGroup> groups;
     TileSet ts;
     int2* d_mm = nullptr;
@@ -979,9 +981,10 @@ struct RegPending {
     PeakOut* h_peaks = nullptr;    // pinned
 };
 
-static int reg_enqueue(sb_ctx* ctx, Lane* lane, const sb_register_job* job, sb_pair_result* out, RegPending& pr) {
+static int reg_enqueue(sb_ctx* ctx, Lane* lane, const sb_register_job* job, sb_pair_result* out, int maxval, RegPending& pr) {
     const int H = job->tile_h, W = job->tile_w, n = job->n_pairs;
     pr.job = *job;
+    pr.maxval = maxval;
     pr.pairs_copy.assign(job->pairs, job->pairs + n);
     pr.job.pairs = pr.pairs_copy.data();
     pr.out = out;
@@ -1034,8 +1037,8 @@ static int reg_enqueue(sb_ctx* ctx, Lane* lane, const sb_register_job* job, sb_p
         grp.first = first;
         first += grp.ids.size();
         rc = job->precision == SB_PREC_F64
-                 ? run_group<double>(ctx, lane, grp.pd, g, W, pr.d_mm, job->upsample_factor, pr.h_peaks + grp.first, false)
-                 : run_group<float>(ctx, lane, grp.pd, g, W, pr.d_mm, job->upsample_factor, pr.h_peaks + grp.first, false);
+                 ? run_group<double>(ctx, lane, grp.pd, g, W, pr.d_mm, job->upsample_factor, maxval, pr.h_peaks + grp.first, false)
+                 : run_group<float>(ctx, lane, grp.pd, g, W, pr.d_mm, job->upsample_factor, maxval, pr.h_peaks + grp.first, false);
         if (rc) return rc;
         pr.groups.push_back(std::move(grp));
     }
@@ -1068,7 +1071,7 @@ static int reg_complete(sb_ctx* ctx, Lane* lane, RegPending& pr) {
                 }
             if (!redo.empty()) {
                 std::vector<PeakOut> res2(redo.size());
-                int rc = run_group<double>(ctx, lane, redo, g, W, pr.d_mm, job->upsample_factor, res2.data(), true);
+                int rc = run_group<double>(ctx, lane, redo, g, W, pr.d_mm, job->upsample_factor, pr.maxval, res2.data(), true);
                 if (rc) return rc;
                 for (size_t j = 0; j < redo_k.size(); ++j) {
                     res[redo_k[j]] = res2[j];
@@ -1108,7 +1111,7 @@ void sb_register_discard(sb_ctx* ctx, int lane_idx) {
     }
 }
 
-int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out, bool async) {
+int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out, bool async, int maxval) {
     SB_CHECK(ctx, job && out, "job/out is NULL");
     SB_CHECK(ctx, job->dtype == SB_U16, "only uint16 pixels are implemented");
     SB_CHECK(ctx, job->n_pairs >= 0 && (job->n_pairs == 0 || job->pairs), "bad pair list");
@@ -1122,7 +1125,7 @@ int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_resu
     if (rc) return rc;
     if (job->n_pairs == 0) return SB_OK;
     RegPending* pr = new RegPending();
-    rc = reg_enqueue(ctx, lane, job, out, *pr);
+    rc = reg_enqueue(ctx, lane, job, out, maxval, *pr);
     if (rc) {
         cudaStreamSynchronize(lane->stream);              // nothing of the failed job may still use its buffers
         delete pr;
@@ -1137,7 +1140,8 @@ int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_resu
     return rc;
 }
 
-int sb_normalize_impl(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int dtype, int mem) {
+int sb_normalize_impl(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int dtype, int mem,
+                      int maxval) {
     SB_CHECK(ctx, dtype == SB_U16, "only uint16 pixels are implemented");
     SB_CHECK(ctx, tiles && out && n_tiles > 0 && tile_h > 0 && tile_w > 0, "bad arguments");
     Lane* lane = sb_lane(ctx, 0);
@@ -1159,7 +1163,7 @@ int sb_normalize_impl(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, in
         if (rc) return rc;
         d_out = (uint16_t*)lane->canvas.p;
     }
-    normalize_kernel<<<dim3(std::max(1, ctx->sm_count * 4 / n_tiles), n_tiles), 256, 0, st>>>(d_in, d_out, d_mm, (int64_t)px);
+    normalize_kernel<<<dim3(std::max(1, ctx->sm_count * 4 / n_tiles), n_tiles), 256, 0, st>>>(d_in, d_out, d_mm, (int64_t)px, maxval);
     ctx->launches++;
     SB_CUDA(ctx, cudaGetLastError());
     if (mem == SB_MEM_HOST) SB_CUDA(ctx, cudaMemcpyAsync(out, d_out, px * 2 * n_tiles, cudaMemcpyDeviceToHost, st));

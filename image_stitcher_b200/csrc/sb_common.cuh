@@ -36,6 +36,7 @@ struct Lane {
     cudaStream_t own = nullptr;
     cudaStream_t stream = nullptr;
     DevBuf tiles, canvas, meta, work;
+    DevBuf u8_stage, u8_tiles, u8_canvas16, u8_canvas8, u8_reg_stage, u8_reg_tiles;   // uint8 pixel path (u8.cu)
     void* meta_host = nullptr;      // pinned staging for per-job metadata
     size_t meta_host_cap = 0;
     cudaEvent_t meta_free = nullptr; // the previous job's metadata H2D has been consumed
@@ -89,11 +90,17 @@ static inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m 
 int sb_fuse_region_impl(sb_ctx* ctx, const sb_fuse_job* job, int lane);
 int sb_flatfield_apply_impl(sb_ctx* ctx, int channel, const void* tiles, void* out, int n_tiles, int tile_h,
                             int tile_w, int dtype, int mem);
-int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out, bool async);
+// maxval: iinfo(dtype).max of the caller's pixels (65535, or 255 when the tiles were widened from uint8)
+int sb_register_pairs_impl(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out, bool async, int maxval = 65535);
 int sb_register_complete(sb_ctx* ctx, int lane);     // finish the lane's parked asynchronous registration, if any
 void sb_register_discard(sb_ctx* ctx, int lane);
 int sb_normalize_impl(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int dtype,
-                      int mem);
+                      int mem, int maxval = 65535);
+// uint8 pixels (u8.cu): widen -> uint16 kernels -> narrow with saturation
+int sb_fuse_region_u8(sb_ctx* ctx, const sb_fuse_job* job, int lane);
+int sb_register_pairs_u8(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out, bool async);
+int sb_flatfield_apply_u8(sb_ctx* ctx, int channel, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int mem);
+int sb_normalize_u8(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int mem);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------- device-side PTX wrappers

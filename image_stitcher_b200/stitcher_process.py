@@ -294,14 +294,23 @@ class StitcherProcess(Process):
     # ------------------------------------------------------------------ registration (reference :573-737, :844-855)
     def normalize_image(self, img):
         """Whole-tile min/max stretch in float64 with truncating cast (:844-855) -- ``sb_normalize``."""
-        return self.ctx.normalize(np.ascontiguousarray(img, dtype=np.uint16))
+        return self.ctx.normalize(np.ascontiguousarray(img, dtype=self._pixel_np()))
+
+    def _pixel_np(self):
+        """uint8 or uint16 -- the dtype of the first image, like the reference's ``self.dtype`` (:340)."""
+        dt = np.dtype(self.dtype)
+        if dt not in (np.dtype(np.uint8), np.dtype(np.uint16)):
+            raise RuntimeError(f"pixel dtype {dt} is not supported (uint8 and uint16 are)")
+        return dt
 
     def _precision(self) -> int:
         return {"auto": _ffi.SB_PREC_AUTO, "float32": _ffi.SB_PREC_F32, "float64": _ffi.SB_PREC_F64}[self.registration_precision]
 
     def _register(self, pairs, max_x_overlap, max_y_overlap):
         shape = pairs[0][0].shape
-        return self.ctx.register_pairs([(np.ascontiguousarray(a), np.ascontiguousarray(b), d) for a, b, d in pairs],
+        dt = self._pixel_np()
+        return self.ctx.register_pairs([(np.ascontiguousarray(a, dtype=dt), np.ascontiguousarray(b, dtype=dt), d)
+                                        for a, b, d in pairs],
                                        shape, max_x_overlap, max_y_overlap, upsample_factor=self.upsample_factor,
                                        precision=self._precision())
 
@@ -381,7 +390,7 @@ class StitcherProcess(Process):
         if channel_idx not in self.flatfields:
             return tile
         self._sync_fields()
-        return self.ctx.flatfield_apply(int(channel_idx), np.ascontiguousarray(tile, dtype=np.uint16))
+        return self.ctx.flatfield_apply(int(channel_idx), np.ascontiguousarray(tile, dtype=self._pixel_np()))
 
     def _tile_planes(self, tile: np.ndarray, channel: str):
         """(:739-769): mono -> one plane; H x W x 3 -> <ch>_R/_G/_B planes; 1 x H x W -> squeezed."""
@@ -425,10 +434,10 @@ class StitcherProcess(Process):
                 p = geo.place_tile(info["x"], info["y"], self.input_width, self.input_height, xs, ys,
                                    self.pixel_size_um, lattice)
                 for c, plane in self._tile_planes(tile, key[4]):
-                    plane = np.ascontiguousarray(plane, dtype=np.uint16)
+                    plane = np.ascontiguousarray(plane, dtype=self._pixel_np())
                     keep.append(plane)
                     job.append((plane, p.x, p.y, c, key[3], p.crop_t, p.crop_b, p.crop_l, p.crop_r))
-            out = np.empty((1, self.num_c, self.num_z, height, width), dtype=np.uint16)
+            out = np.empty((1, self.num_c, self.num_z, height, width), dtype=self._pixel_np())
             if self.apply_flatfield:
                 self._sync_fields()
             ov = geo.strip_overlaps(self.input_width, self.input_height, xs, ys, self.pixel_size_um, 2) \

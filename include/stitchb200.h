@@ -45,7 +45,11 @@ typedef enum sb_status {
 } sb_status;
 
 enum { SB_MEM_HOST = 0, SB_MEM_DEVICE = 1 };
-enum { SB_U16 = 0, SB_U8 = 1 };                               /* pixel dtype (self.dtype, :160,:340)            */
+enum { SB_U16 = 0, SB_U8 = 1 };                               /* pixel dtype (self.dtype, :160,:340).  SB_U8: every
+                                                                 range follows the dtype like the reference's
+                                                                 iinfo(self.dtype) -- stretch to 255 (:854), clip at
+                                                                 255 (:838-841), uint8 canvas (:503); paste mode
+                                                                 only, tile_w % 8 == 0                           */
 enum { SB_FIELD_F32 = 0, SB_FIELD_F64 = 1 };                  /* flat/dark-field dtype (a12: result_type rule)  */
 enum { SB_BLEND_PASTE = 0,                                    /* reference: crop-to-seam + overwrite (:789-817) */
        SB_BLEND_LINEAR = 1, SB_BLEND_FEATHER = 2 };           /* extensions, defined by oracle/blend_ref.py     */

@@ -37,10 +37,13 @@ def load_golden(name):
                      apply_flatfield=kw.get("apply_flatfield", False),
                      scan_pattern=kw.get("scan_pattern", "Unidirectional"),
                      registration_channel=kw.get("registration_channel", ""), flatfields=flat)
+    if tiles:
+        st.dtype = np.dtype(tiles[0].pixels.dtype)
     return g, st, tiles, kw
 
 
-SMALL_GOLDENS = ["reg_2x2_mono", "reg_3x3_spattern_flat", "coord_3x4_flat64", "coord_2x2_plain", "reg_2x3_negdrift"]
+SMALL_GOLDENS = ["reg_2x2_mono", "reg_3x3_spattern_flat", "coord_3x4_flat64", "coord_2x2_plain", "reg_2x3_negdrift",
+                 "reg_2x2_u8_flat"]
 
 
 @pytest.fixture(scope="session")

@@ -41,6 +41,9 @@ CASES = {
                              apply_flatfield=True),
     "coord_2x2_plain": dict(rows=2, cols=2, tile_h=128, tile_w=128, seed=14, jitter=0),
     "reg_2x3_negdrift": dict(rows=2, cols=3, tile_h=160, tile_w=192, seed=21, jitter=3, use_registration=True),
+    # 8-bit acquisition (the reference takes every range from the dtype of the first image, :340/:838/:854)
+    "reg_2x2_u8_flat": dict(rows=2, cols=2, tile_h=192, tile_w=256, seed=15, jitter=2, use_registration=True,
+                            apply_flatfield=True, bits=8),
 }
 FULL = {
     "full_2x2_2048": dict(rows=2, cols=2, tile_h=2048, tile_w=2048, seed=7, jitter=3, use_registration=True),
@@ -52,7 +55,11 @@ def sha(a: np.ndarray) -> str:
 
 
 def run_case(name, kw, store_arrays=True):
-    st, tiles, truth = synth.make_region(**kw)
+    gen_kw = {k: v for k, v in kw.items() if k != "bits"}
+    st, tiles, truth = synth.make_region(**gen_kw)
+    if kw.get("bits") == 8:
+        for t in tiles:
+            t.pixels = (t.pixels >> 8).astype(np.uint8)
     flat64 = name.endswith("flat64")
     with tempfile.TemporaryDirectory() as tmp:
         root = os.path.join(tmp, "acq")

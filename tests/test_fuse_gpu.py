@@ -44,7 +44,7 @@ def test_paste_matches_reference_golden(ctx, name):
     ctx.clear_fields()
     for c, ff in st.flatfields.items():
         ctx.set_flatfield(c, ff)
-    out = np.full((1,) + cshape, 0xABCD, np.uint16)
+    out = np.full((1,) + cshape, 0xAB, g["canvas"].dtype)       # canvas dtype == tile dtype (uint16, or uint8)
     ctx.fuse_region(job, (st.tile_h, st.tile_w), cshape, out=out, apply_flatfield=st.apply_flatfield)
     assert np.array_equal(out, g["canvas"])
 
@@ -194,3 +194,48 @@ def test_band_sharded_fusion_equals_whole_canvas(ctx):
             ctx.fuse_region(band, (th, tw), (1, 1, y1 - y0, Wc), out=out, apply_flatfield=True)
             parts[0, c, z, y0:y1] = out[0, 0, 0]
     assert np.array_equal(parts, whole)
+
+
+def test_uint8_pixels_paste_flatfield_and_elementwise(ctx):
+    """SB_U8 (8-bit acquisitions): canvas dtype uint8, flat-field clip at 255 (stitcher_process.py:838-841), normalize_image
+    scaled to 255 (:854) -- against plain NumPy statements of the reference lines."""
+    rng = np.random.default_rng(21)
+    th, tw, C, Z, Hc, Wc = 96, 136, 2, 1, 301, 407
+    job = []
+    for i in range(17):
+        px = rng.integers(0, 256, (th, tw), dtype=np.uint8)
+        job.append((px, int(rng.integers(0, Wc - 40)), int(rng.integers(0, Hc - 40)), int(rng.integers(0, C)), 0,
+                    *[int(v) for v in rng.integers(0, 7, 4)]))
+    flat = rng.uniform(0.5, 1.6, (th, tw)).astype(np.float32)
+    ctx.clear_fields()
+    ctx.set_flatfield(1, flat)
+    for layout_chunked in (False, True):
+        exp = np.zeros((1, C, Z, Hc, Wc), np.uint8)
+        for px, x, y, c, z, ct, cb, cl, cr in job:
+            v = px
+            if c == 1:
+                v = (px / flat).clip(min=0, max=255).astype(np.uint8)
+            v = v[ct:th - cb, cl:tw - cr]
+            y0, x0 = y + ct, x + cl
+            y1, x1 = min(y0 + v.shape[0], Hc), min(x0 + v.shape[1], Wc)
+            exp[0, c, z, y0:y1, x0:x1] = v[:y1 - y0, :x1 - x0]
+        if not layout_chunked:
+            out = np.full((1, C, Z, Hc, Wc), 77, np.uint8)
+            ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=out, apply_flatfield=True)
+            assert out.dtype == np.uint8 and np.array_equal(out, exp)
+        else:
+            from image_stitcher_b200 import _ffi
+            ch = 128
+            ncy, ncx = -(-Hc // ch), -(-Wc // ch)
+            out = np.full((C * Z, ncy, ncx, ch, ch), 77, np.uint8)
+            ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=out, apply_flatfield=True, layout=_ffi.SB_LAYOUT_CHUNKED,
+                            chunk=(ch, ch))
+            dense = out.transpose(0, 1, 3, 2, 4).reshape(C * Z, ncy * ch, ncx * ch)
+            assert np.array_equal(dense[:, :Hc, :Wc], exp[0, :, 0])
+    a = job[0][0]
+    assert np.array_equal(ctx.flatfield_apply(1, a), (a / flat).clip(min=0, max=255).astype(np.uint8))
+    from oracle import stitch_ref as sr
+    assert np.array_equal(ctx.normalize(a), sr.normalize_image(a, np.uint8))
+    with pytest.raises(RuntimeError, match="paste"):
+        ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=np.zeros((1, C, Z, Hc, Wc), np.uint8), blend=1, blend_ov=(10, 10))
+    ctx.clear_fields()

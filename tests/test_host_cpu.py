@@ -121,7 +121,7 @@ def test_parse_squid_layout_and_geometry_match_reference_golden(name, tmp_path, 
     assert s.timepoints == ["0"] and s.regions == ["A1"]
     assert s.monochrome_channels == [str(c) for c in g["monochrome_channels"]]
     assert s.pixel_size_um == float(g["pixel_size_um"])
-    assert (s.input_height, s.input_width) == (kw["tile_h"], kw["tile_w"]) and s.dtype == np.uint16
+    assert (s.input_height, s.input_width) == (kw["tile_h"], kw["tile_w"]) and s.dtype == tiles[0].pixels.dtype
     assert s.num_z == kw.get("num_z", 1)
     # paste order == sorted file names == the order the reference iterated (golden tile_names)
     order = [os.path.basename(v["filepath"]) for v in s.get_region_data(0, "A1").values()]

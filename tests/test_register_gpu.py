@@ -228,3 +228,22 @@ def test_well_pipeline_host_buffers_match_oracle(ctx):
         assert np.array_equal(outs[w], sr.stitch_region(st, recs))
     pipe.close()
     ctx.clear_fields()
+
+
+def test_uint8_tiles_registration_matches_oracle(ctx):
+    """8-bit tiles: normalize_image scales to iinfo(uint8).max = 255 before the phase correlation (:854)."""
+    from oracle import stitch_ref as sr
+    rng = np.random.default_rng(8)
+    H, W, ov = 256, 320, 34
+    world = synth.make_world(H * 2 + 64, W * 2 + 64, rng)
+    a = (np.clip(world[20:20 + H, 20:20 + W], 0, 65535).astype(np.uint16) >> 8).astype(np.uint8)
+    bh = (np.clip(world[22:22 + H, 20 + W - ov - 1:20 + 2 * W - ov - 1], 0, 65535).astype(np.uint16) >> 8).astype(np.uint8)
+    bv = (np.clip(world[20 + H - ov + 1:20 + 2 * H - ov + 1, 17:17 + W], 0, 65535).astype(np.uint16) >> 8).astype(np.uint8)
+    res = ctx.register_pairs([(a, bh, H_DIR), (a, bv, V_DIR)], (H, W), ov, ov)
+    eh = sr.calculate_horizontal_shift(a, bh, ov, dtype=np.uint8, return_details=True)
+    ev = sr.calculate_vertical_shift(a, bv, ov, dtype=np.uint8, return_details=True)
+    for r, e in zip(res, (eh, ev)):
+        assert (r["dy"], r["dx"]) == e[0]
+        assert r["coarse"] == e[2]["coarse"] and r["fine"] == e[2]["fine"]
+    pend = ctx.register_pairs_async([(a, bh, H_DIR)], (H, W), ov, ov, lane=2)
+    assert (pend.get()[0]["dy"], pend.get()[0]["dx"]) == eh[0]
