@@ -13,7 +13,7 @@ registered in ``sys.modules`` for them:
 * ``skimage.registration.phase_cross_correlation`` -> ``oracle.pcc_ref`` restatement
 * ``dask.array.zeros`` -> ``numpy.zeros`` (NumPy slice assignment reproduces dask's
   sequential last-writer-wins ``__setitem__``)
-* ``dask_image.imread.imread`` -> ``cv2.imread(..., IMREAD_UNCHANGED)[None]``
+* ``dask_image.imread.imread`` -> ``cv2.imread(..., IMREAD_UNCHANGED)[None]`` (colour images flipped BGR -> RGB)
 * writers / BaSiC / pyvips / zarr -> inert placeholders (never called by the hot path)
 """
 from __future__ import annotations
@@ -61,6 +61,8 @@ def install_stubs() -> None:
         img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
         if img is None:
             raise FileNotFoundError(path)
+        if img.ndim == 3 and img.shape[2] == 3:
+            img = np.ascontiguousarray(img[:, :, ::-1])     # OpenCV decodes BGR; dask_image (pims) yields RGB
         return img[None]
 
     class _DaskArray:  # only used in isinstance() checks (stitcher_process.py:1993)

@@ -142,7 +142,8 @@ def write_squid_layout(root: str, regions: Dict[str, List[TileRec]], timepoint: 
             if key not in seen:
                 seen.add(key)
                 rows.append(f"{region},{t.fov},{t.z_level},{t.x_mm!r},{t.y_mm!r},{t.z_level * acq.get('dz(um)', 1.0)!r}")
-            ok = cv2.imwrite(os.path.join(root, str(timepoint), t.name), t.pixels)
+            px = t.pixels[:, :, ::-1] if (t.pixels.ndim == 3 and t.pixels.shape[2] == 3) else t.pixels   # OpenCV stores BGR
+            ok = cv2.imwrite(os.path.join(root, str(timepoint), t.name), np.ascontiguousarray(px))
             if not ok:
                 raise IOError(f"cv2.imwrite failed for {t.name}")
     with open(os.path.join(root, str(timepoint), "coordinates.csv"), "w") as f:

@@ -46,6 +46,9 @@ SMALL_GOLDENS = ["reg_2x2_mono", "reg_3x3_spattern_flat", "coord_3x4_flat64", "c
                  "reg_2x2_u8_flat"]
 
 
+RGB_GOLDENS = ["coord_2x3_rgb_u8"]       # colour tiles: only through the paths that split planes (oracle, StitcherProcess)
+
+
 @pytest.fixture(scope="session")
 def golden_loader():
     return load_golden

@@ -44,6 +44,9 @@ CASES = {
     # 8-bit acquisition (the reference takes every range from the dtype of the first image, :340/:838/:854)
     "reg_2x2_u8_flat": dict(rows=2, cols=2, tile_h=192, tile_w=256, seed=15, jitter=2, use_registration=True,
                             apply_flatfield=True, bits=8),
+    # 8-bit RGB camera tiles: one file per fov, expanded to <channel>_R/_G/_B planes (:355-362, :757-763)
+    "coord_2x3_rgb_u8": dict(rows=2, cols=3, tile_h=96, tile_w=128, seed=16, jitter=0, bits=8, rgb=True,
+                             channels=("c0", "c1", "c2")),
 }
 FULL = {
     "full_2x2_2048": dict(rows=2, cols=2, tile_h=2048, tile_w=2048, seed=7, jitter=3, use_registration=True),
@@ -55,11 +58,24 @@ def sha(a: np.ndarray) -> str:
 
 
 def run_case(name, kw, store_arrays=True):
-    gen_kw = {k: v for k, v in kw.items() if k != "bits"}
+    gen_kw = {k: v for k, v in kw.items() if k not in ("bits", "rgb")}
     st, tiles, truth = synth.make_region(**gen_kw)
     if kw.get("bits") == 8:
         for t in tiles:
             t.pixels = (t.pixels >> 8).astype(np.uint8)
+    if kw.get("rgb"):
+        # merge the three synthetic channels of every (fov, z) into one H x W x 3 colour tile of channel "BF LED matrix full"
+        by_key = {}
+        for t in tiles:
+            by_key.setdefault((t.fov, t.z_level), {})[t.channel] = t
+        merged = []
+        for (fov, z), chans in sorted(by_key.items()):
+            first = chans["c0"]
+            first.pixels = np.stack([chans[c].pixels for c in ("c0", "c1", "c2")], axis=-1)
+            first.channel = "BF LED matrix full"
+            first.name = f"A1_{fov}_{z}_BF_LED_matrix_full.tiff"
+            merged.append(first)
+        tiles = sorted(merged, key=lambda t: t.name)
     flat64 = name.endswith("flat64")
     with tempfile.TemporaryDirectory() as tmp:
         root = os.path.join(tmp, "acq")

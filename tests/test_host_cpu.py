@@ -9,7 +9,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, SMALL_GOLDENS, load_golden
+from conftest import RGB_GOLDENS, ROOT, SMALL_GOLDENS, load_golden
 from image_stitcher_b200 import geometry as geo
 from image_stitcher_b200 import ome_zarr_writer as ozw
 from image_stitcher_b200.stitcher_parameters import StitchingParameters
@@ -111,7 +111,7 @@ def _stitcher(root, **params):
     return s
 
 
-@pytest.mark.parametrize("name", SMALL_GOLDENS)
+@pytest.mark.parametrize("name", SMALL_GOLDENS + RGB_GOLDENS)
 def test_parse_squid_layout_and_geometry_match_reference_golden(name, tmp_path, capsys):
     g, st, tiles, kw = load_golden(name)
     root = str(tmp_path / "acq")

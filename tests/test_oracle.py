@@ -7,7 +7,7 @@ import pytest
 from scipy import ndimage
 import scipy.fft as sfft
 
-from conftest import SMALL_GOLDENS, GOLDEN_DIR, load_golden
+from conftest import RGB_GOLDENS, SMALL_GOLDENS, GOLDEN_DIR, load_golden
 from oracle import pcc_ref, stitch_ref as sr, synth
 
 
@@ -59,7 +59,7 @@ def test_shift_calls_match_reference():
         assert sr.calculate_vertical_shift(g[f"a_{i}"], g[f"bv_{i}"], ov) == tuple(g[f"v_{i}"])
 
 
-@pytest.mark.parametrize("name", SMALL_GOLDENS)
+@pytest.mark.parametrize("name", SMALL_GOLDENS + RGB_GOLDENS)
 def test_oracle_reproduces_reference_golden(name):
     g, st, tiles, kw = load_golden(name)
     if st.use_registration:

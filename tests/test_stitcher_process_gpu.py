@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import SMALL_GOLDENS, load_golden
+from conftest import RGB_GOLDENS, SMALL_GOLDENS, load_golden
 from image_stitcher_b200 import ome_zarr_writer as ozw
 from image_stitcher_b200.stitcher_parameters import StitchingParameters
 from oracle import synth
@@ -40,7 +40,7 @@ def _prepare(s):
     s.parse_acquisition_metadata()
 
 
-@pytest.mark.parametrize("name", SMALL_GOLDENS)
+@pytest.mark.parametrize("name", SMALL_GOLDENS + RGB_GOLDENS)
 def test_methods_in_run_order_match_reference_golden(name, tmp_path):
     g, st, tiles, kw = load_golden(name)
     root = str(tmp_path / "acq")
