@@ -725,12 +725,14 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     const int rs = (3 * uf + 1) / 2;            // ceil(1.5 * uf)
     const int dftshift = rs / 2;                // fix(rs / 2)
 
-    // Sub-batches sized so that Z + R of the sub-batches in flight stay L2 resident.  Two sub-batches run
-    // concurrently (the lane's stream and its auxiliary stream, each with its own workspace half): the chain is a
-    // sequence of short dependent kernels, and the neighbour's blocks fill the tails and launch gaps.
-    static const int kWays = getenv("SB_REG_WAYS") ? std::max(1, std::min(4, atoi(getenv("SB_REG_WAYS")))) : 2;
+    // Sub-batches: up to kWays of them run concurrently (the lane's stream and its auxiliary streams, each with its own
+    // workspace slice) -- the chain is a sequence of short dependent kernels, and the neighbours' blocks fill the tails
+    // and launch gaps.  Measured on B200 (1152 pairs): 64 MB of spectra in flight (L2 resident) 18.6 ms, 128 MB 17.1,
+    // 256 MB 16.7, 384 MB over 3 streams 16.1: fewer, larger launches beat strict L2 residency, so the budget is 384 MB.
+    static const int kWays = getenv("SB_REG_WAYS") ? std::max(1, std::min(4, atoi(getenv("SB_REG_WAYS")))) : 3;
     const size_t per_pair = 2 * strip * sizeof(T2);
-    int B = (int)std::max<size_t>(1, (size_t)(64u << 20) / per_pair);
+    static const size_t kL2Budget = (size_t)(getenv("SB_REG_L2_MB") ? std::max(8, atoi(getenv("SB_REG_L2_MB"))) : 384) << 20;
+    int B = (int)std::max<size_t>(1, kL2Budget / per_pair);
     int ways = 1;
     while (ways < kWays && B / (ways + 1) >= 2 && n > B / (ways + 1)) ++ways;
     B = std::min(std::max(1, B / ways), n);

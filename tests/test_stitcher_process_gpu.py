@@ -169,3 +169,25 @@ def test_stop_event_terminates_before_the_next_region(tmp_path):
     s.stop_event.set()
     with pytest.raises(SystemExit):
         s.stitch_region(0, "A1")
+
+
+def test_stitcher_class_and_sync_cli(tmp_path, capsys):
+    """The reference's second orchestrator (``stitcher.Stitcher``) and ``stitcher_cli``: same canvas, delivered through
+    the Qt-style signals; the CLI runs in-process like stitcher_cli.py:112."""
+    from image_stitcher_b200 import stitcher_cli
+    from image_stitcher_b200.stitcher import Stitcher
+    g, st, tiles, kw = load_golden("reg_2x2_mono")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    s = Stitcher(StitchingParameters(input_folder=root, use_registration=True))
+    seen = {}
+    s.finished_saving.connect(lambda path, dtype: seen.update(path=path, dtype=dtype))
+    s.update_progress.connect(lambda cur, total: seen.update(progress=(cur, total)))
+    s.run()
+    assert s.chunks == (1, 1, 1, 512, 512) and seen["progress"] == (4, 4)
+    assert np.array_equal(ozw.read_ome_zarr_level(seen["path"], 0), g["canvas"])
+    with pytest.raises(ValueError):
+        Stitcher(StitchingParameters(input_folder=str(tmp_path / "missing")))       # validate() in the constructor
+    assert stitcher_cli.main(["-i", root, "-r"]) == 0
+    assert "Stitching completed" in capsys.readouterr().out
+    assert stitcher_cli.main(["-i", str(tmp_path / "missing")]) == 1
