@@ -55,7 +55,9 @@ def parse_args():
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  It is started before the warm-up steps (same load as
+    the timed steps; nvidia-smi itself needs ~100 ms to come up) and every sample is stamped with the host time it
+    arrived, so the ones inside the timed region can be told apart."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -67,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -76,9 +78,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_load0=None, t_timed0=None, t_timed1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -86,9 +88,11 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, timed = [], [], set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if t_load0 is not None and not (t_load0 <= ts <= (t_timed1 or ts) + 0.06):
+                continue
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 7:
                 continue
@@ -97,11 +101,14 @@ class ClockSampler:
                 mx.append(float(p[1]))
             except ValueError:
                 continue
+            if t_timed0 is not None and t_timed0 <= ts <= t_timed1 + 0.06:
+                timed += 1
             for nm, v in zip(names, p[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": timed,
+                "window": "warm-up + timed steps (identical load), 50 ms period"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm (oracle)
@@ -307,13 +314,16 @@ def run_b200(args, rank, world, local_rank):
         if record is not None:
             record.append((e0, e1, e2))
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step(None)                                           # first touch (allocations inside the library), not sampled
+    torch.cuda.synchronize()
+    t_load0 = time.perf_counter()
     for _ in range(args.warmup):
         step(None)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.kernel_launches
     torch.cuda.synchronize()
     t_start, t_end = ev(), ev()
@@ -326,7 +336,7 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
     launches = ctx.kernel_launches - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_load0, wall0, wall0 + wall)
     total_ms = t_start.elapsed_time(t_end)
     reg_ms = [a.elapsed_time(b) for a, b, _ in recs]
     fuse_ms = [b.elapsed_time(c) for _, b, c in recs]
