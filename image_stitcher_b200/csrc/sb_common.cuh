@@ -48,6 +48,8 @@ struct Lane {
     void* reg_pending = nullptr;    // parked asynchronous registration job (RegPending in reg.cu)
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // extra streams of the lane: registration sub-batches rotate over them
     cudaEvent_t aux_fork = nullptr, aux_join[3] = {nullptr, nullptr, nullptr};
+    std::vector<int32_t> rect_pieces;   // cached rectangle decomposition of the rectangle-streaming paste kernel ...
+    uint64_t rect_sig = 0;              // ... and the geometry signature it was computed for
     std::vector<int32_t> perm;      // cached block-row order of the paste kernel (fuse.cu) ...
     uint64_t perm_sig = 0;          // ... and the geometry signature it was computed for
 };
@@ -158,6 +160,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// bulk prefetch of [p, p + bytes) into L2 (p 16-byte aligned, bytes a multiple of 16); no destination, no completion
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 // streaming 128-bit store: written once, never re-read by this kernel
 __device__ __forceinline__ void st_stream_v4(void* p, uint4 v) {
