@@ -304,6 +304,9 @@ __device__ __forceinline__ float2 fx2_unpack(unsigned long long v) {
     return r;
 }
 
+#ifndef SB_GEMM_LT
+#define SB_GEMM_LT 4          // lines per thread of the GEMM tile (4 or 2): 4 q x LT lines complex accumulators for Ce and So
+#endif
 __device__ __forceinline__ void pass_odd_gemm(float2* __restrict__ a, float2* __restrict__ b, const float2* __restrict__ tw,
                                               const float* __restrict__ ctab, int N, int Ns, int R, int nlines, bool inverse) {
     const int M = N / R;
@@ -337,7 +340,8 @@ __device__ __forceinline__ void pass_odd_gemm(float2* __restrict__ a, float2* __
     }
     __syncthreads();
     // ---- step 2: the GEMM.  item = (q tile of 4, column group = (j, 4 lines)); lanes run over column groups.
-    const int lgs = nlines >> 2;
+    constexpr int LT = SB_GEMM_LT;
+    const int lgs = nlines / LT;
     const int ncg = M * lgs;
     const int nqt = h >> 2;                                // FULL tiles of 4 outputs q; the h & 3 leftover outputs go below
     const float* cosb = ctab;
@@ -352,30 +356,35 @@ __device__ __forceinline__ void pass_odd_gemm(float2* __restrict__ a, float2* __
         if (it < n_gemm) {
             const int qt = it / ncg, cg = it - qt * ncg;
             const int j = cg / lgs, lg = cg - j * lgs;
-            const ulonglong2* ep = reinterpret_cast<const ulonglong2*>(b + (size_t)(M + j) * nlines + lg * 4);
-            const ulonglong2* op = reinterpret_cast<const ulonglong2*>(b + (size_t)((R - 1) * M + j) * nlines + lg * 4);
+            const ulonglong2* ep = reinterpret_cast<const ulonglong2*>(b + (size_t)(M + j) * nlines + lg * LT);
+            const ulonglong2* op = reinterpret_cast<const ulonglong2*>(b + (size_t)((R - 1) * M + j) * nlines + lg * LT);
             const float4* cp = reinterpret_cast<const float4*>(cosb + qt * 4);
             const float4* sp = reinterpret_cast<const float4*>(sinb + qt * 4);
-            unsigned long long ce[4][4], so[4][4];
+            unsigned long long ce[4][LT], so[4][LT];
 #pragma unroll
             for (int t = 0; t < 4; ++t)
 #pragma unroll
-                for (int l = 0; l < 4; ++l) ce[t][l] = so[t][l] = 0ull;
+                for (int l = 0; l < LT; ++l) ce[t][l] = so[t][l] = 0ull;
 #pragma unroll 2
             for (int r = 1; r <= h; ++r) {
                 const float4 c = *cp, s = *sp;
-                const ulonglong2 e01 = ep[0], e23 = ep[1], o01 = op[0], o23 = op[1];
+                unsigned long long e[LT], o[LT];
+#pragma unroll
+                for (int v = 0; v < LT / 2; ++v) {
+                    const ulonglong2 ev = ep[v], ov = op[v];
+                    e[2 * v] = ev.x; e[2 * v + 1] = ev.y;
+                    o[2 * v] = ov.x; o[2 * v + 1] = ov.y;
+                }
                 cp += QP >> 2;
                 sp += QP >> 2;
                 ep += es;
                 op -= es;
-                const unsigned long long e[4] = {e01.x, e01.y, e23.x, e23.y}, o[4] = {o01.x, o01.y, o23.x, o23.y};
                 const float cv[4] = {c.x, c.y, c.z, c.w}, sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const unsigned long long cc = fx2_dup(cv[t]), ss = fx2_dup(sv[t]);
 #pragma unroll
-                    for (int l = 0; l < 4; ++l) {
+                    for (int l = 0; l < LT; ++l) {
                         ce[t][l] = fx2_fma(e[l], cc, ce[t][l]);
                         so[t][l] = fx2_fma(o[l], ss, so[t][l]);
                     }
@@ -383,11 +392,11 @@ __device__ __forceinline__ void pass_odd_gemm(float2* __restrict__ a, float2* __
             }
             const int k = j % Ns;
             const int dst0 = (j / Ns) * Ns * R + k;
-            const float2* y0p = b + (size_t)j * nlines + lg * 4;
+            const float2* y0p = b + (size_t)j * nlines + lg * LT;
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
+            for (int l = 0; l < LT; ++l) {
                 const float2 y0 = y0p[l];
-                float2* out = a + (size_t)(lg * 4 + l) * N + dst0;
+                float2* out = a + (size_t)(lg * LT + l) * N + dst0;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int q = qt * 4 + t + 1;

@@ -26,6 +26,10 @@
 #include <cmath>
 #include <map>
 
+#ifndef SB_REG_CTAS
+#define SB_REG_CTAS 2        // resident blocks per SM the FFT kernels are sized for (registers and shared memory)
+#endif
+
 namespace {
 
 constexpr double kInScale = 1.0 / 65536.0;                       // exact power-of-two input scaling
@@ -140,7 +144,7 @@ __device__ __forceinline__ float* stage_ctab(T2* after_tw, const float* __restri
 
 // ------------------------------------------------------------------------------------------ K1
 template <typename T, int LB>
-__global__ void __launch_bounds__(256, 2) rows_fwd_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm,
+__global__ void __launch_bounds__(256, SB_REG_CTAS) rows_fwd_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm,
                                                        int tile_w, int Sh, int Sw, int lpb, int nrb, int swap, int maxval,
                                                        const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
                                                        const float* __restrict__ ctab_g, int ctab_n,
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(256, 2) rows_fwd_kernel(const PairDesc* __rest
 // ------------------------------------------------------------------------------------------ K2
 // One block owns G columns kx and their mirrors (Sw - kx) % Sw: 2G lines of length Sh.
 template <typename T, int G>
-__global__ void __launch_bounds__(256, 2) cols_xpower_kernel(int Sh, int Sw, int ncg,
+__global__ void __launch_bounds__(256, SB_REG_CTAS) cols_xpower_kernel(int Sh, int Sw, int ncg,
                                                           const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
                                                           const float* __restrict__ ctab_g, int ctab_n,
                                                           typename Vec2<T>::type* __restrict__ Z,
@@ -328,7 +332,7 @@ __device__ __forceinline__ void best_update(V& bv, int& bi, V v, int i) {
 }
 
 template <typename T, int LB>
-__global__ void __launch_bounds__(256, 2) rows_inv_argmax_kernel(int Sh, int Sw, int lpb, int nrb, int swap,
+__global__ void __launch_bounds__(256, SB_REG_CTAS) rows_inv_argmax_kernel(int Sh, int Sw, int lpb, int nrb, int swap,
                                                               const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
                                                               const float* __restrict__ ctab_g, int ctab_n,
                                                               const typename Vec2<T>::type* __restrict__ Y,
@@ -756,7 +760,7 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     const size_t ctab_xb = ctab_xn ? (size_t)ctab_xn * 4 + 16 : 0, ctab_yb = ctab_yn ? (size_t)ctab_yn * 4 + 16 : 0;
 
     // launch geometry: two blocks per SM wherever the lines + tables allow it
-    constexpr size_t kBudget = 113 * 1024;
+    constexpr size_t kBudget = (size_t)(227 / SB_REG_CTAS - 1) * 1024 + 512;
     int lbx = 4, lpbx = pick_lines(Sw, sizeof(T2), 4, kBudget - ctab_xb);
     if (lpbx < 4) { lbx = 1; lpbx = pick_lines(Sw, sizeof(T2), 1, 200 * 1024 - ctab_xb); }
     if (lpbx < 1) return sb_fail(ctx, SB_ERR_UNSUPPORTED, "strip width %d too large for the shared-memory FFT", Sw);
