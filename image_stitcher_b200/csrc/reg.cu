@@ -113,6 +113,9 @@ __device__ __forceinline__ int stretch_px_f64(unsigned v, int mn, int mx, int ma
 __device__ __forceinline__ int stretch_px(unsigned v, int mn, int mx, float inv, int maxval) {
     if (mx <= mn) return 0;
     const unsigned b = (unsigned)(mx - mn);
+    // full-range tile (saturated pixels next to a zero): every quotient is exact, and float64 gives (a / maxval) * maxval
+    // == a for all a <= maxval (checked exhaustively for 255 and 65535) -- skip the float64 sequence for the whole tile
+    if (b == (unsigned)maxval) return (int)v - mn;
     const unsigned num = (unsigned)((int)v - mn) * (unsigned)maxval;       // < 2^32
     unsigned k = (unsigned)__float2int_rz(__uint2float_rn((unsigned)((int)v - mn)) * inv);
     unsigned rem = num - k * b;                                            // k is off by at most one either way

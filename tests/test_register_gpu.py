@@ -247,3 +247,20 @@ def test_uint8_tiles_registration_matches_oracle(ctx):
         assert r["coarse"] == e[2]["coarse"] and r["fine"] == e[2]["fine"]
     pend = ctx.register_pairs_async([(a, bh, H_DIR)], (H, W), ov, ov, lane=2)
     assert (pend.get()[0]["dy"], pend.get()[0]["dx"]) == eh[0]
+
+
+def test_full_range_and_exact_quotient_tiles(ctx):
+    """normalize_image on tiles whose range makes quotients exact: max - min == 65535 (every pixel) and a range that
+    divides 65535 * a for many a (b = 255 * 5) -- the integer stretch must agree with the float64 expression."""
+    from oracle import stitch_ref as sr
+    rng = np.random.default_rng(12)
+    a = rng.integers(0, 65536, (64, 96), dtype=np.uint16)
+    a[0, 0], a[0, 1] = 0, 65535
+    b = rng.integers(1000, 1000 + 1276, (64, 96), dtype=np.uint16)
+    b[0, 0], b[0, 1] = 1000, 1000 + 1275
+    for t in (a, b):
+        assert np.array_equal(ctx.normalize(t), sr.normalize_image(t))
+    res = ctx.register_pairs([(a, b, H_DIR), (b, a, V_DIR)], a.shape, 12, 10, precision=1)
+    for r, (x, y, d, ov) in zip(res, [(a, b, H_DIR, 12), (b, a, V_DIR, 10)]):
+        exp_int, exp_shift, det = oracle_pair(x, y, ov, d)
+        assert r["coarse"] == det["coarse"] and (r["dy"], r["dx"]) == exp_int
