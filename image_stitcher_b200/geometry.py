@@ -55,6 +55,8 @@ def strip_overlaps(tile_w: int, tile_h: int, x_positions: Sequence[float], y_pos
     ``round(|W - dx_px| * 1.05) // 2 * binning`` -- floor-divide first, then scale.
     """
     def extent(n_px: int, pos: Sequence[float]) -> int:
+        if len(pos) < 2:          # single row / column: no pair along this axis (the reference raises IndexError here)
+            return 0
         step_px = (pos[1] - pos[0]) * 1000 / pixel_size_um
         return round(abs(n_px - step_px) * 1.05) // 2 * pixel_binning
     return extent(tile_w, x_positions), extent(tile_h, y_positions)

@@ -191,3 +191,64 @@ def test_stitcher_class_and_sync_cli(tmp_path, capsys):
     assert stitcher_cli.main(["-i", root, "-r"]) == 0
     assert "Stitching completed" in capsys.readouterr().out
     assert stitcher_cli.main(["-i", str(tmp_path / "missing")]) == 1
+
+
+def _write_region(root, tiles):
+    synth.write_squid_layout(root, {"A1": tiles})
+
+
+def test_edge_cases_single_tile_single_row_and_ragged_grid(tmp_path):
+    """Degenerate grids: 1x1 (nothing to register), 1x3 (no vertical pair -- the reference raises IndexError at :603, here
+    the missing axis simply keeps its (0, 0) shift), and a ragged 2x2 grid whose centre-right tile is missing (the reference
+    warns and keeps (0, 0), :630-633).  Canvases are compared with the oracle on the same tiles."""
+    from oracle import stitch_ref as sr
+    # ---- 1 x 1
+    st, tiles, _ = synth.make_region(rows=1, cols=1, tile_h=96, tile_w=128, seed=91, jitter=0, use_registration=True)
+    root = str(tmp_path / "one")
+    _write_region(root, tiles)
+    s = _make(root, st)
+    try:
+        _prepare(s)
+        s.calculate_shifts(0, "A1")
+        assert tuple(s.h_shift) == (0, 0) and tuple(s.v_shift) == (0, 0)
+        out = s.stitch_region(0, "A1")
+        assert out.shape == (1, 1, 1, 96, 128) and np.array_equal(out[0, 0, 0], tiles[0].pixels)
+    finally:
+        s.cleanup()
+    # ---- 1 x 3 row with registration
+    st, tiles, truth = synth.make_region(rows=1, cols=3, tile_h=192, tile_w=256, seed=92, jitter=2, use_registration=True)
+    root = str(tmp_path / "row")
+    _write_region(root, tiles)
+    s = _make(root, st)
+    try:
+        _prepare(s)
+        s.calculate_shifts(0, "A1")
+        xs = sorted(set(t.x_mm for t in tiles))
+        lut = {t.x_mm: t.pixels for t in tiles}
+        ovx = geo_overlap(192, 256, xs, st.pixel_size_um)
+        assert tuple(s.h_shift) == sr.calculate_horizontal_shift(lut[xs[1]], lut[xs[2]], ovx) and tuple(s.v_shift) == (0, 0)
+        st.h_shift, st.v_shift = tuple(s.h_shift), (0, 0)
+        assert np.array_equal(s.stitch_region(0, "A1"), sr.stitch_region(st, tiles))
+    finally:
+        s.cleanup()
+    # ---- ragged 2 x 2: the tile right of the centre tile is missing
+    st, tiles, _ = synth.make_region(rows=2, cols=2, tile_h=128, tile_w=160, seed=93, jitter=1, use_registration=True)
+    xs, ys = sorted(set(t.x_mm for t in tiles)), sorted(set(t.y_mm for t in tiles))
+    ragged = [t for t in tiles if not (t.x_mm == xs[1] and t.y_mm == ys[0])]
+    root = str(tmp_path / "ragged")
+    _write_region(root, ragged)
+    s = _make(root, st)
+    try:
+        _prepare(s)
+        s.calculate_shifts(0, "A1")
+        assert tuple(s.h_shift) == (0, 0)                      # right neighbour of the centre tile is missing
+        st2 = sr.calculate_shifts(st, ragged)
+        assert tuple(s.v_shift) == tuple(st2.v_shift)
+        assert np.array_equal(s.stitch_region(0, "A1"), sr.stitch_region(st2, ragged))
+    finally:
+        s.cleanup()
+
+
+def geo_overlap(tile_h, tile_w, xs, px):
+    from image_stitcher_b200 import geometry as geo
+    return geo.strip_overlaps(tile_w, tile_h, xs, [0.0], px, 2)[0]
