@@ -110,21 +110,30 @@ def test_blend_modes_within_one_lsb(ctx, mode, fields):
     assert (diff != 0).mean() < 0.01           # disagreements only at exact .5 ties
 
 
-def test_chunked_layout_equals_rowmajor(ctx):
+@pytest.mark.parametrize("chunk,fields", [((128, 256), "none"), ((128, 256), "flat"), ((64, 384), "none"), ((128, 128), "flat+dark")])
+def test_chunked_layout_equals_rowmajor(ctx, chunk, fields):
+    """zarr-chunk-ordered output == row-major output, edge chunks zero padded.  Power-of-two chunk widths take the
+    rectangle-streaming kernel, 384 and dark-fields the TMA kernel: the two kernels check each other."""
     from image_stitcher_b200 import _ffi
     rng = np.random.default_rng(8)
-    th, tw, C, Z, Hc, Wc = 100, 120, 1, 2, 300, 411
+    th, tw, C, Z, Hc, Wc = 96, 120, 1, 2, 300, 411
     job = random_job(rng, 9, th, tw, C, Z, Hc, Wc)
     ctx.clear_fields()
+    if "flat" in fields:
+        ctx.set_flatfield(0, rng.uniform(0.6, 1.4, (th, tw)).astype(np.float32))
+    if "dark" in fields:
+        ctx.set_darkfield(0, rng.uniform(0, 300, (th, tw)).astype(np.float32))
     ref = np.empty((1, C, Z, Hc, Wc), np.uint16)
-    ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=ref)
-    ch, cw = 128, 256
+    ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=ref, apply_flatfield=fields != "none")
+    ch, cw = chunk
     ncy, ncx = -(-Hc // ch), -(-Wc // cw)
-    out = np.empty((C * Z, ncy, ncx, ch, cw), np.uint16)
-    ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=out, layout=_ffi.SB_LAYOUT_CHUNKED, chunk=(ch, cw))
+    out = np.full((C * Z, ncy, ncx, ch, cw), 3, np.uint16)
+    ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=out, layout=_ffi.SB_LAYOUT_CHUNKED, chunk=(ch, cw),
+                    apply_flatfield=fields != "none")
     full = out.transpose(0, 1, 3, 2, 4).reshape(C * Z, ncy * ch, ncx * cw)
     assert np.array_equal(full[:, :Hc, :Wc], ref.reshape(C * Z, Hc, Wc))
     assert not full[:, Hc:, :].any() and not full[:, :, Wc:].any()      # zarr-v2 edge chunks are zero padded
+    ctx.clear_fields()
 
 
 def test_empty_region_is_zero(ctx):
