@@ -66,17 +66,27 @@ __global__ void __launch_bounds__(256) tile_minmax_kernel(const uint16_t* const*
     unsigned lo = 0xffffu, hi = 0u;
     const int64_t nvec = ((reinterpret_cast<uintptr_t>(t) & 15) == 0) ? px / 8 : 0;
     const uint4* tv = reinterpret_cast<const uint4*>(t);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint4 v = __ldg(tv + i);
-        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    // packed running min / max (two uint16 per register); four independent 128-bit loads in flight per thread
+    unsigned lo2 = 0xffffffffu, hi2 = 0u;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        uint4 v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned mn2 = __vminu2(w[k], lo | (lo << 16));
-            const unsigned mx2 = __vmaxu2(w[k], hi | (hi << 16));
-            lo = min(mn2 & 0xffffu, mn2 >> 16);
-            hi = max(mx2 & 0xffffu, mx2 >> 16);
+        for (int u = 0; u < 4; ++u) v[u] = __ldcs(tv + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            lo2 = __vminu2(__vminu2(lo2, v[u].x), __vminu2(v[u].y, __vminu2(v[u].z, v[u].w)));
+            hi2 = __vmaxu2(__vmaxu2(hi2, v[u].x), __vmaxu2(v[u].y, __vmaxu2(v[u].z, v[u].w)));
         }
     }
+    for (; i < nvec; i += stride) {
+        const uint4 v = __ldcs(tv + i);
+        lo2 = __vminu2(__vminu2(lo2, v.x), __vminu2(v.y, __vminu2(v.z, v.w)));
+        hi2 = __vmaxu2(__vmaxu2(hi2, v.x), __vmaxu2(v.y, __vmaxu2(v.z, v.w)));
+    }
+    lo = min(lo2 & 0xffffu, lo2 >> 16);
+    hi = max(hi2 & 0xffffu, hi2 >> 16);
     for (int64_t i = nvec * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < px; i += (int64_t)gridDim.x * blockDim.x) {
         const unsigned v = t[i];
         lo = min(lo, v);
@@ -959,7 +969,7 @@ int prepare_tiles(sb_ctx* ctx, Lane* lane, const std::vector<const void*>& ptrs,
     SB_CUDA(ctx, cudaMemcpyAsync(lane->reg_meta.p, ts.dev.data(), (size_t)nt * sizeof(void*), cudaMemcpyHostToDevice, st));
     int2* d_mm = (int2*)((uint8_t*)lane->reg_meta.p + round_up64((size_t)nt * sizeof(void*), 256));
     minmax_init_kernel<<<(nt + 255) / 256, 256, 0, st>>>(d_mm, nt);
-    const int bpt = std::max(1, std::min(64, (ctx->sm_count * 8 + nt - 1) / nt));
+    const int bpt = std::max(1, std::min(64, (ctx->sm_count * 16 + nt - 1) / nt));
     tile_minmax_kernel<<<dim3(bpt, nt), 256, 0, st>>>((const uint16_t* const*)lane->reg_meta.p, (int64_t)H * W, d_mm);
     ctx->launches += 2;
     SB_CUDA(ctx, cudaGetLastError());
