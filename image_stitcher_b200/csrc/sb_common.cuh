@@ -50,6 +50,8 @@ struct Lane {
     cudaEvent_t aux_fork = nullptr, aux_join[3] = {nullptr, nullptr, nullptr};
     std::vector<int32_t> rect_pieces;   // cached rectangle decomposition of the rectangle-streaming paste kernel ...
     uint64_t rect_sig = 0;              // ... and the geometry signature it was computed for
+    std::vector<int32_t> blend_cells;   // cached cell decomposition of the blend modes (10 ints per cell) ...
+    uint64_t blend_sig = 0;             // ... and its geometry signature
     std::vector<int32_t> perm;      // cached block-row order of the paste kernel (fuse.cu) ...
     uint64_t perm_sig = 0;          // ... and the geometry signature it was computed for
 };
