@@ -137,3 +137,34 @@ def grid_pairs(n_rows: int, n_cols: int) -> List[Tuple[str, Tuple[int, int], Tup
             if r + 1 < n_rows:
                 out.append(("v", (r, c), (r + 1, c)))
     return out
+
+
+def solve_positions(n_tiles: int, tile_w: int, tile_h: int, pairs: Sequence[Tuple[str, int, int]],
+                    shifts: Sequence[Tuple[int, int]], weights: Optional[Sequence[float]] = None) -> List[Tuple[int, int]]:
+    """Global placement from pairwise shifts (extension; the reference applies ONE lattice to every tile).
+
+    ``pairs[k] = (kind, a, b)`` with kind 'h' (b is the right neighbour of a) or 'v' (b below a) and
+    ``shifts[k] = (dy, dx)`` exactly as ``calculate_horizontal_shift`` / ``calculate_vertical_shift`` return them, i.e.
+    the origin of b relative to a is ``(dy, tile_w + dx)`` for 'h' and ``(tile_h + dy, dx)`` for 'v'.  Solves the
+    least-squares system ``p_b - p_a = d_ab`` (tile 0 anchored, optional per-pair weights) and returns integer pixel
+    origins ``(x, y)`` shifted so that the minimum is 0.  With consistent pair shifts the solution is exact.
+    """
+    m = len(pairs)
+    if n_tiles == 0:
+        return []
+    A = np.zeros((m + 1, n_tiles), np.float64)
+    bx = np.zeros(m + 1, np.float64)
+    by = np.zeros(m + 1, np.float64)
+    for k, ((kind, a, b), (dy, dx)) in enumerate(zip(pairs, shifts)):
+        w = 1.0 if weights is None else float(weights[k])
+        A[k, a], A[k, b] = -w, w
+        if kind == "v":
+            bx[k], by[k] = w * dx, w * (tile_h + dy)
+        else:
+            bx[k], by[k] = w * (tile_w + dx), w * dy
+    A[m, 0] = 1.0                                   # anchor
+    x = np.linalg.lstsq(A, bx, rcond=None)[0]
+    y = np.linalg.lstsq(A, by, rcond=None)[0]
+    xi = np.rint(x - x.min()).astype(np.int64)
+    yi = np.rint(y - y.min()).astype(np.int64)
+    return [(int(a), int(b)) for a, b in zip(xi, yi)]

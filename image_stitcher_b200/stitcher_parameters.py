@@ -34,6 +34,8 @@ class StitchingParameters:
     blend_mode: str = "paste"             # 'paste' = reference crop-to-seam + overwrite
     upsample_factor: int = 10             # the reference hard-codes 10 (stitcher_process.py:684)
     registration_precision: str = "auto"
+    placement: str = "lattice"            # 'lattice' = the reference's single (h_shift, v_shift) model; 'global' = every
+                                          # adjacent pair of every region registered, least-squares tile positions
     device: int = 0
     rank: int = 0                         # multi-GPU: this worker stitches regions rank, rank + world, ...
     world: int = 1
@@ -52,6 +54,8 @@ class StitchingParameters:
             problems.append("Scan pattern must be either 'Unidirectional' or 'S-Pattern'")
         if self.use_registration and self.registration_z_level < 0:
             problems.append("Registration Z-level must be non-negative")
+        if self.placement not in ("lattice", "global"):
+            problems.append("placement must be 'lattice' or 'global'")
         if self.blend_mode not in _BLENDS:
             problems.append(f"blend_mode must be one of {_BLENDS}")
         if self.registration_precision not in _PRECISIONS:

@@ -69,6 +69,8 @@ class StitcherProcess(Process):
         self.blend_mode = getattr(params, "blend_mode", "paste")
         self.upsample_factor = int(getattr(params, "upsample_factor", 10))
         self.registration_precision = getattr(params, "registration_precision", "auto")
+        self.placement = getattr(params, "placement", "lattice")
+        self.tile_positions: Dict[tuple, Dict[tuple, tuple]] = {}     # (t, region) -> {(x_mm, y_mm): (x_px, y_px)}
         self.device = int(getattr(params, "device", 0))
         self.decode_threads = max(1, min(16, os.cpu_count() or 1))
         # multi-GPU: worker `rank` of `world` stitches regions rank, rank + world, ... on its own device.  Every worker
@@ -384,6 +386,32 @@ class StitcherProcess(Process):
                 self.h_shift_rev_odd = rev_odd
         print(f"Calculated Shifts - Horizontal: {self.h_shift}, Vertical: {self.v_shift}")
 
+    def register_region_global(self, t, region):
+        """Extension (``placement='global'``): register EVERY adjacent pair of this region in one GPU batch and solve
+        the tile origins by least squares (``geometry.solve_positions``).  The reference has neither per-pair
+        registration nor a global solve; its lattice model stays the default."""
+        if not self.registration_channel or self.registration_channel not in self.channel_names:
+            self.registration_channel = self.channel_names[0]
+        self.calculate_output_dimensions(int(t), region)
+        xs, ys = list(self.x_positions), list(self.y_positions)
+        ov_x, ov_y = geo.strip_overlaps(self.input_width, self.input_height, xs, ys, self.pixel_size_um, self.pixel_binning)
+        index = {(x, y): r * len(xs) + c for r, y in enumerate(ys) for c, x in enumerate(xs)}
+        tiles = {}
+        for (x, y) in index:
+            tiles[(x, y)] = self.get_tile(t, region, x, y, self.registration_channel, self.registration_z_level)
+        plan, job = [], []
+        for kind, (r0, c0), (r1, c1) in geo.grid_pairs(len(ys), len(xs)):
+            a, b = tiles[(xs[c0], ys[r0])], tiles[(xs[c1], ys[r1])]
+            if a is None or b is None:
+                continue
+            plan.append((kind, index[(xs[c0], ys[r0])], index[(xs[c1], ys[r1])]))
+            job.append((a, b, _ffi.SB_DIR_VERTICAL if kind == "v" else _ffi.SB_DIR_HORIZONTAL))
+        res = self._register(job, ov_x, ov_y) if job else []
+        pos = geo.solve_positions(len(index), self.input_width, self.input_height, plan, [(r["dy"], r["dx"]) for r in res],
+                                  weights=[max(float(r["peak"]), 1e-3) for r in res])
+        self.tile_positions[(int(t), region)] = {xy: pos[i] for xy, i in index.items()}
+        return self.tile_positions[(int(t), region)]
+
     # ------------------------------------------------------------------ fusion (reference :739-956)
     def apply_flatfield_correction(self, tile, channel_idx):
         """``(tile / flatfield).clip(0, max).astype(dtype)`` (:828-842) -- ``sb_flatfield_apply``."""
@@ -412,6 +440,11 @@ class StitcherProcess(Process):
             width, height = self.calculate_output_dimensions(timepoint, region)
             lattice = self._lattice()
             xs, ys = list(self.x_positions), list(self.y_positions)
+            solved = None
+            if self.use_registration and self.placement == "global":
+                solved = self.tile_positions.get((int(timepoint), region)) or self.register_region_global(timepoint, region)
+                width = max(p[0] for p in solved.values()) + self.input_width
+                height = max(p[1] for p in solved.values()) + self.input_height
             self.emit_status(f"Stitching... (Timepoint:{timepoint} Region:{region})")
             self.check_stop()
             job, keep = [], []
@@ -431,8 +464,11 @@ class StitcherProcess(Process):
                 if tile is None:
                     self.emit_status(f"Error Loading Image {info['filepath']}: {exc}")
                     continue
-                p = geo.place_tile(info["x"], info["y"], self.input_width, self.input_height, xs, ys,
-                                   self.pixel_size_um, lattice)
+                if solved is not None:
+                    p = geo.Placement(*solved[(info["x"], info["y"])])
+                else:
+                    p = geo.place_tile(info["x"], info["y"], self.input_width, self.input_height, xs, ys,
+                                       self.pixel_size_um, lattice)
                 for c, plane in self._tile_planes(tile, key[4]):
                     plane = np.ascontiguousarray(plane, dtype=self._pixel_np())
                     keep.append(plane)
@@ -501,7 +537,7 @@ class StitcherProcess(Process):
             last_path = ""
             if self.apply_flatfield and not self.flatfields:
                 self.get_flatfields()
-            if self.use_registration:
+            if self.use_registration and self.placement != "global":
                 self.calculate_shifts(self.timepoints[0], self.regions[0])
             from .shard import wells_for_rank
             my_regions = [self.regions[i] for i in wells_for_rank(len(self.regions), self.world, self.rank)]

@@ -38,6 +38,8 @@ def parse_args(argv=None) -> argparse.Namespace:
     p.add_argument("--params-json", help="JSON file with stitching parameters (overrides the other arguments)")
     # extensions (defaults = reference behaviour)
     p.add_argument("--blend-mode", choices=["paste", "linear", "feather"], default="paste")
+    p.add_argument("--placement", choices=["lattice", "global"], default="lattice",
+                   help="lattice = the reference's single shift pair; global = all pairs of every region + least squares")
     p.add_argument("--upsample-factor", type=int, default=10)
     p.add_argument("--registration-precision", choices=["auto", "float32", "float64"], default="auto")
     p.add_argument("--device", type=int, default=0, help="CUDA device index")
@@ -55,7 +57,7 @@ def create_params(args: argparse.Namespace) -> StitchingParameters:
         "registration_channel": args.registration_channel, "registration_z_level": args.registration_z_level,
         "scan_pattern": args.scan_pattern, "merge_timepoints": args.merge_timepoints,
         "merge_hcs_regions": args.merge_hcs_regions, "dynamic_registration": args.dynamic_registration,
-        "blend_mode": args.blend_mode, "upsample_factor": args.upsample_factor,
+        "blend_mode": args.blend_mode, "placement": args.placement, "upsample_factor": args.upsample_factor,
         "registration_precision": args.registration_precision, "device": args.device})
 
 

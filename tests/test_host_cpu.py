@@ -214,3 +214,20 @@ def test_multi_device_workers_split_regions_without_exchange(tmp_path):
     assert sorted(sum(got, [])) == sorted(regions) and got[1][:2] == ["A2", "A5"]
     p = StitchingParameters(input_folder=str(tmp_path), rank=1, world=3, device=1)
     assert StitchingParameters.from_dict(p.to_dict()).world == 3
+
+
+def test_solve_positions_recovers_per_tile_jitter():
+    """geometry.solve_positions: consistent pairwise shifts of a jittered (non-lattice) grid -> exact tile origins."""
+    rng = np.random.default_rng(0)
+    R, C, W, H = 3, 4, 256, 192
+    true = {(r, c): (c * 230 + int(rng.integers(-3, 4)), r * 172 + int(rng.integers(-3, 4))) for r in range(R) for c in range(C)}
+    pairs, shifts = [], []
+    for kind, (r0, c0), (r1, c1) in geo.grid_pairs(R, C):
+        a, b = true[(r0, c0)], true[(r1, c1)]
+        ddx, ddy = b[0] - a[0], b[1] - a[1]
+        pairs.append((kind, r0 * C + c0, r1 * C + c1))
+        shifts.append((ddy, ddx - W) if kind == "h" else (ddy - H, ddx))       # what calculate_*_shift returns
+    pos = geo.solve_positions(R * C, W, H, pairs, shifts)
+    mx, my = min(v[0] for v in true.values()), min(v[1] for v in true.values())
+    assert all(pos[r * C + c] == (true[(r, c)][0] - mx, true[(r, c)][1] - my) for r in range(R) for c in range(C))
+    assert geo.solve_positions(1, W, H, [], []) == [(0, 0)] and geo.solve_positions(0, W, H, [], []) == []

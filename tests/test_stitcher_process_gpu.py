@@ -252,3 +252,47 @@ def test_edge_cases_single_tile_single_row_and_ragged_grid(tmp_path):
 def geo_overlap(tile_h, tile_w, xs, px):
     from image_stitcher_b200 import geometry as geo
     return geo.strip_overlaps(tile_w, tile_h, xs, [0.0], px, 2)[0]
+
+
+def test_global_placement_recovers_per_tile_jitter(tmp_path):
+    """Extension ``placement='global'``: tiles cut from one noise-free world at lattice + independent per-tile jitter
+    (which the reference's single-lattice model cannot express).  All adjacent pairs are registered on the GPU and the
+    least-squares origins recover the true ones (within one pixel: a single pair may round the other way); the fused
+    canvas is exactly the paste of the tiles at the solved origins."""
+    from oracle import blend_ref
+    from oracle.stitch_ref import TileRec
+    rng = np.random.default_rng(77)
+    R, C, H, W = 3, 3, 512, 512
+    step_x, step_y, J = 460, 460, 2
+    world = synth.make_world(R * step_y + H + 40, C * step_x + W + 40, rng).astype(np.float32)
+    world = np.clip(world, 0, 65535).astype(np.uint16)
+    px = synth.pixel_size_um()
+    tiles, true = [], {}
+    for r in range(R):
+        for c in range(C):
+            x = 10 + c * step_x + int(rng.integers(-J, J + 1))
+            y = 10 + r * step_y + int(rng.integers(-J, J + 1))
+            true[(r, c)] = (x, y)
+            fov = r * C + c
+            tiles.append(TileRec(x_mm=10.0 + c * step_x * px / 1000.0, y_mm=20.0 + r * step_y * px / 1000.0, z_level=0,
+                                 channel="Fluorescence 488 nm Ex", pixels=world[y:y + H, x:x + W].copy(), fov=fov,
+                                 name=f"A1_{fov}_0_Fluorescence_488_nm_Ex.tiff"))
+    tiles.sort(key=lambda t: t.name)
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    from image_stitcher_b200.stitcher_process import StitcherProcess
+    s = StitcherProcess(StitchingParameters(input_folder=root, use_registration=True, placement="global"),
+                        mp.Queue(), mp.Queue(), mp.Queue(), mp.Event())
+    try:
+        _prepare(s)
+        pos = s.register_region_global(0, "A1")
+        xs, ys = list(s.x_positions), list(s.y_positions)
+        mx, my = min(v[0] for v in true.values()), min(v[1] for v in true.values())
+        err = [max(abs(pos[(xs[c], ys[r])][0] - (true[(r, c)][0] - mx)), abs(pos[(xs[c], ys[r])][1] - (true[(r, c)][1] - my)))
+               for r in range(R) for c in range(C)]
+        assert max(err) <= 1 and sum(e == 0 for e in err) >= 6, err
+        out = s.stitch_region(0, "A1")
+        job = [(t.pixels, *pos[(t.x_mm, t.y_mm)], 0, 0, 0, 0, 0, 0) for t in tiles]      # paste order = sorted names
+        assert np.array_equal(out, blend_ref.fuse_paste(job, (1, 1, out.shape[3], out.shape[4])))
+    finally:
+        s.cleanup()
