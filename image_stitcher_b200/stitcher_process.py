@@ -432,8 +432,24 @@ class StitcherProcess(Process):
             return [(self.monochrome_channels.index(channel), tile[0])]
         raise ValueError(f"Unexpected tile shape: {tile.shape}")
 
-    def stitch_region(self, timepoint, region):
-        """One region -> ``(1, C, Z, Hc, Wc)`` NumPy canvas, ONE ``sb_fuse_region`` call (:883-956)."""
+    def _decode_region(self, timepoint, region):
+        """Decode every tile of a region on a thread pool (cv2 releases the GIL).  Returns ``[(key, info, tile | None,
+        exc)]`` in dict order -- the sorted-file-name paste order of the reference (:283-288, :908)."""
+        from concurrent.futures import ThreadPoolExecutor
+        data = self.get_region_data(int(timepoint), region)
+
+        def _load(item):
+            key, info = item
+            try:
+                return key, info, read_image(info["filepath"]), None
+            except Exception as exc:                       # the reference reports and skips (:912-916)
+                return key, info, None, exc
+        with ThreadPoolExecutor(max_workers=self.decode_threads) as pool:
+            return list(pool.map(_load, data.items()))
+
+    def stitch_region(self, timepoint, region, loaded=None):
+        """One region -> ``(1, C, Z, Hc, Wc)`` NumPy canvas, ONE ``sb_fuse_region`` call (:883-956).  ``loaded`` takes the
+        result of an earlier ``_decode_region`` (``run`` decodes the next region while this one is fused and saved)."""
         start = time.time()
         try:
             data = self.get_region_data(int(timepoint), region)
@@ -448,18 +464,8 @@ class StitcherProcess(Process):
             self.emit_status(f"Stitching... (Timepoint:{timepoint} Region:{region})")
             self.check_stop()
             job, keep = [], []
-            # decode the tiles on a thread pool (cv2 releases the GIL); results are consumed in dict order, which is
-            # the sorted-file-name paste order of the reference (:283-288, :908)
-            from concurrent.futures import ThreadPoolExecutor
-
-            def _load(item):
-                key, info = item
-                try:
-                    return key, info, read_image(info["filepath"]), None
-                except Exception as exc:                   # the reference reports and skips (:912-916)
-                    return key, info, None, exc
-            with ThreadPoolExecutor(max_workers=self.decode_threads) as pool:
-                loaded = list(pool.map(_load, data.items()))
+            if loaded is None:
+                loaded = self._decode_region(timepoint, region)
             for key, info, tile, exc in loaded:
                 if tile is None:
                     self.emit_status(f"Error Loading Image {info['filepath']}: {exc}")
@@ -515,13 +521,13 @@ class StitcherProcess(Process):
             self.place_single_channel_tile(stitched_region, plane, x_pixel, y_pixel, z_level, c, 0)
 
     # ------------------------------------------------------------------ output
-    def save_region_ome_zarr(self, timepoint, region, stitched_region):
+    def save_region_ome_zarr(self, timepoint, region, stitched_region, num_levels=None):
         from .ome_zarr_writer import write_ome_zarr
         path = self.per_timepoint_region_output_template.format(timepoint=timepoint, region=region)
         dz = self.acquisition_params.get("dz(um)", 1.0) if self.acquisition_params else 1.0
         write_ome_zarr(path, np.asarray(stitched_region), pixel_size_um=self.pixel_size_um, dz_um=dz,
                        channel_names=self.monochrome_channels, channel_colors=self.monochrome_colors,
-                       num_levels=self.num_pyramid_levels, chunks=self.chunks)
+                       num_levels=self.num_pyramid_levels if num_levels is None else num_levels, chunks=self.chunks)
         return path
 
     def run(self):
@@ -539,19 +545,32 @@ class StitcherProcess(Process):
                 self.get_flatfields()
             if self.use_registration and self.placement != "global":
                 self.calculate_shifts(self.timepoints[0], self.regions[0])
+            from concurrent.futures import ThreadPoolExecutor
             from .shard import wells_for_rank
             my_regions = [self.regions[i] for i in wells_for_rank(len(self.regions), self.world, self.rank)]
+            if not self.output_format.endswith(".zarr"):
+                raise RuntimeError("OME-TIFF output relies on the reference's third-party writers "
+                                   "(out of scope, SURVEY.md section 2); use .ome.zarr")
+            work = [(t, r) for t in self.timepoints for r in my_regions]
             for timepoint in self.timepoints:
-                self.check_stop()
                 os.makedirs(os.path.join(self.output_folder, f"{timepoint}_stitched"), exist_ok=True)
-                for region in my_regions:
+            # three stages in flight: decode of region i+1 (thread pool), GPU fusion of region i (this thread),
+            # OME-Zarr write of region i-1 (writer thread)
+            with ThreadPoolExecutor(max_workers=1) as prefetch, ThreadPoolExecutor(max_workers=1) as writer:
+                nxt = prefetch.submit(self._decode_region, *work[0]) if work else None
+                pending_write = None
+                for i, (timepoint, region) in enumerate(work):
                     self.check_stop()
-                    stitched = self.stitch_region(timepoint, region)
-                    if not self.output_format.endswith(".zarr"):
-                        raise RuntimeError("OME-TIFF output relies on the reference's third-party writers "
-                                           "(out of scope, SURVEY.md section 2); use .ome.zarr")
+                    loaded = nxt.result()
+                    nxt = prefetch.submit(self._decode_region, *work[i + 1]) if i + 1 < len(work) else None
+                    stitched = self.stitch_region(timepoint, region, loaded=loaded)
+                    if pending_write is not None:
+                        last_path = pending_write.result()
                     self.emit_status(f"Saving... (Timepoint:{timepoint} Region:{region})", is_saving=True)
-                    last_path = self.save_region_ome_zarr(timepoint, region, stitched)
+                    pending_write = writer.submit(self.save_region_ome_zarr, timepoint, region, stitched,
+                                                  self.num_pyramid_levels)      # per-region value, fixed before the next region
+                if pending_write is not None:
+                    last_path = pending_write.result()
             self.check_stop()
             self.emit_complete(last_path, self.dtype)
             print(f"Processing complete. Total time: {time.time() - stime:.1f}s")

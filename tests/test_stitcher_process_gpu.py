@@ -296,3 +296,27 @@ def test_global_placement_recovers_per_tile_jitter(tmp_path):
         assert np.array_equal(out, blend_ref.fuse_paste(job, (1, 1, out.shape[3], out.shape[4])))
     finally:
         s.cleanup()
+
+
+def test_run_pipelines_several_regions_and_timepoints(tmp_path):
+    """``run()`` over 3 regions x 2 timepoints: decode of the next region, fusion of the current one and the OME-Zarr
+    write of the previous one overlap; every output equals the oracle's canvas of that (timepoint, region)."""
+    import shutil
+    from oracle import stitch_ref as sr
+    root = str(tmp_path / "acq")
+    regions = {}
+    for k, name in enumerate(["A1", "A2", "B1"]):
+        st, tiles, _ = synth.make_region(rows=2, cols=2, tile_h=128, tile_w=160, seed=100 + k, jitter=0, region=name)
+        regions[name] = (st, tiles)
+    synth.write_squid_layout(root, {n: t for n, (_, t) in regions.items()}, timepoint=0)
+    shutil.copytree(os.path.join(root, "0"), os.path.join(root, "1"))
+    s = _make(root, regions["A1"][0])
+    s.run()
+    kind, (path, dtype) = s.complete_queue.get(timeout=5)
+    assert kind == "complete" and path.endswith(os.path.join("1_stitched", "B1_stitched.ome.zarr"))
+    for t in (0, 1):
+        for name, (st, tiles) in regions.items():
+            p = os.path.join(s.output_folder, f"{t}_stitched", f"{name}_stitched.ome.zarr")
+            assert np.array_equal(ozw.read_ome_zarr_level(p, 0), sr.stitch_region(st, tiles)), (t, name)
+    saving = [m[1][0] for m in _drain(s.status_queue) if m[0] == "status" and "Saving" in m[1][0]]
+    assert len(saving) == 6
