@@ -411,7 +411,7 @@ def run_b200(args, rank, world, local_rank):
         "registration_f64_redo_pairs": int(sum(r["precision"] == 1 for r in last_reg)),
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "paste_rect_kernel" if args.blend == "paste" else "fuse_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "roofline": {"kernel": "paste_rect_kernel" if args.blend == "paste" else "paste_rect_kernel<ROUND> + blend_cells_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": "profiles/fusion_traffic.json (ncu --set full, per launch)" if traffic else None,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fuse_launch_ms,

@@ -320,3 +320,23 @@ def test_run_pipelines_several_regions_and_timepoints(tmp_path):
             assert np.array_equal(ozw.read_ome_zarr_level(p, 0), sr.stitch_region(st, tiles)), (t, name)
     saving = [m[1][0] for m in _drain(s.status_queue) if m[0] == "status" and "Saving" in m[1][0]]
     assert len(saving) == 6
+
+
+def test_process_cli_worker_process_end_to_end(tmp_path):
+    """``python -m image_stitcher_b200.stitcher_process_cli``: the parent never touches CUDA, the forked worker creates
+    the context lazily, reports over the three queues and writes the OME-Zarr (the reference's CLI flow, :187-232)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    g, st, tiles, kw = load_golden("reg_2x2_mono")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    r = subprocess.run([sys.executable, "-m", "image_stitcher_b200.stitcher_process_cli", "-i", root, "-r", "--devices", "0"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Stitching completed. Output saved to:" in r.stdout and "Status: Calculating Registration Shifts..." in r.stdout
+    path = r.stdout.split("Output saved to:")[1].split()[0]
+    assert np.array_equal(ozw.read_ome_zarr_level(path, 0), g["canvas"])
+    bad = subprocess.run([sys.executable, "-m", "image_stitcher_b200.stitcher_process_cli", "-i", str(tmp_path / "missing")],
+                         cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert bad.returncode != 0
