@@ -723,7 +723,7 @@ int pick_lines(int n, size_t elem, int lb, size_t budget) {
 // `h_out` (pinned for asynchronous jobs).  With do_sync the call returns when they have arrived.
 template <typename T>
 int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const GroupGeom& g, int tile_w,
-              const int2* d_mm, int uf, int maxval, PeakOut* h_out, bool do_sync) {
+              const int2* d_mm, int uf, int maxval, PeakOut* h_out, bool do_sync, PairDesc* pinned_pairs = nullptr) {
     cudaStream_t st = lane->stream;
     using T2 = typename Vec2<T>::type;
     const int n = (int)pairs.size();
@@ -830,7 +830,14 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     PairDesc* d_pairs = (PairDesc*)(w + o_pairs);
     int* d_nz = (int*)(w + o_nz);
     SB_CUDA(ctx, cudaMemsetAsync(d_nz, 0, (size_t)n * sizeof(int), st));
-    SB_CUDA(ctx, cudaMemcpyAsync(d_pairs, pairs.data(), (size_t)n * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+    // Descriptors go up from PINNED memory when the caller provides it: a copy from pageable memory synchronises the
+    // stream first, i.e. the host would wait for everything already enqueued on this lane (uploads, earlier groups).
+    const PairDesc* h_pairs = pairs.data();
+    if (pinned_pairs) {
+        memcpy(pinned_pairs, pairs.data(), (size_t)n * sizeof(PairDesc));
+        h_pairs = pinned_pairs;
+    }
+    SB_CUDA(ctx, cudaMemcpyAsync(d_pairs, h_pairs, (size_t)n * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
 
     auto k1 = lbx == 4 ? rows_fwd_kernel<T, 4> : rows_fwd_kernel<T, 1>;
     auto k3 = lbx == 4 ? rows_inv_argmax_kernel<T, 4> : rows_inv_argmax_kernel<T, 1>;
@@ -943,7 +950,7 @@ struct TileSet {
 };
 
 int prepare_tiles(sb_ctx* ctx, Lane* lane, const std::vector<const void*>& ptrs, int H, int W, int mem, TileSet& ts,
-                  int2** d_mm_out, int2* h_mm) {
+                  int2** d_mm_out, int2* h_mm, const uint16_t** pinned_table = nullptr) {
     cudaStream_t st = lane->stream;
     for (const void* p : ptrs) {
         if (!p) return sb_fail(ctx, SB_ERR_INVALID, "NULL tile pointer");
@@ -966,7 +973,12 @@ int prepare_tiles(sb_ctx* ctx, Lane* lane, const std::vector<const void*>& ptrs,
     const size_t meta = round_up64((size_t)nt * sizeof(void*), 256) + (size_t)nt * sizeof(int2);
     int rc = sb_reserve(ctx, lane->reg_meta, meta);
     if (rc) return rc;
-    SB_CUDA(ctx, cudaMemcpyAsync(lane->reg_meta.p, ts.dev.data(), (size_t)nt * sizeof(void*), cudaMemcpyHostToDevice, st));
+    const uint16_t* const* h_table = ts.dev.data();
+    if (pinned_table) {                      // see run_group: pageable sources would stall the host on the lane's stream
+        memcpy(pinned_table, ts.dev.data(), (size_t)nt * sizeof(void*));
+        h_table = pinned_table;
+    }
+    SB_CUDA(ctx, cudaMemcpyAsync(lane->reg_meta.p, h_table, (size_t)nt * sizeof(void*), cudaMemcpyHostToDevice, st));
     int2* d_mm = (int2*)((uint8_t*)lane->reg_meta.p + round_up64((size_t)nt * sizeof(void*), 256));
     minmax_init_kernel<<<(nt + 255) / 256, 256, 0, st>>>(d_mm, nt);
     const int bpt = std::max(1, std::min(64, (ctx->sm_count * 16 + nt - 1) / nt));
@@ -1014,13 +1026,17 @@ static int reg_enqueue(sb_ctx* ctx, Lane* lane, const sb_register_job* job, sb_p
         ptrs.push_back(job->pairs[i].ref);
         ptrs.push_back(job->pairs[i].mov);
     }
-    // pinned result block of the lane: [min/max of every unique tile | PeakOut of every pair]
+    // pinned block of the lane: [min/max of every unique tile | PeakOut of every pair | tile pointer table | pair descriptors]
     const size_t mm_bytes = round_up64((size_t)2 * n * sizeof(int2), 64);
-    int rc = sb_reserve_pinned(ctx, &lane->reg_host, &lane->reg_host_cap, mm_bytes + (size_t)n * sizeof(PeakOut));
+    const size_t pk_bytes = round_up64((size_t)n * sizeof(PeakOut), 64);
+    const size_t tb_bytes = round_up64((size_t)2 * n * sizeof(void*), 64);
+    int rc = sb_reserve_pinned(ctx, &lane->reg_host, &lane->reg_host_cap, mm_bytes + pk_bytes + tb_bytes + (size_t)n * sizeof(PairDesc));
     if (rc) return rc;
     pr.h_mm = reinterpret_cast<int2*>(lane->reg_host);
     pr.h_peaks = reinterpret_cast<PeakOut*>((uint8_t*)lane->reg_host + mm_bytes);
-    rc = prepare_tiles(ctx, lane, ptrs, H, W, job->mem, pr.ts, &pr.d_mm, pr.h_mm);
+    const uint16_t** pinned_table = reinterpret_cast<const uint16_t**>((uint8_t*)lane->reg_host + mm_bytes + pk_bytes);
+    PairDesc* pinned_pairs = reinterpret_cast<PairDesc*>((uint8_t*)lane->reg_host + mm_bytes + pk_bytes + tb_bytes);
+    rc = prepare_tiles(ctx, lane, ptrs, H, W, job->mem, pr.ts, &pr.d_mm, pr.h_mm, pinned_table);
     if (rc) return rc;
 
     size_t first = 0;
@@ -1056,8 +1072,10 @@ static int reg_enqueue(sb_ctx* ctx, Lane* lane, const sb_register_job* job, sb_p
         grp.first = first;
         first += grp.ids.size();
         rc = job->precision == SB_PREC_F64
-                 ? run_group<double>(ctx, lane, grp.pd, g, W, pr.d_mm, job->upsample_factor, maxval, pr.h_peaks + grp.first, false)
-                 : run_group<float>(ctx, lane, grp.pd, g, W, pr.d_mm, job->upsample_factor, maxval, pr.h_peaks + grp.first, false);
+                 ? run_group<double>(ctx, lane, grp.pd, g, W, pr.d_mm, job->upsample_factor, maxval, pr.h_peaks + grp.first, false,
+                                     pinned_pairs + grp.first)
+                 : run_group<float>(ctx, lane, grp.pd, g, W, pr.d_mm, job->upsample_factor, maxval, pr.h_peaks + grp.first, false,
+                                    pinned_pairs + grp.first);
         if (rc) return rc;
         pr.groups.push_back(std::move(grp));
     }
