@@ -305,7 +305,7 @@ __device__ __forceinline__ float2 fx2_unpack(unsigned long long v) {
 }
 
 #ifndef SB_GEMM_LT
-#define SB_GEMM_LT 4          // lines per thread of the GEMM tile (4 or 2): 4 q x LT lines complex accumulators for Ce and So
+#define SB_GEMM_LT 2          // lines per thread of the GEMM tile (4 or 2): 4 q x LT lines complex accumulators for Ce and So
 #endif
 __device__ __forceinline__ void pass_odd_gemm(float2* __restrict__ a, float2* __restrict__ b, const float2* __restrict__ tw,
                                               const float* __restrict__ ctab, int N, int Ns, int R, int nlines, bool inverse) {

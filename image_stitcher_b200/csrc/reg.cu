@@ -27,7 +27,7 @@
 #include <map>
 
 #ifndef SB_REG_CTAS
-#define SB_REG_CTAS 2        // resident blocks per SM the FFT kernels are sized for (registers and shared memory)
+#define SB_REG_CTAS 3        // resident blocks per SM the FFT kernels are sized for (registers and shared memory)
 #endif
 
 namespace {
