@@ -10,7 +10,6 @@ build() { # name, defines...
   echo built $name: $(grep -A2 "rows_fwd_kernelIfLi4" /tmp/err_$name.txt | grep -E "spill|Used" | tr '\n' ' ' | cut -c1-200)
 }
 rm -f $L/var_*.so
-build c3l2 -DSB_REG_CTAS=3 -DSB_GEMM_LT=2 &
-build c3l4 -DSB_REG_CTAS=3 -DSB_GEMM_LT=4 &
-build c2l2 -DSB_REG_CTAS=2 -DSB_GEMM_LT=2 &
+build c4l2 -DSB_REG_CTAS=4 -DSB_GEMM_LT=2 &
+build c2l4 -DSB_REG_CTAS=2 -DSB_GEMM_LT=4 &
 wait
