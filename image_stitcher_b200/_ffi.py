@@ -30,6 +30,7 @@ EXPORTS = [
     "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_memcpy_async", "sb_set_flatfield", "sb_set_darkfield", "sb_clear_fields",
     "sb_flatfield_apply", "sb_fuse_region", "sb_sync", "sb_lane_mark", "sb_lane_wait_mark", "sb_set_lane_stream", "sb_canvas_pitch",
     "sb_chunked_plane_elems", "sb_register_pairs", "sb_register_pairs_async", "sb_normalize",
+    "sb_pyramid_elems", "sb_pyramid",
 ]
 
 
@@ -115,6 +116,9 @@ def load_library(path: Optional[str] = None):
     lib.sb_register_pairs.argtypes = [vp, C.POINTER(SbRegisterJob), C.POINTER(SbPairResult)]
     lib.sb_register_pairs_async.argtypes = [vp, C.POINTER(SbRegisterJob), C.POINTER(SbPairResult)]
     lib.sb_normalize.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32]
+    lib.sb_pyramid_elems.argtypes = [i32, i32, i32, i32]
+    lib.sb_pyramid_elems.restype = i64
+    lib.sb_pyramid.argtypes = [vp, vp, i32, i32, i32, i32, i64, i32, i32, vp, i32, i32]
     if path == LIB_PATH:
         _lib = lib
     return lib
@@ -337,6 +341,47 @@ class Context:
         self._check(self.lib.sb_normalize(self.handle, _ptr(t3), _ptr(out), t3.shape[0], t3.shape[1], t3.shape[2],
                                           _pixel_dtype(t3), SB_MEM_HOST), "sb_normalize")
         return out.reshape(tiles.shape)
+
+    @staticmethod
+    def pyramid_shapes(canvas_shape, n_levels: int):
+        """``(planes, h_l, w_l)`` of levels ``1 .. n_levels - 1`` (``[..., ::2, ::2]`` per level)."""
+        planes, h, w = int(np.prod(canvas_shape[:-2], dtype=np.int64)), int(canvas_shape[-2]), int(canvas_shape[-1])
+        shapes = []
+        for _ in range(1, max(1, int(n_levels))):
+            h, w = (h + 1) // 2, (w + 1) // 2
+            shapes.append((planes, h, w))
+        return shapes
+
+    def pyramid(self, canvas_shape, n_levels: int, *, src=None, src_mem=SB_MEM_HOST, src_row_pitch=0, dtype=None,
+                out=None, out_mem=SB_MEM_HOST, lane=-1):
+        """Nearest-neighbour x2 levels ``1 .. n_levels - 1`` of a ``(..., H, W)`` canvas (``sb_pyramid``).
+
+        ``src=None`` takes the canvas the lane's last row-major ``fuse_region`` left on the device (no upload).
+        Returns the list of level arrays, each shaped ``canvas_shape[:-2] + (h_l, w_l)`` -- views into ``out``
+        (allocated here when ``None``; host output only)."""
+        shapes = self.pyramid_shapes(canvas_shape, n_levels)
+        if not shapes:
+            return []
+        planes, h, w = shapes[0][0], int(canvas_shape[-2]), int(canvas_shape[-1])
+        if dtype is None:
+            dtype = _pixel_dtype(src if src is not None else out)
+        np_dt = np.uint8 if dtype == SB_U8 else np.uint16
+        total = sum(p * a * b for p, a, b in shapes)
+        if out is None:
+            if out_mem != SB_MEM_HOST:
+                raise ValueError("device output needs an explicit `out` address")
+            out = np.empty(total, dtype=np_dt)
+        self._check(self.lib.sb_pyramid(self.handle, _ptr(src) if src is not None else None, src_mem, planes, h, w,
+                                        int(src_row_pitch), int(dtype), int(n_levels), _ptr(out), out_mem, lane),
+                    "sb_pyramid")
+        if out_mem != SB_MEM_HOST or not isinstance(out, np.ndarray):
+            return out
+        levels, off = [], 0
+        flat = out.reshape(-1)
+        for p, a, b in shapes:
+            levels.append(flat[off:off + p * a * b].reshape(tuple(canvas_shape[:-2]) + (a, b)))
+            off += p * a * b
+        return levels
 
 
 class PendingRegistration:

@@ -120,7 +120,7 @@ void sb_destroy(sb_ctx* ctx) {
         Lane& l = ctx->lanes[i];
         sb_register_discard(ctx, i);
         for (DevBuf* b : {&l.tiles, &l.canvas, &l.meta, &l.work, &l.reg_tiles, &l.reg_work, &l.reg_meta, &l.u8_stage, &l.u8_tiles,
-                          &l.u8_canvas16, &l.u8_canvas8, &l.u8_reg_stage, &l.u8_reg_tiles})
+                          &l.u8_canvas16, &l.u8_canvas8, &l.u8_reg_stage, &l.u8_reg_tiles, &l.pyr_src, &l.pyr_out})
             if (b->p) cudaFree(b->p);
         if (l.meta_host) cudaFreeHost(l.meta_host);
         if (l.reg_host) cudaFreeHost(l.reg_host);
@@ -264,8 +264,37 @@ int64_t sb_chunked_plane_elems(int32_t height, int32_t width, int32_t chunk_h, i
 int sb_fuse_region(sb_ctx* ctx, const sb_fuse_job* job, int lane) {
     if (!ctx) return SB_ERR_INVALID;
     if (lane >= SB_NUM_LANES) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
-    if (job && job->dtype == SB_U8) return sb_fuse_region_u8(ctx, job, lane);
-    return sb_fuse_region_impl(ctx, job, lane);
+    Lane* l = sb_lane(ctx, lane < 0 ? 0 : lane);
+    l->resident = ResidentCanvas();
+    const bool u8 = job && job->dtype == SB_U8;
+    const int rc = u8 ? sb_fuse_region_u8(ctx, job, lane) : sb_fuse_region_impl(ctx, job, lane);
+    if (rc == SB_OK && job->out_layout == SB_LAYOUT_ROWMAJOR) {
+        // remember where the canvas lives on the device: sb_pyramid(src == NULL) builds the multiscale levels from it
+        ResidentCanvas& r = l->resident;
+        if (job->out_mem == SB_MEM_DEVICE) {
+            r.p = job->out;
+            r.pitch = job->out_row_pitch ? job->out_row_pitch : sb_canvas_pitch(job->width);
+        } else {
+            r.p = u8 ? l->u8_canvas8.p : l->canvas.p;
+            r.pitch = sb_canvas_pitch(job->width);
+        }
+        r.planes = job->num_c * job->num_z;
+        r.h = job->height;
+        r.w = job->width;
+        r.dtype = job->dtype;
+    }
+    return rc;
+}
+
+int64_t sb_pyramid_elems(int32_t n_planes, int32_t height, int32_t width, int32_t n_levels) {
+    if (n_planes <= 0 || height <= 0 || width <= 0 || n_levels < 1) return -1;
+    return sb_pyramid_elems_impl(n_planes, height, width, n_levels);
+}
+
+int sb_pyramid(sb_ctx* ctx, const void* src, int src_mem, int32_t n_planes, int32_t height, int32_t width,
+               int64_t src_row_pitch, int dtype, int32_t n_levels, void* out, int out_mem, int lane) {
+    if (!ctx) return SB_ERR_INVALID;
+    return sb_pyramid_impl(ctx, src, src_mem, n_planes, height, width, src_row_pitch, dtype, n_levels, out, out_mem, lane);
 }
 
 int sb_sync(sb_ctx* ctx, int lane) {

@@ -32,6 +32,12 @@ struct FieldPool {            // flat- or dark-fields of all channels, one conti
     int slot(int c) const { return (c >= 0 && c < (int)slot_of_channel.size()) ? slot_of_channel[c] : -1; }
 };
 
+struct ResidentCanvas {       // the row-major canvas the lane's last sb_fuse_region left on the device (sb_pyramid, src == NULL)
+    const void* p = nullptr;
+    int64_t pitch = 0;        // elements per row
+    int planes = 0, h = 0, w = 0, dtype = 0;
+};
+
 struct Lane {
     cudaStream_t own = nullptr;
     cudaStream_t stream = nullptr;
@@ -42,6 +48,8 @@ struct Lane {
     cudaEvent_t meta_free = nullptr; // the previous job's metadata H2D has been consumed
     cudaEvent_t mark = nullptr;      // sb_lane_mark / sb_lane_wait_mark
     bool marked = false;
+    DevBuf pyr_src, pyr_out;        // sb_pyramid: uploaded level 0 (host sources only) and the levels before their download
+    ResidentCanvas resident;
     DevBuf reg_tiles, reg_work, reg_meta;   // registration workspace of this lane (grown on demand)
     void* reg_host = nullptr;       // pinned block the registration results are copied into
     size_t reg_host_cap = 0;
@@ -105,6 +113,10 @@ int sb_fuse_region_u8(sb_ctx* ctx, const sb_fuse_job* job, int lane);
 int sb_register_pairs_u8(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out, bool async);
 int sb_flatfield_apply_u8(sb_ctx* ctx, int channel, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int mem);
 int sb_normalize_u8(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int mem);
+// pyramid.cu
+int64_t sb_pyramid_elems_impl(int64_t n_planes, int height, int width, int n_levels);
+int sb_pyramid_impl(sb_ctx* ctx, const void* src, int src_mem, int n_planes, int height, int width, int64_t src_row_pitch,
+                    int dtype, int n_levels, void* out, int out_mem, int lane);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------- device-side PTX wrappers

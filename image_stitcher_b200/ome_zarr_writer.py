@@ -111,8 +111,10 @@ def _group_attrs(name, n_levels, pixel_size_um, dz_um, channel_names, channel_co
 
 def write_ome_zarr(path: str, data: np.ndarray, *, pixel_size_um: float, dz_um: float = 1.0,
                    channel_names: Sequence[str], channel_colors: Sequence[int], num_levels: int = 1,
-                   chunks=(1, 1, 1, 2048, 2048), compressor: Optional[str] = None, name: Optional[str] = None) -> str:
-    """Write a (1, C, Z, H, W) canvas as a multiscale OME-Zarr group; returns ``path``."""
+                   chunks=(1, 1, 1, 2048, 2048), compressor: Optional[str] = None, name: Optional[str] = None,
+                   levels: Optional[Sequence[np.ndarray]] = None) -> str:
+    """Write a (1, C, Z, H, W) canvas as a multiscale OME-Zarr group; returns ``path``.  ``levels`` takes levels
+    ``1 ..`` already made on the GPU (``sb_pyramid``); missing ones are sliced on the host."""
     if data.ndim != 5:
         raise ValueError(f"expected a 5-D TCZYX array, got shape {data.shape}")
     if compressor not in (None, "zlib"):
@@ -123,7 +125,10 @@ def write_ome_zarr(path: str, data: np.ndarray, *, pixel_size_um: float, dz_um: 
     n_written = 0
     for l in range(max(1, int(num_levels))):
         if l > 0:
-            level = level[..., ::2, ::2]                       # nearest-neighbour x2 (Scaler.nearest)
+            if levels is not None and l - 1 < len(levels):
+                level = levels[l - 1]
+            else:
+                level = level[..., ::2, ::2]                   # nearest-neighbour x2 (Scaler.nearest)
             if level.shape[-1] < 1 or level.shape[-2] < 1:
                 break
         _write_level(os.path.join(path, str(l)), level, chunks, compressor)

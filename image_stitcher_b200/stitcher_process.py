@@ -77,6 +77,7 @@ class StitcherProcess(Process):
         # registers the same first region itself (2-3 pairs), so all of them hold the same lattice without any exchange.
         self.rank, self.world = int(getattr(params, "rank", 0)), max(1, int(getattr(params, "world", 1)))
         self._ctx: Optional[_ffi.Context] = None
+        self._pyramids = {}                               # (timepoint, region) -> (n_levels, GPU-made levels 1..)
         self._flat_dirty = True
         self.init_stitching_parameters()
 
@@ -489,6 +490,10 @@ class StitcherProcess(Process):
                 job = [t[:5] + (0, 0, 0, 0) for t in job]
             self.ctx.fuse_region(job, (self.input_height, self.input_width), (self.num_c, self.num_z, height, width),
                                  out=out, apply_flatfield=self.apply_flatfield, blend=blend, blend_ov=ov)
+            if self.num_pyramid_levels > 1 and str(self.output_format).endswith(".zarr"):
+                # multiscale levels from the canvas while it is still on the device (Scaler.nearest, :1061-1062)
+                self._pyramids[(int(timepoint), region)] = (self.num_pyramid_levels, self.ctx.pyramid(
+                    out.shape, self.num_pyramid_levels, dtype=_ffi._pixel_dtype(out)))
             self.emit_progress(len(data), len(data))
             print(f"(Timepoint:{timepoint}, Region:{region}) Complete Stitching in {time.time() - start:.1f}s\n")
             return out
@@ -525,9 +530,15 @@ class StitcherProcess(Process):
         from .ome_zarr_writer import write_ome_zarr
         path = self.per_timepoint_region_output_template.format(timepoint=timepoint, region=region)
         dz = self.acquisition_params.get("dz(um)", 1.0) if self.acquisition_params else 1.0
-        write_ome_zarr(path, np.asarray(stitched_region), pixel_size_um=self.pixel_size_um, dz_um=dz,
+        stitched_region = np.asarray(stitched_region)
+        n_levels = self.num_pyramid_levels if num_levels is None else num_levels
+        made_for, levels = self._pyramids.pop((int(timepoint), region), (0, None))
+        if levels is not None and (made_for < n_levels or levels[0].shape[-2:] !=
+                                   ((stitched_region.shape[-2] + 1) // 2, (stitched_region.shape[-1] + 1) // 2)):
+            levels = None                                  # not the canvas stitch_region produced: slice on the host
+        write_ome_zarr(path, stitched_region, pixel_size_um=self.pixel_size_um, dz_um=dz,
                        channel_names=self.monochrome_channels, channel_colors=self.monochrome_colors,
-                       num_levels=self.num_pyramid_levels if num_levels is None else num_levels, chunks=self.chunks)
+                       num_levels=n_levels, chunks=self.chunks, levels=levels)
         return path
 
     def run(self):

@@ -200,6 +200,18 @@ int sb_register_pairs_async(sb_ctx* ctx, const sb_register_job* job, sb_pair_res
 int sb_normalize(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w,
                  int dtype, int mem);
 
+/* Multiscale levels of a fused canvas: the reference saves regions through ome_zarr's Scaler(method="nearest")
+ * (stitcher_process.py:1061-1062, stitcher.py:797-798), i.e. level l+1 = level l[..., ::2, ::2] with
+ * ceil(h/2) x ceil(w/2) pixels.  Levels 1 .. n_levels-1 are written to `out` back to back, each a dense
+ * (n_planes, h_l, w_l) array; sb_pyramid_elems() is their total element count (-1 on bad arguments).
+ * `src` is level 0: n_planes planes of height x width, rows src_row_pitch elements apart (0 = width), planes
+ * height rows apart -- or NULL for the canvas the lane's last row-major sb_fuse_region left on the device
+ * (host or device output), which costs no upload; shape and dtype must match that job.
+ * lane < 0: synchronous on lane 0; lane >= 0: enqueued, valid after sb_sync(lane). */
+int64_t sb_pyramid_elems(int32_t n_planes, int32_t height, int32_t width, int32_t n_levels);
+int sb_pyramid(sb_ctx* ctx, const void* src, int src_mem, int32_t n_planes, int32_t height, int32_t width,
+               int64_t src_row_pitch, int dtype, int32_t n_levels, void* out, int out_mem, int lane);
+
 #ifdef __cplusplus
 }
 #endif

@@ -203,6 +203,22 @@ def test_ome_zarr_from_chunk_ordered_buffer(tmp_path):
     assert np.array_equal(ozw.read_ome_zarr_level(path, 0)[0], dense)
 
 
+def test_ome_zarr_takes_precomputed_levels_and_pyramid_shapes(tmp_path):
+    """``levels=`` (made by ``sb_pyramid`` on the GPU) are written as given; missing ones are sliced on the host."""
+    from image_stitcher_b200 import _ffi
+    rng = np.random.default_rng(2)
+    data = rng.integers(0, 65535, (1, 2, 1, 101, 77), dtype=np.uint16)
+    assert _ffi.Context.pyramid_shapes(data.shape, 4) == [(2, 51, 39), (2, 26, 20), (2, 13, 10)]
+    assert _ffi.Context.pyramid_shapes(data.shape, 1) == []
+    marked = data[..., ::2, ::2].copy()
+    marked[0, 0, 0, 0, 0] ^= 1                        # prove the given level is the one stored
+    path = str(tmp_path / "l.ome.zarr")
+    ozw.write_ome_zarr(path, data, pixel_size_um=1.0, channel_names=["a", "b"], channel_colors=[1, 2], num_levels=3,
+                       chunks=(1, 1, 1, 64, 64), levels=[marked])
+    assert np.array_equal(ozw.read_ome_zarr_level(path, 1), marked)
+    assert np.array_equal(ozw.read_ome_zarr_level(path, 2), marked[..., ::2, ::2])
+
+
 def test_multi_device_workers_split_regions_without_exchange(tmp_path):
     """--devices 0,1: worker r of w stitches regions r, r + w, ...; both register the same first region."""
     from image_stitcher_b200 import stitcher_process_cli as cli
