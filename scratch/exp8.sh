@@ -1,4 +1,5 @@
 #!/bin/bash
+# NOTE: record of an experiment -- the SB_REG_SMEM_KB / SB_FUSE_PERSIST knobs it used were removed again (no gain).
 # concurrent registration + fusion with the registration blocks per SM capped through the shared-memory request
 for kb in 0 100 120; do
   SB_REG_SMEM_KB=$kb python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/b8_$kb.json 2>/dev/null

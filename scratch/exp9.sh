@@ -1,4 +1,5 @@
 #!/bin/bash
+# NOTE: record of an experiment -- the SB_REG_SMEM_KB / SB_FUSE_PERSIST knobs it used were removed again (no gain).
 # concurrent registration + fusion: registration blocks per SM capped (SB_REG_SMEM_KB), fusion from a bounded persistent grid
 for cfg in "100 1" "100 2" "120 2" "120 3" "0 5" "0 2"; do
   set -- $cfg
