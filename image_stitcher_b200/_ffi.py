@@ -30,7 +30,7 @@ EXPORTS = [
     "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_memcpy_async", "sb_set_flatfield", "sb_set_darkfield", "sb_clear_fields",
     "sb_flatfield_apply", "sb_fuse_region", "sb_sync", "sb_lane_mark", "sb_lane_wait_mark", "sb_set_lane_stream", "sb_canvas_pitch",
     "sb_chunked_plane_elems", "sb_register_pairs", "sb_register_pairs_async", "sb_normalize",
-    "sb_pyramid_elems", "sb_pyramid",
+    "sb_pyramid_elems", "sb_pyramid", "sb_estimate_flatfield",
 ]
 
 
@@ -116,6 +116,7 @@ def load_library(path: Optional[str] = None):
     lib.sb_register_pairs.argtypes = [vp, C.POINTER(SbRegisterJob), C.POINTER(SbPairResult)]
     lib.sb_register_pairs_async.argtypes = [vp, C.POINTER(SbRegisterJob), C.POINTER(SbPairResult)]
     lib.sb_normalize.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32]
+    lib.sb_estimate_flatfield.argtypes = [vp, C.POINTER(C.c_void_p), i32, i32, i32, i32, i32, i32, C.c_double, vp, i32]
     lib.sb_pyramid_elems.argtypes = [i32, i32, i32, i32]
     lib.sb_pyramid_elems.restype = i64
     lib.sb_pyramid.argtypes = [vp, vp, i32, i32, i32, i32, i64, i32, i32, vp, i32, i32]
@@ -341,6 +342,27 @@ class Context:
         self._check(self.lib.sb_normalize(self.handle, _ptr(t3), _ptr(out), t3.shape[0], t3.shape[1], t3.shape[2],
                                           _pixel_dtype(t3), SB_MEM_HOST), "sb_normalize")
         return out.reshape(tiles.shape)
+
+    def estimate_flatfield(self, tiles, *, grid: int = 128, sigma: float = 2.0, mem=SB_MEM_HOST, tile_shape=None,
+                           dtype=None) -> np.ndarray:
+        """Robust flat-field estimate (``sb_estimate_flatfield``, an extension -- not BaSiC) from a sequence of
+        same-shaped 2-D tiles (numpy arrays, or device addresses with ``mem=SB_MEM_DEVICE`` and ``tile_shape``)."""
+        tiles = list(tiles)
+        if not tiles:
+            raise ValueError("no tiles")
+        if mem == SB_MEM_HOST:
+            tiles = [np.ascontiguousarray(t) for t in tiles]
+            tile_shape = tiles[0].shape
+            if any(t.shape != tile_shape or t.dtype != tiles[0].dtype for t in tiles) or len(tile_shape) != 2:
+                raise ValueError("tiles must be 2-D arrays of one shape and dtype")
+        if dtype is None:
+            dtype = _pixel_dtype(tiles[0])
+        ptrs = (C.c_void_p * len(tiles))(*[_ptr(t) for t in tiles])
+        out = np.empty((int(tile_shape[0]), int(tile_shape[1])), dtype=np.float32)
+        self._check(self.lib.sb_estimate_flatfield(self.handle, ptrs, len(tiles), int(tile_shape[0]), int(tile_shape[1]),
+                                                   int(dtype), mem, int(grid), float(sigma), _ptr(out), SB_MEM_HOST),
+                    "sb_estimate_flatfield")
+        return out
 
     @staticmethod
     def pyramid_shapes(canvas_shape, n_levels: int):

@@ -286,6 +286,12 @@ int sb_fuse_region(sb_ctx* ctx, const sb_fuse_job* job, int lane) {
     return rc;
 }
 
+int sb_estimate_flatfield(sb_ctx* ctx, const void* const* tiles, int32_t n_tiles, int32_t tile_h, int32_t tile_w, int dtype,
+                          int mem, int32_t grid, double sigma, float* field_out, int out_mem) {
+    if (!ctx) return SB_ERR_INVALID;
+    return sb_estimate_flatfield_impl(ctx, tiles, n_tiles, tile_h, tile_w, dtype, mem, grid, sigma, field_out, out_mem);
+}
+
 int64_t sb_pyramid_elems(int32_t n_planes, int32_t height, int32_t width, int32_t n_levels) {
     if (n_planes <= 0 || height <= 0 || width <= 0 || n_levels < 1) return -1;
     return sb_pyramid_elems_impl(n_planes, height, width, n_levels);

@@ -113,6 +113,9 @@ int sb_fuse_region_u8(sb_ctx* ctx, const sb_fuse_job* job, int lane);
 int sb_register_pairs_u8(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out, bool async);
 int sb_flatfield_apply_u8(sb_ctx* ctx, int channel, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int mem);
 int sb_normalize_u8(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int mem);
+// flatfield.cu
+int sb_estimate_flatfield_impl(sb_ctx* ctx, const void* const* tiles, int n_tiles, int tile_h, int tile_w, int dtype, int mem,
+                               int grid, double sigma, float* field_out, int out_mem);
 // pyramid.cu
 int64_t sb_pyramid_elems_impl(int64_t n_planes, int height, int width, int n_levels);
 int sb_pyramid_impl(sb_ctx* ctx, const void* src, int src_mem, int n_planes, int height, int width, int64_t src_row_pitch,

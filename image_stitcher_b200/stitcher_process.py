@@ -11,7 +11,8 @@ from the reference's *behaviour* (file layout, ordering and rounding rules are c
 
 Out of scope: BaSiC flat-field *fitting*, OME-TIFF / bioio / aicsimageio /
 pyvips writers, pyramid merges, HCS plate merges.  ``get_flatfields`` uses BaSiCPy when it is
-installed and otherwise asks for ``set_flatfields``; ``.ome.zarr`` output goes through the minimal
+installed and otherwise the GPU's robust estimator (``sb_estimate_flatfield``, an extension with its own
+definition -- or provide the fields with ``set_flatfields``); ``.ome.zarr`` output goes through the minimal
 NGFF writer in ``ome_zarr_writer``.
 """
 from __future__ import annotations
@@ -277,21 +278,60 @@ class StitcherProcess(Process):
 
     # ------------------------------------------------------------------ flat-field estimation (out of scope)
     def get_flatfields(self):
-        try:
-            from basicpy import BaSiC      # noqa: F401
-        except ImportError as exc:
-            raise RuntimeError("flat-field *fitting* (BaSiCPy) is outside this package; install basicpy or provide "
-                               "the fields with set_flatfields({channel_index: HxW array})") from exc
+        """Per-channel flat-fields from a random sample of tiles (:505-571: at most 32 tiles per timepoint, stop above
+        48).  With BaSiCPy installed the fit is the reference's ``BaSiC(get_darkfield=False, smoothness_flatfield=1)``;
+        without it (this image) the sample goes to the GPU's robust estimator ``sb_estimate_flatfield`` -- an
+        extension with its own definition (oracle/flatfield_ref.py), NOT a reimplementation of BaSiC."""
         import random
+        try:
+            from basicpy import BaSiC
+        except ImportError:
+            BaSiC = None
+            self.emit_status("BaSiCPy is not installed: flat-fields from the GPU median estimator (not BaSiC)")
+
+        def process_images(images, channel_name):
+            if images.size == 0:
+                print(f"Warning: No images found for channel {channel_name}")
+                return
+            if images.ndim == 4:                           # (N, Z, Y, X): every plane is one sample
+                images = images.reshape((-1,) + images.shape[-2:])
+            if images.ndim != 3:
+                raise ValueError("Images must be 3 or 4-dimensional array, with dimension of (T, Y, X) or (T, Z, Y, X). "
+                                 f"Got shape {images.shape}")
+            channel_index = self.monochrome_channels.index(channel_name)
+            if BaSiC is not None:
+                basic = BaSiC(get_darkfield=False, smoothness_flatfield=1)
+                basic.fit(images)
+                self.flatfields[channel_index] = basic.flatfield
+            else:
+                self.flatfields[channel_index] = self.ctx.estimate_flatfield(list(images[:128]))
+            self.emit_progress(channel_index + 1, self.num_c)
+
+        self.emit_progress(0, self.num_c)
         for channel in self.channel_names:
             self.check_stop()
             self.emit_status(f"Calculating Flatfield... ({channel})")
-            paths = [v["filepath"] for v in self.acquisition_metadata.values() if v["channel"] == channel]
-            random.shuffle(paths)
-            images = np.array([read_image(p) for p in paths[:48]])
-            basic = BaSiC(get_darkfield=False, smoothness_flatfield=1)
-            basic.fit(images)
-            self.flatfields[self.monochrome_channels.index(channel)] = basic.flatfield
+            images = []
+            for t in self.timepoints:
+                paths = [tile["filepath"] for key, tile in self.acquisition_metadata.items()
+                         if tile["channel"] == channel and key[0] == int(t)]
+                if not paths:
+                    print(f"Warning: No images found for channel {channel} at timepoint {t}")
+                    continue
+                random.shuffle(paths)
+                images.extend(read_image(p) for p in paths[:min(32, len(paths))])
+                if len(images) > 48:
+                    break
+            if not images:
+                print(f"Warning: No images found for channel {channel} across all timepoints")
+                continue
+            images = np.array(images)
+            if images.ndim == 4 and images.shape[-1] == 3:  # (N, Y, X, 3) RGB tiles: one field per colour plane
+                base = channel.split("_")[0]
+                for i, suffix in enumerate(("_R", "_G", "_B")):
+                    process_images(np.ascontiguousarray(images[..., i]), base + suffix)
+            else:
+                process_images(images, channel)
         self._flat_dirty = True
 
     # ------------------------------------------------------------------ registration (reference :573-737, :844-855)

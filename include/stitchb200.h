@@ -200,6 +200,16 @@ int sb_register_pairs_async(sb_ctx* ctx, const sb_register_job* job, sb_pair_res
 int sb_normalize(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w,
                  int dtype, int mem);
 
+/* Flat-field ESTIMATE from a sample of n_tiles tiles of one channel (EXTENSION).  The reference fits its fields with
+ * the third-party BaSiCPy (get_flatfields, stitcher_process.py:505-571: <= 32 random tiles per timepoint, stop above
+ * 48); BaSiC is not reproduced here.  When it is not importable the host mirror calls this robust estimator instead:
+ * g x g cell means per tile (g = grid, 0 = 128, at most 512) / tile mean -> per-cell median over the tiles -> separable
+ * Gaussian (sigma in cells, symmetric boundary) -> mean 1 -> bilinear interpolation to tile_h x tile_w float32
+ * (definition and oracle: oracle/flatfield_ref.py).  The result is what sb_set_flatfield() takes.  At most 128 tiles.
+ * tiles: array of n_tiles pointers (host array; the pixels are `mem`).  Synchronous. */
+int sb_estimate_flatfield(sb_ctx* ctx, const void* const* tiles, int32_t n_tiles, int32_t tile_h, int32_t tile_w, int dtype,
+                          int mem, int32_t grid, double sigma, float* field_out, int out_mem);
+
 /* Multiscale levels of a fused canvas: the reference saves regions through ome_zarr's Scaler(method="nearest")
  * (stitcher_process.py:1061-1062, stitcher.py:797-798), i.e. level l+1 = level l[..., ::2, ::2] with
  * ceil(h/2) x ceil(w/2) pixels.  Levels 1 .. n_levels-1 are written to `out` back to back, each a dense
