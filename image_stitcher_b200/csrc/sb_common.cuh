@@ -182,6 +182,17 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void l2_prefetch_bulk_hint(const void* p, unsigned bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(policy) : "memory");
+}
+// read-only 128-bit load with an L2 eviction-priority hint (createpolicy result)
+__device__ __forceinline__ float4 ldg_f4_hint(const float4* p, uint64_t policy) {
+    float4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(policy));
+    return v;
+}
 // streaming 128-bit store: written once, never re-read by this kernel
 __device__ __forceinline__ void st_stream_v4(void* p, uint4 v) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
