@@ -55,6 +55,25 @@ int sb_reserve_pinned(sb_ctx* ctx, void** p, size_t* cap, size_t bytes) {
     return SB_OK;
 }
 
+// Every entry point runs on the context's device, whatever the calling thread's current device is (several contexts
+// on different GPUs may live in one process); the caller's device is restored on return.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(const sb_ctx* ctx) {
+        int cur = -1;
+        if (ctx && cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device) {
+            prev = cur;
+            cudaSetDevice(ctx->device);
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define SB_ENTER(ctx) DeviceGuard sb_device_guard__(ctx)
+
 Lane* sb_lane(sb_ctx* ctx, int lane) {
     if (!ctx || lane < 0 || lane >= SB_NUM_LANES) return nullptr;
     return &ctx->lanes[lane];
@@ -114,7 +133,7 @@ static void free_field(FieldPool& f) {
 
 void sb_destroy(sb_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    SB_ENTER(ctx);
     cudaDeviceSynchronize();
     for (int i = 0; i < SB_NUM_LANES; ++i) {
         Lane& l = ctx->lanes[i];
@@ -146,6 +165,7 @@ int sb_num_lanes(const sb_ctx*) { return SB_NUM_LANES; }
 int sb_device_sm_count(const sb_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 void* sb_host_alloc(sb_ctx* ctx, size_t bytes) {
+    SB_ENTER(ctx);
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
         sb_fail(ctx, SB_ERR_NOMEM, "cudaMallocHost(%zu) failed", bytes);
@@ -153,10 +173,12 @@ void* sb_host_alloc(sb_ctx* ctx, size_t bytes) {
     }
     return p;
 }
-void sb_host_free(sb_ctx*, void* p) {
+void sb_host_free(sb_ctx* ctx, void* p) {
+    SB_ENTER(ctx);
     if (p) cudaFreeHost(p);
 }
 void* sb_device_alloc(sb_ctx* ctx, size_t bytes) {
+    SB_ENTER(ctx);
     void* p = nullptr;
     if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
         sb_fail(ctx, SB_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
@@ -164,19 +186,23 @@ void* sb_device_alloc(sb_ctx* ctx, size_t bytes) {
     }
     return p;
 }
-void sb_device_free(sb_ctx*, void* p) {
+void sb_device_free(sb_ctx* ctx, void* p) {
+    SB_ENTER(ctx);
     if (p) cudaFree(p);
 }
 int sb_memcpy_h2d(sb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    SB_ENTER(ctx);
     SB_CUDA(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
     return SB_OK;
 }
 int sb_memcpy_d2h(sb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    SB_ENTER(ctx);
     SB_CUDA(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
     return SB_OK;
 }
 
 int sb_memcpy_async(sb_ctx* ctx, int lane, void* dst, const void* src, size_t bytes, int kind) {
+    SB_ENTER(ctx);
     Lane* l = sb_lane(ctx, lane);
     if (!l) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
     const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
@@ -242,13 +268,18 @@ static int set_field(sb_ctx* ctx, FieldPool& pool, const char* what, int channel
 }
 
 int sb_set_flatfield(sb_ctx* ctx, int channel, const void* field, int dtype, int mem, int h, int w) {
+    if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
     return set_field(ctx, ctx->flat, "sb_set_flatfield", channel, field, dtype, mem, h, w);
 }
 int sb_set_darkfield(sb_ctx* ctx, int channel, const void* field, int dtype, int mem, int h, int w) {
+    if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
     return set_field(ctx, ctx->dark, "sb_set_darkfield", channel, field, dtype, mem, h, w);
 }
 int sb_clear_fields(sb_ctx* ctx) {
-    SB_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+    if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
     cudaDeviceSynchronize();
     free_field(ctx->flat);
     free_field(ctx->dark);
@@ -263,6 +294,7 @@ int64_t sb_chunked_plane_elems(int32_t height, int32_t width, int32_t chunk_h, i
 
 int sb_fuse_region(sb_ctx* ctx, const sb_fuse_job* job, int lane) {
     if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
     if (lane >= SB_NUM_LANES) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
     Lane* l = sb_lane(ctx, lane < 0 ? 0 : lane);
     l->resident = ResidentCanvas();
@@ -289,6 +321,7 @@ int sb_fuse_region(sb_ctx* ctx, const sb_fuse_job* job, int lane) {
 int sb_estimate_flatfield(sb_ctx* ctx, const void* const* tiles, int32_t n_tiles, int32_t tile_h, int32_t tile_w, int dtype,
                           int mem, int32_t grid, double sigma, float* field_out, int out_mem) {
     if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
     return sb_estimate_flatfield_impl(ctx, tiles, n_tiles, tile_h, tile_w, dtype, mem, grid, sigma, field_out, out_mem);
 }
 
@@ -300,10 +333,12 @@ int64_t sb_pyramid_elems(int32_t n_planes, int32_t height, int32_t width, int32_
 int sb_pyramid(sb_ctx* ctx, const void* src, int src_mem, int32_t n_planes, int32_t height, int32_t width,
                int64_t src_row_pitch, int dtype, int32_t n_levels, void* out, int out_mem, int lane) {
     if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
     return sb_pyramid_impl(ctx, src, src_mem, n_planes, height, width, src_row_pitch, dtype, n_levels, out, out_mem, lane);
 }
 
 int sb_sync(sb_ctx* ctx, int lane) {
+    SB_ENTER(ctx);
     if (!ctx) return SB_ERR_INVALID;
     if (lane >= SB_NUM_LANES) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
     for (int i = 0; i < SB_NUM_LANES; ++i)
@@ -316,6 +351,7 @@ int sb_sync(sb_ctx* ctx, int lane) {
 }
 
 int sb_lane_mark(sb_ctx* ctx, int lane) {
+    SB_ENTER(ctx);
     Lane* l = sb_lane(ctx, lane);
     if (!l) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
     if (!l->mark) SB_CUDA(ctx, cudaEventCreateWithFlags(&l->mark, cudaEventDisableTiming));
@@ -325,6 +361,7 @@ int sb_lane_mark(sb_ctx* ctx, int lane) {
 }
 
 int sb_lane_wait_mark(sb_ctx* ctx, int lane, int other) {
+    SB_ENTER(ctx);
     Lane* l = sb_lane(ctx, lane);
     Lane* o = sb_lane(ctx, other);
     if (!l || !o) return sb_fail(ctx, SB_ERR_INVALID, "lane %d / %d out of range", lane, other);
@@ -333,6 +370,7 @@ int sb_lane_wait_mark(sb_ctx* ctx, int lane, int other) {
 }
 
 int sb_set_lane_stream(sb_ctx* ctx, int lane, void* cuda_stream) {
+    SB_ENTER(ctx);
     Lane* l = sb_lane(ctx, lane);
     if (!l) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
     SB_CUDA(ctx, cudaStreamSynchronize(l->stream));
@@ -343,24 +381,28 @@ int sb_set_lane_stream(sb_ctx* ctx, int lane, void* cuda_stream) {
 int sb_flatfield_apply(sb_ctx* ctx, int channel, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w,
                        int dtype, int mem) {
     if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
     if (dtype == SB_U8) return sb_flatfield_apply_u8(ctx, channel, tiles, out, n_tiles, tile_h, tile_w, mem);
     return sb_flatfield_apply_impl(ctx, channel, tiles, out, n_tiles, tile_h, tile_w, dtype, mem);
 }
 
 int sb_register_pairs(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out) {
     if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
     if (job && job->dtype == SB_U8) return sb_register_pairs_u8(ctx, job, out, false);
     return sb_register_pairs_impl(ctx, job, out, false);
 }
 
 int sb_register_pairs_async(sb_ctx* ctx, const sb_register_job* job, sb_pair_result* out) {
     if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
     if (job && job->dtype == SB_U8) return sb_register_pairs_u8(ctx, job, out, true);
     return sb_register_pairs_impl(ctx, job, out, true);
 }
 
 int sb_normalize(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int dtype, int mem) {
     if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
     if (dtype == SB_U8) return sb_normalize_u8(ctx, tiles, out, n_tiles, tile_h, tile_w, mem);
     return sb_normalize_impl(ctx, tiles, out, n_tiles, tile_h, tile_w, dtype, mem);
 }

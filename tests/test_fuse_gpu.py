@@ -274,3 +274,38 @@ def test_blend_cells_path_flat_only_random_geometry(ctx, mode):
     assert diff.max() <= 1, (int(diff.max()), int((diff > 1).sum()))
     assert (diff > 0).mean() < 0.02                       # rounding ties only
     ctx.clear_fields()
+
+
+def test_two_contexts_on_two_devices_in_one_process():
+    """Every entry point binds the context's device itself: two contexts on different GPUs can be driven alternately
+    from one thread without the caller switching devices (skipped on a single-GPU box)."""
+    from image_stitcher_b200 import _ffi
+    c0 = _ffi.Context(0)
+    try:
+        try:
+            c1 = _ffi.Context(1)
+        except RuntimeError:
+            pytest.skip("needs two GPUs")
+        try:
+            rng = np.random.default_rng(3)
+            H = W = 128
+            tiles = [rng.integers(0, 65536, size=(H, W), dtype=np.uint16) for _ in range(4)]
+            job = [(tiles[0], 0, 0, 0, 0, 0, 0, 0, 0), (tiles[1], 115, 2, 0, 0, 0, 0, 0, 0),
+                   (tiles[2], 3, 117, 0, 0, 0, 0, 0, 0), (tiles[3], 118, 119, 0, 0, 0, 0, 0, 0)]
+            shape = (1, 1, 1, 249, 247)
+            flat = rng.uniform(0.7, 1.1, (H, W)).astype(np.float32)
+            outs = []
+            for c in (c0, c1, c0, c1):
+                c.set_flatfield(0, flat)
+                out = np.empty(shape, np.uint16)
+                c.fuse_region(job, (H, W), shape[1:], out=out, apply_flatfield=True)
+                lv = c.pyramid(shape, 2, dtype=_ffi.SB_U16)
+                assert np.array_equal(lv[0], out[..., ::2, ::2])
+                r = c.register_pairs([(tiles[0], tiles[0], _ffi.SB_DIR_HORIZONTAL)], (H, W), 16, 16)
+                outs.append((out, (r[0]["dy"], r[0]["dx"])))
+            for out, shift in outs[1:]:
+                assert np.array_equal(out, outs[0][0]) and shift == outs[0][1]
+        finally:
+            c1.close()
+    finally:
+        c0.close()
