@@ -116,3 +116,34 @@ def test_run_with_apply_flatfield_estimates_fields_when_basicpy_is_absent(tmp_pa
     st.apply_flatfield = True
     st.flatfields = {c: np.asarray(f) for c, f in s.flatfields.items()}
     assert np.array_equal(ozw.read_ome_zarr_level(path, 0), sr.stitch_region(st, tiles))
+
+
+@pytest.mark.gpu
+def test_get_flatfields_splits_rgb_tiles_into_planes(tmp_path):
+    """8-bit RGB camera tiles: one estimated field per colour plane, keyed like the reference (``<ch>_R/_G/_B``, :557-565)."""
+    try:
+        import basicpy  # noqa: F401
+        pytest.skip("BaSiCPy is installed: the reference's own fit is used")
+    except ImportError:
+        pass
+    from conftest import load_golden
+    from image_stitcher_b200.stitcher_parameters import StitchingParameters
+    from image_stitcher_b200.stitcher_process import StitcherProcess
+    from oracle import synth
+    g, st, tiles, kw = load_golden("coord_2x3_rgb_u8")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    s = StitcherProcess(StitchingParameters(input_folder=root, apply_flatfield=True), mp.Queue(), mp.Queue(), mp.Queue(), mp.Event())
+    try:
+        s.get_timepoints()
+        s.extract_acquisition_parameters()
+        s.get_pixel_size()
+        s.parse_acquisition_metadata()
+        s.get_flatfields()
+        assert sorted(s.flatfields) == [0, 1, 2] and len(s.monochrome_channels) == 3
+        for i, suffix in enumerate("RGB"):
+            idx = [k for k, name in enumerate(s.monochrome_channels) if name.endswith("_" + suffix)][0]
+            want = fr.estimate_flatfield(np.array([t.pixels[:, :, i] for t in tiles]))
+            assert s.flatfields[idx].shape == want.shape and np.allclose(s.flatfields[idx], want, rtol=2e-6)
+    finally:
+        s.cleanup()
