@@ -219,6 +219,49 @@ def test_ome_zarr_takes_precomputed_levels_and_pyramid_shapes(tmp_path):
     assert np.array_equal(ozw.read_ome_zarr_level(path, 2), marked[..., ::2, ::2])
 
 
+def test_get_flatfields_samples_like_the_reference(tmp_path, monkeypatch):
+    """(:529-548) at most 32 random tiles per timepoint, stop once more than 48 are collected; one field per channel.
+    The estimator itself is replaced by a recorder here (the CUDA estimator is covered by the GPU tests)."""
+    import multiprocessing as mp
+    import sys
+    from image_stitcher_b200.stitcher_process import StitcherProcess
+    monkeypatch.setitem(sys.modules, "basicpy", None)             # "not installed", whatever the environment holds
+    chans = ("Fluorescence 405 nm Ex", "Fluorescence 488 nm Ex")
+    st, tiles, _ = synth.make_region(5, 8, 16, 24, channels=chans, jitter=0)
+    root = str(tmp_path / "acq")
+    for t in range(3):
+        synth.write_squid_layout(root, {"A1": tiles}, timepoint=t)
+    s = StitcherProcess(StitchingParameters(input_folder=root, apply_flatfield=True), mp.Queue(), mp.Queue(), mp.Queue(), mp.Event())
+    s.get_timepoints()
+    s.extract_acquisition_parameters()
+    s.get_pixel_size()
+    s.parse_acquisition_metadata()
+    calls = []
+
+    class Recorder:
+        def estimate_flatfield(self, sample, **kw):
+            calls.append([np.asarray(t) for t in sample])
+            return np.full(sample[0].shape, float(len(calls)), np.float32)
+
+    s._ctx = Recorder()
+    s.get_flatfields()
+    s._ctx = None
+    assert [len(c) for c in calls] == [64, 64]                    # 32 from timepoint 0, 32 more from timepoint 1, then > 48
+    assert all(t.shape == (16, 24) and t.dtype == np.uint16 for c in calls for t in c)
+    assert sorted(s.flatfields) == [0, 1] and float(s.flatfields[1][0, 0]) == 2.0
+    by_channel = {ch: {t.pixels.tobytes() for t in tiles if t.channel == ch} for ch in chans}
+    for ci, ch in enumerate(sorted(chans)):                        # every sampled tile belongs to the channel being fitted
+        assert all(t.tobytes() in by_channel[ch] for t in calls[ci])
+    from queue import Empty
+    msgs = []
+    while True:
+        try:
+            msgs.append(s.status_queue.get(timeout=0.5))
+        except Empty:
+            break
+    assert any("not BaSiC" in str(m) for m in msgs)
+
+
 def test_multi_device_workers_split_regions_without_exchange(tmp_path):
     """--devices 0,1: worker r of w stitches regions r, r + w, ...; both register the same first region."""
     from image_stitcher_b200 import stitcher_process_cli as cli
