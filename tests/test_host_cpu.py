@@ -219,6 +219,25 @@ def test_ome_zarr_takes_precomputed_levels_and_pyramid_shapes(tmp_path):
     assert np.array_equal(ozw.read_ome_zarr_level(path, 2), marked[..., ::2, ::2])
 
 
+def test_integration_md_stub_matches_the_binding():
+    """The ctypes stub printed in INTEGRATION.md must stay in step with the header: its structures have the layout of
+    the real binding's, and every prototype it sets names an exported symbol."""
+    import ctypes as C
+    import re
+    from image_stitcher_b200 import _ffi
+    text = open(os.path.join(os.path.dirname(__file__), "..", "INTEGRATION.md")).read()
+    code = re.search(r"```python\n# stitcher_process_b200.py.*?```", text, re.S).group(0)
+    structs = code[code.index("class SbPair("):code.index("lib.sb_create.argtypes")]
+    ns = {"C": C}
+    exec(structs, ns)
+    for mine, real in [("SbPair", _ffi.SbPair), ("SbPairResult", _ffi.SbPairResult), ("SbRegisterJob", _ffi.SbRegisterJob),
+                       ("SbTile", _ffi.SbTile), ("SbFuseJob", _ffi.SbFuseJob)]:
+        assert C.sizeof(ns[mine]) == C.sizeof(real), mine
+        assert [(n, C.sizeof(t)) for n, t in ns[mine]._fields_] == [(n, C.sizeof(t)) for n, t in real._fields_], mine
+    for sym in re.findall(r"lib\.(sb_[a-z0-9_]+)", code):
+        assert sym in _ffi.EXPORTS, sym
+
+
 def test_get_flatfields_samples_like_the_reference(tmp_path, monkeypatch):
     """(:529-548) at most 32 random tiles per timepoint, stop once more than 48 are collected; one field per channel.
     The estimator itself is replaced by a recorder here (the CUDA estimator is covered by the GPU tests)."""
