@@ -745,10 +745,11 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     // Sub-batches: up to kWays of them run concurrently (the lane's stream and its auxiliary streams, each with its own
     // workspace slice) -- the chain is a sequence of short dependent kernels, and the neighbours' blocks fill the tails
     // and launch gaps.  Measured on B200 (1152 pairs): 64 MB of spectra in flight (L2 resident) 18.6 ms, 128 MB 17.1,
-    // 256 MB 16.7, 384 MB over 3 streams 16.1: fewer, larger launches beat strict L2 residency, so the budget is 384 MB.
-    static const int kWays = getenv("SB_REG_WAYS") ? std::max(1, std::min(4, atoi(getenv("SB_REG_WAYS")))) : 3;
+    // 256 MB 16.7, 384 MB over 3 streams 16.1 (15.3 with 3 blocks per SM), 768 MB over 4 streams 14.9: fewer, larger launches beat
+    // strict L2 residency, so the budget is 768 MB (54 pairs of 1024 x 214 per sub-batch).
+    static const int kWays = getenv("SB_REG_WAYS") ? std::max(1, std::min(4, atoi(getenv("SB_REG_WAYS")))) : 4;
     const size_t per_pair = 2 * strip * sizeof(T2);
-    static const size_t kL2Budget = (size_t)(getenv("SB_REG_L2_MB") ? std::max(8, atoi(getenv("SB_REG_L2_MB"))) : 384) << 20;
+    static const size_t kL2Budget = (size_t)(getenv("SB_REG_L2_MB") ? std::max(8, atoi(getenv("SB_REG_L2_MB"))) : 768) << 20;
     int B = (int)std::max<size_t>(1, kL2Budget / per_pair);
     int ways = 1;
     while (ways < kWays && B / (ways + 1) >= 2 && n > B / (ways + 1)) ++ways;
