@@ -382,6 +382,7 @@ int sb_flatfield_apply(sb_ctx* ctx, int channel, const void* tiles, void* out, i
                        int dtype, int mem) {
     if (!ctx) return SB_ERR_INVALID;
     SB_ENTER(ctx);
+    ctx->lanes[0].resident = ResidentCanvas();   // these helpers stage through lane 0's canvas buffers
     if (dtype == SB_U8) return sb_flatfield_apply_u8(ctx, channel, tiles, out, n_tiles, tile_h, tile_w, mem);
     return sb_flatfield_apply_impl(ctx, channel, tiles, out, n_tiles, tile_h, tile_w, dtype, mem);
 }
@@ -403,6 +404,7 @@ int sb_register_pairs_async(sb_ctx* ctx, const sb_register_job* job, sb_pair_res
 int sb_normalize(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int tile_h, int tile_w, int dtype, int mem) {
     if (!ctx) return SB_ERR_INVALID;
     SB_ENTER(ctx);
+    ctx->lanes[0].resident = ResidentCanvas();   // these helpers stage through lane 0's canvas buffers
     if (dtype == SB_U8) return sb_normalize_u8(ctx, tiles, out, n_tiles, tile_h, tile_w, mem);
     return sb_normalize_impl(ctx, tiles, out, n_tiles, tile_h, tile_w, dtype, mem);
 }

@@ -216,7 +216,8 @@ int sb_estimate_flatfield(sb_ctx* ctx, const void* const* tiles, int32_t n_tiles
  * (n_planes, h_l, w_l) array; sb_pyramid_elems() is their total element count (-1 on bad arguments).
  * `src` is level 0: n_planes planes of height x width, rows src_row_pitch elements apart (0 = width), planes
  * height rows apart -- or NULL for the canvas the lane's last row-major sb_fuse_region left on the device
- * (host or device output), which costs no upload; shape and dtype must match that job.
+ * (host or device output), which costs no upload; shape and dtype must match that job.  Any later sb_fuse_region on
+ * the lane, and sb_flatfield_apply / sb_normalize (which stage through lane 0's buffers), invalidate it.
  * lane < 0: synchronous on lane 0; lane >= 0: enqueued, valid after sb_sync(lane). */
 int64_t sb_pyramid_elems(int32_t n_planes, int32_t height, int32_t width, int32_t n_levels);
 int sb_pyramid(sb_ctx* ctx, const void* src, int src_mem, int32_t n_planes, int32_t height, int32_t width,

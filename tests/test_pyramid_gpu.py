@@ -84,6 +84,9 @@ def test_errors(ctx):
         c.fuse_region([(tile, 0, 0, 0, 0, 0, 0, 0, 0)], (64, 64), (1, 1, 64, 64), out=out)
         with pytest.raises(RuntimeError, match="resident canvas is"):
             c.pyramid((1, 1, 1, 64, 32), 2, dtype=_ffi.SB_U16)
+        c.normalize(tile)                                   # stages through lane 0's canvas buffer: the resident canvas is gone
+        with pytest.raises(RuntimeError, match="no resident canvas"):
+            c.pyramid((1, 1, 1, 64, 64), 2, dtype=_ffi.SB_U16)
         with pytest.raises(RuntimeError, match="bad canvas shape"):
             c.pyramid((1, 0, 8), 2, src=np.zeros(8, np.uint16))
     finally:
