@@ -534,6 +534,8 @@ class StitcherProcess(Process):
                 # multiscale levels from the canvas while it is still on the device (Scaler.nearest, :1061-1062)
                 self._pyramids[(int(timepoint), region)] = (self.num_pyramid_levels, self.ctx.pyramid(
                     out.shape, self.num_pyramid_levels, dtype=_ffi._pixel_dtype(out)))
+                while len(self._pyramids) > 4:             # callers that never save: do not hoard levels (dicts keep insertion order)
+                    self._pyramids.pop(next(iter(self._pyramids)))
             self.emit_progress(len(data), len(data))
             print(f"(Timepoint:{timepoint}, Region:{region}) Complete Stitching in {time.time() - start:.1f}s\n")
             return out
