@@ -30,7 +30,7 @@ EXPORTS = [
     "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_memcpy_async", "sb_set_flatfield", "sb_set_darkfield", "sb_clear_fields",
     "sb_flatfield_apply", "sb_fuse_region", "sb_sync", "sb_lane_mark", "sb_lane_wait_mark", "sb_set_lane_stream", "sb_canvas_pitch",
     "sb_chunked_plane_elems", "sb_register_pairs", "sb_register_pairs_async", "sb_normalize",
-    "sb_pyramid_elems", "sb_pyramid", "sb_estimate_flatfield",
+    "sb_pyramid_elems", "sb_pyramid", "sb_estimate_flatfield", "sb_selftest",
 ]
 
 
@@ -54,7 +54,8 @@ class SbPair(C.Structure):
 
 class SbPairResult(C.Structure):
     _fields_ = [("dy", C.c_int32), ("dx", C.c_int32), ("shift", C.c_double * 2), ("coarse", C.c_int32 * 2),
-                ("fine", C.c_int32 * 2), ("peak", C.c_float), ("runner_up", C.c_float), ("fine_peak", C.c_float),
+                ("fine", C.c_int32 * 2), ("peak", C.c_float), ("second", C.c_float), ("runner_up", C.c_float), ("fine_peak", C.c_float),
+                ("fine_second", C.c_float),
                 ("ref_min", C.c_int32), ("ref_max", C.c_int32), ("mov_min", C.c_int32), ("mov_max", C.c_int32),
                 ("precision", C.c_int32)]
 
@@ -120,6 +121,7 @@ def load_library(path: Optional[str] = None):
     lib.sb_pyramid_elems.argtypes = [i32, i32, i32, i32]
     lib.sb_pyramid_elems.restype = i64
     lib.sb_pyramid.argtypes = [vp, vp, i32, i32, i32, i32, i64, i32, i32, vp, i32, i32]
+    lib.sb_selftest.argtypes = [vp, i32, i64, C.POINTER(C.c_uint64)]
     if path == LIB_PATH:
         _lib = lib
     return lib
@@ -296,7 +298,7 @@ class Context:
     def _pair_dicts(res):
         return [{"dy": r.dy, "dx": r.dx, "shift": (r.shift[0], r.shift[1]),
                  "coarse": (r.coarse[0], r.coarse[1]), "fine": (r.fine[0], r.fine[1]), "peak": r.peak,
-                 "runner_up": r.runner_up, "fine_peak": r.fine_peak, "ref_minmax": (r.ref_min, r.ref_max),
+                 "second": r.second, "runner_up": r.runner_up, "fine_peak": r.fine_peak, "fine_second": r.fine_second, "ref_minmax": (r.ref_min, r.ref_max),
                  "mov_minmax": (r.mov_min, r.mov_max), "precision": r.precision} for r in res]
 
     def _register_job(self, pairs, tile_shape, max_overlap_x, max_overlap_y, mem, upsample_factor, precision, lane,
@@ -363,6 +365,12 @@ class Context:
                                                    int(dtype), mem, int(grid), float(sigma), _ptr(out), SB_MEM_HOST),
                     "sb_estimate_flatfield")
         return out
+
+    def selftest(self, which: int, arg: int):
+        """Test hook (``sb_selftest``): returns ``(cases_checked, mismatches, first_mismatch_key)``."""
+        out = (C.c_uint64 * 4)()
+        self._check(self.lib.sb_selftest(self.handle, int(which), int(arg), out), "sb_selftest")
+        return int(out[0]), int(out[1]), int(out[2])
 
     @staticmethod
     def pyramid_shapes(canvas_shape, n_levels: int):

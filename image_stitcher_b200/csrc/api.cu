@@ -337,6 +337,15 @@ int sb_pyramid(sb_ctx* ctx, const void* src, int src_mem, int32_t n_planes, int3
     return sb_pyramid_impl(ctx, src, src_mem, n_planes, height, width, src_row_pitch, dtype, n_levels, out, out_mem, lane);
 }
 
+int sb_selftest(sb_ctx* ctx, int which, int64_t arg, uint64_t* out) {
+    if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
+    SB_CHECK(ctx, out != nullptr, "out is NULL");
+    if (which == SB_SELFTEST_STRETCH) return sb_selftest_stretch_impl(ctx, (int)arg, out);
+    if (which == SB_SELFTEST_DIVIDE) return sb_selftest_div_impl(ctx, (int)arg, out);
+    return sb_fail(ctx, SB_ERR_INVALID, "unknown self-test %d", which);
+}
+
 int sb_sync(sb_ctx* ctx, int lane) {
     SB_ENTER(ctx);
     if (!ctx) return SB_ERR_INVALID;

@@ -41,8 +41,9 @@ struct PairDesc {            // device-side description of one pair of a batch
     int32_t a_tile, b_tile;  // indices into the min/max table
 };
 
-struct CtaBest {             // block-local first maximum; double keeps the float64 path's resolution
+struct CtaBest {             // block-local first maximum and the second-largest value; double keeps the float64 path's resolution
     double val;
+    double second;           // largest |cc| of the block at any OTHER pixel (may equal val)
     int32_t idx;
     int32_t pad;
 };
@@ -50,7 +51,8 @@ struct CtaBest {             // block-local first maximum; double keeps the floa
 struct PeakOut {             // per pair, written by the device, read back by the host
     int32_t coarse_y, coarse_x;
     int32_t fine_y, fine_x;
-    float peak, runner_up, fine_peak;
+    float peak, second, runner_up;     // see sb_pair_result
+    float fine_peak, fine_second;
     int32_t pad;
 };
 
@@ -343,13 +345,24 @@ template <typename V>
 __device__ __forceinline__ void best_update(V& bv, int& bi, V v, int i) {
     if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
 }
+// first maximum (ties -> lowest index) plus the largest value at any other position
+template <typename V>
+__device__ __forceinline__ void top2_update(V& bv, int& bi, V& b2, V v, int i) {
+    if (v > bv || (v == bv && i < bi)) { b2 = bv; bv = v; bi = i; }
+    else if (v > b2) b2 = v;
+}
+template <typename V>
+__device__ __forceinline__ void top2_merge(V& bv, int& bi, V& b2, V ov, int oi, V o2) {
+    if (ov > bv || (ov == bv && oi < bi)) { b2 = bv > o2 ? bv : o2; bv = ov; bi = oi; }
+    else if (ov > b2) b2 = ov;
+}
 
 template <typename T, int LB>
 __global__ void __launch_bounds__(256, SB_REG_CTAS) rows_inv_argmax_kernel(int Sh, int Sw, int lpb, int nrb, int swap,
                                                               const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
                                                               const float* __restrict__ ctab_g, int ctab_n,
                                                               const typename Vec2<T>::type* __restrict__ Y,
-                                                              CtaBest* __restrict__ best) {
+                                                              CtaBest* __restrict__ best, float* __restrict__ rowmax) {
     using T2 = typename Vec2<T>::type;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     T2* buf0 = reinterpret_cast<T2*>(smem_raw);
@@ -388,75 +401,107 @@ __global__ void __launch_bounds__(256, SB_REG_CTAS) rows_inv_argmax_kernel(int S
     }
     __syncthreads();
     const T2* res = fft_lines<T2, LB>(buf0, buf1, tw, plan, lpb, true, ctab);
-    T bv = (T)-1;
+    T bv = (T)-1, b2 = (T)-1;
     int bi = 0x7fffffff;
+    float* rmax = rowmax + (size_t)p * Sh;
     for (int l = warp; l < lpb; l += nwarps) {
         const int y1 = 2 * (l0 + l), y2 = y1 + 1;
         if (y1 >= Sh) break;
         const T2* row = res + (size_t)l * Sw;
+        T m1 = (T)0, m2 = (T)0;                                  // maxima of the two rows of this line (|cc| >= 0)
         for (int x = lane; x < Sw; x += 32) {
             const T2 v = row[x];
+            const T a1 = fabs(v.x), a2 = fabs(v.y);
             // first maximum in the C order of the ORIGINAL strip: in a transposed frame (y, x) is (col, row) there
-            best_update<T>(bv, bi, fabs(v.x), swap ? x * Sh + y1 : y1 * Sw + x);
-            if (y2 < Sh) best_update<T>(bv, bi, fabs(v.y), swap ? x * Sh + y2 : y2 * Sw + x);
+            top2_update<T>(bv, bi, b2, a1, swap ? x * Sh + y1 : y1 * Sw + x);
+            m1 = a1 > m1 ? a1 : m1;
+            if (y2 < Sh) {
+                top2_update<T>(bv, bi, b2, a2, swap ? x * Sh + y2 : y2 * Sw + x);
+                m2 = a2 > m2 ? a2 : m2;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const T o1 = __shfl_xor_sync(0xffffffffu, m1, o), o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+            m1 = o1 > m1 ? o1 : m1;
+            m2 = o2 > m2 ? o2 : m2;
+        }
+        if (lane == 0) {                                         // per-row maxima: the runner-up outside the peak's band
+            const double sc = 1.0 / ((double)Sh * (double)Sw);
+            rmax[y1] = (float)((double)m1 * sc);
+            if (y2 < Sh) rmax[y2] = (float)((double)m2 * sc);
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const T ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const T o2 = __shfl_xor_sync(0xffffffffu, b2, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        best_update<T>(bv, bi, ov, oi);
+        top2_merge<T>(bv, bi, b2, ov, oi, o2);
     }
-    __shared__ double sv[8];
+    __shared__ double sv[8], s2[8];
     __shared__ int si[8];
-    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = (double)bv; si[threadIdx.x >> 5] = bi; }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = (double)bv; s2[threadIdx.x >> 5] = (double)b2; si[threadIdx.x >> 5] = bi; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double b = (double)bv;
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best_update<double>(b, bi, sv[w], si[w]);
-        best[(size_t)p * nrb + rb].val = b / ((double)Sh * (double)Sw);
-        best[(size_t)p * nrb + rb].idx = bi;
+        double b = (double)bv, c = (double)b2;
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) top2_merge<double>(b, bi, c, sv[w], si[w], s2[w]);
+        const double sc = 1.0 / ((double)Sh * (double)Sw);
+        CtaBest& o = best[(size_t)p * nrb + rb];
+        o.val = b * sc;
+        o.second = c > 0.0 ? c * sc : 0.0;
+        o.idx = bi;
     }
 }
 
-// one warp per pair: global first-maximum and the best value found by any OTHER block
+// One warp per pair: the global first maximum, the second-largest |cc| anywhere else (the near-tie test of SB_PREC_AUTO)
+// and the runner-up = largest |cc| outside the band of three frame rows (circular) centred on the peak row -- the frame
+// row is the strip's LONG axis position (image row for horizontal pairs, image column for vertical pairs in the
+// transposed frame), so the band removes the peak's own line and its two neighbours.
 __global__ void __launch_bounds__(32) peak_final_kernel(const CtaBest* __restrict__ best, int nrb, int Sh, int Sw, int swap,
-                                                        const int* __restrict__ nonzero, PeakOut* out) {
+                                                        const float* __restrict__ rowmax, const int* __restrict__ nonzero,
+                                                        PeakOut* out) {
     const int p = blockIdx.x;
     if (nonzero[p] != 3) {                       // a strip is identically zero: cc == 0 everywhere, first index wins
         if (threadIdx.x == 0) {
             out[p].coarse_y = out[p].coarse_x = 0;
-            out[p].peak = out[p].runner_up = out[p].fine_peak = 0.f;
+            out[p].peak = out[p].second = out[p].runner_up = out[p].fine_peak = out[p].fine_second = 0.f;
             out[p].fine_y = out[p].fine_x = -1;
         }
         return;
     }
-    double bv = -1.0;
-    int bi = 0x7fffffff, bb = -1;
+    double bv = -1.0, b2 = -1.0;
+    int bi = 0x7fffffff;
     for (int i = threadIdx.x; i < nrb; i += 32) {
         const CtaBest c = best[(size_t)p * nrb + i];
-        if (c.val > bv || (c.val == bv && c.idx < bi)) { bv = c.val; bi = c.idx; bb = i; }
+        top2_merge<double>(bv, bi, b2, c.val, c.idx, c.second);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const double o2 = __shfl_xor_sync(0xffffffffu, b2, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        const int ob = __shfl_xor_sync(0xffffffffu, bb, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bb = ob; }
+        top2_merge<double>(bv, bi, b2, ov, oi, o2);
     }
-    double ru = 0.0;
-    for (int i = threadIdx.x; i < nrb; i += 32)
-        if (i != bb) ru = fmax(ru, best[(size_t)p * nrb + i].val);
+    // frame coordinates of the peak (the index was formed in the original strip's C order)
+    const int cy = swap ? bi % Sh : bi / Sw, cx = swap ? bi / Sh : bi % Sw;
+    float ru = 0.f;
+    const float* rm = rowmax + (size_t)p * Sh;
+    for (int y = threadIdx.x; y < Sh; y += 32) {
+        int d = y - cy;
+        if (d < 0) d = -d;
+        if (d > 1 && d < Sh - 1) ru = fmaxf(ru, rm[y]);
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ru = fmax(ru, __shfl_xor_sync(0xffffffffu, ru, o));
+    for (int o = 16; o > 0; o >>= 1) ru = fmaxf(ru, __shfl_xor_sync(0xffffffffu, ru, o));
     if (threadIdx.x == 0) {
-        // frame coordinates of the peak (the index was formed in the original strip's C order)
-        out[p].coarse_y = swap ? bi % Sh : bi / Sw;
-        out[p].coarse_x = swap ? bi / Sh : bi % Sw;
+        out[p].coarse_y = cy;
+        out[p].coarse_x = cx;
         out[p].peak = (float)bv;
-        out[p].runner_up = (float)ru;
+        out[p].second = (float)fmax(b2, 0.0);
+        out[p].runner_up = ru;
         out[p].fine_y = out[p].fine_x = -1;
-        out[p].fine_peak = 0.f;
+        out[p].fine_peak = out[p].fine_second = 0.f;
     }
 }
 
@@ -589,30 +634,32 @@ __global__ void __launch_bounds__(256) updft_cols_kernel(int Sh, int rs, const t
     }
 }
 
-// first maximum (C order) of the rs x rs window; one warp per pair
+// first maximum (C order) of the rs x rs window and the second-largest value (near-tie test); one warp per pair
 __global__ void __launch_bounds__(32) updft_final_kernel(int rs, int swap, const double* __restrict__ mag2, float inv_n,
                                                          const int* __restrict__ nonzero, PeakOut* __restrict__ peaks) {
     const int p = blockIdx.x;
     if (nonzero[p] != 3) {                       // zero cross-power: the upsampled window is all zero -> index 0
-        if (threadIdx.x == 0) { peaks[p].fine_y = peaks[p].fine_x = 0; peaks[p].fine_peak = 0.f; }
+        if (threadIdx.x == 0) { peaks[p].fine_y = peaks[p].fine_x = 0; peaks[p].fine_peak = peaks[p].fine_second = 0.f; }
         return;
     }
-    double bv = -1.0;
+    double bv = -1.0, b2 = -1.0;
     int bi = 0x7fffffff;
     for (int o = threadIdx.x; o < rs * rs; o += 32) {
         const int v = o / rs, u = o - v * rs;            // mag2 is [v][u] in the frame; original order is [u][v] when swapped
-        best_update<double>(bv, bi, mag2[(size_t)p * rs * rs + o], swap ? u * rs + v : o);
+        top2_update<double>(bv, bi, b2, mag2[(size_t)p * rs * rs + o], swap ? u * rs + v : o);
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, bv, s);
+        const double o2 = __shfl_xor_sync(0xffffffffu, b2, s);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
-        best_update<double>(bv, bi, ov, oi);
+        top2_merge<double>(bv, bi, b2, ov, oi, o2);
     }
     if (threadIdx.x == 0) {
         peaks[p].fine_y = swap ? bi % rs : bi / rs;      // frame coordinates again
         peaks[p].fine_x = swap ? bi / rs : bi % rs;
         peaks[p].fine_peak = (float)(sqrt(bv) * (double)inv_n);
+        peaks[p].fine_second = (float)(sqrt(fmax(b2, 0.0)) * (double)inv_n);
     }
 }
 
@@ -825,6 +872,7 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     const size_t o_T = carve((size_t)B * rs * Sh * sizeof(T2));
     const size_t o_best = carve((size_t)B * nrb_inv * sizeof(CtaBest));
     const size_t o_mag = carve((size_t)B * rs * rs * sizeof(double));
+    const size_t o_rmax = carve((size_t)B * Sh * sizeof(float));
     const size_t way_bytes = off;                           // everything above exists once per concurrent sub-batch
     off = way_bytes * ways;
     const size_t o_peaks = carve((size_t)n * sizeof(PeakOut));
@@ -840,6 +888,7 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     T2* Tm = (T2*)(w + o_T);
     CtaBest* best = (CtaBest*)(w + o_best);
     double* mag2 = (double*)(w + o_mag);
+    float* rowmax = (float*)(w + o_rmax);
     PeakOut* peaks = (PeakOut*)(w + o_peaks);
     PairDesc* d_pairs = (PairDesc*)(w + o_pairs);
     int* d_nz = (int*)(w + o_nz);
@@ -888,10 +937,11 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
         T2 *Eyw = (T2*)((uint8_t*)Ey + wo), *Tw = (T2*)((uint8_t*)Tm + wo);
         CtaBest* bestw = (CtaBest*)((uint8_t*)best + wo);
         double* magw = (double*)((uint8_t*)mag2 + wo);
+        float* rmaxw = (float*)((uint8_t*)rowmax + wo);
         k1<<<nb * nrb_fwd, 256, smem_x, ws>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, swap, maxval, tw_x, px_plan, cx, cxn, Zw, d_nz + p0);
         k2<<<nb * ncg, 256, smem_y, ws>>>(Sh, Sw, ncg, tw_y, py_plan, cy, cyn, Zw, Rw);
-        k3<<<nb * nrb_inv, 256, smem_x, ws>>>(Sh, Sw, lpbx, nrb_inv, swap, tw_x, px_plan, cx, cxn, Zw, bestw);
-        peak_final_kernel<<<nb, 32, 0, ws>>>(bestw, nrb_inv, Sh, Sw, swap, d_nz + p0, peaks + p0);
+        k3<<<nb * nrb_inv, 256, smem_x, ws>>>(Sh, Sw, lpbx, nrb_inv, swap, tw_x, px_plan, cx, cxn, Zw, bestw, rmaxw);
+        peak_final_kernel<<<nb, 32, 0, ws>>>(bestw, nrb_inv, Sh, Sw, swap, rmaxw, d_nz + p0, peaks + p0);
         ctx->launches += 4;
         if (uf > 1) {
             updft_twiddle_kernel<T><<<dim3(8, nb), 256, 0, ws>>>(peaks + p0, Sh, Sw, uf, rs, dftshift, Exw, Eyw);
@@ -953,8 +1003,10 @@ void finish_pair(const PeakOut& pk_frame, const GroupGeom& g, int dir, int uf, s
     r->fine[0] = uf > 1 ? pk.fine_y : -1;
     r->fine[1] = uf > 1 ? pk.fine_x : -1;
     r->peak = pk.peak;
+    r->second = pk.second;
     r->runner_up = pk.runner_up;
     r->fine_peak = pk.fine_peak;
+    r->fine_second = uf > 1 ? pk.fine_second : 0.f;
 }
 
 // upload (host) or adopt (device) the unique tiles of a job and compute their min/max
@@ -1108,18 +1160,32 @@ static int reg_complete(sb_ctx* ctx, Lane* lane, RegPending& pr) {
         std::vector<PeakOut> res(pr.h_peaks + grp.first, pr.h_peaks + grp.first + grp.ids.size());
         std::vector<int> prec(grp.ids.size(), first_prec);
         if (job->precision == SB_PREC_AUTO) {
-            // A peak that does not stand clear of the correlation noise floor (rms 1/sqrt(N), expected
-            // maximum ~ sqrt(2 ln N / N)) is an argmax among near-equal values: redo those in float64,
-            // the arithmetic the reference uses.
+            // Two reasons to repeat a pair in float64, the arithmetic the reference uses:
+            //  (1) low confidence -- the peak does not stand clear of the correlation noise floor (rms 1/sqrt(N), expected
+            //      maximum ~ sqrt(2 ln N / N)) or of the best value outside its own band of rows: an argmax among
+            //      near-equal noise values;
+            //  (2) a near-tie -- the second-largest |cc| (typically the neighbouring pixel of a half-pixel shift) or the
+            //      second-largest value of the upsampled window is within kTie (relative) of the maximum.  The float32
+            //      chain is accurate to ~1e-6 of the peak (FFT error eps * sqrt(log2 N) per element, averaged over N
+            //      unit-magnitude bins), so a margin above 1e-4 cannot be reversed by the arithmetic; below it float32
+            //      and complex128 may pick different indices, and after the reference's half-even round() a different
+            //      integer shift.
             const double N = (double)g.Sh * g.Sw;
             const double floor_max = std::sqrt(2.0 * std::log(N) / N);
+            constexpr float kTie = 1e-4f;
             std::vector<PairDesc> redo;
             std::vector<int> redo_k;
-            for (size_t k = 0; k < grp.ids.size(); ++k)
-                if (!(res[k].peak > 4.0 * floor_max) || !(res[k].peak > 1.5f * res[k].runner_up)) {
+            for (size_t k = 0; k < grp.ids.size(); ++k) {
+                const PeakOut& q = res[k];
+                const bool zero = q.peak == 0.f && q.second == 0.f;      // identically zero strip (peak_final_kernel): cc == 0 exactly
+                const bool low = !(q.peak > 4.0 * floor_max) || !(q.peak > 1.5f * q.runner_up);
+                const bool tie_c = !(q.peak - q.second > kTie * q.peak);
+                const bool tie_f = job->upsample_factor > 1 && !(q.fine_peak - q.fine_second > kTie * q.fine_peak);
+                if (!zero && (low || tie_c || tie_f)) {
                     redo.push_back(grp.pd[k]);
                     redo_k.push_back((int)k);
                 }
+            }
             if (!redo.empty()) {
                 std::vector<PeakOut> res2(redo.size());
                 int rc = run_group<double>(ctx, lane, redo, g, W, pr.d_mm, job->upsample_factor, pr.maxval, res2.data(), true);
@@ -1219,5 +1285,45 @@ int sb_normalize_impl(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, in
     SB_CUDA(ctx, cudaGetLastError());
     if (mem == SB_MEM_HOST) SB_CUDA(ctx, cudaMemcpyAsync(out, d_out, px * 2 * n_tiles, cudaMemcpyDeviceToHost, st));
     SB_CUDA(ctx, cudaStreamSynchronize(st));
+    return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ self-test (test hook)
+// Exhaustive proof that the integer stretch fused into the strip load (stretch_px) equals the float64 expression of
+// normalize_image (stretch_px_f64, stitcher_process.py:844-855) for EVERY pixel value and tile range: all pairs
+// a = v - min, b = max - min with 0 <= a <= b, 1 <= b <= maxval (2^31 pairs for uint16).
+namespace {
+__global__ void __launch_bounds__(256) selftest_stretch_kernel(int maxval, unsigned long long* __restrict__ res) {
+    const int b = blockIdx.x + 1;
+    const float inv = (float)maxval / (float)b;                         // as rows_fwd_kernel forms it
+    unsigned long long bad = 0, first = ~0ull;
+    for (int a = threadIdx.x; a <= b; a += blockDim.x) {
+        const int fast = stretch_px((unsigned)a, 0, b, inv, maxval), ref = stretch_px_f64((unsigned)a, 0, b, maxval);
+        if (fast != ref) {
+            ++bad;
+            const unsigned long long key = ((unsigned long long)b << 32) | (unsigned)a;
+            first = key < first ? key : first;
+        }
+    }
+    if (bad) {
+        atomicAdd(res + 1, bad);
+        atomicMin(res + 2, first);
+    }
+}
+}  // namespace
+
+int sb_selftest_stretch_impl(sb_ctx* ctx, int maxval, uint64_t* out) {
+    SB_CHECK(ctx, maxval == 255 || maxval == 65535, "selftest: maxval must be 255 or 65535");
+    Lane* lane = sb_lane(ctx, 0);
+    int rc = sb_reserve(ctx, lane->work, 64);
+    if (rc) return rc;
+    unsigned long long init[3] = {0ull, 0ull, ~0ull};
+    SB_CUDA(ctx, cudaMemcpyAsync(lane->work.p, init, sizeof(init), cudaMemcpyHostToDevice, lane->stream));
+    selftest_stretch_kernel<<<maxval, 256, 0, lane->stream>>>(maxval, (unsigned long long*)lane->work.p);
+    ctx->launches++;
+    SB_CUDA(ctx, cudaGetLastError());
+    SB_CUDA(ctx, cudaMemcpyAsync(out, lane->work.p, 24, cudaMemcpyDeviceToHost, lane->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(lane->stream));
+    out[0] = (uint64_t)maxval * ((uint64_t)maxval + 3) / 2;            // sum over b of (b + 1)
     return SB_OK;
 }

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SB_ABI_VERSION 1
+#define SB_ABI_VERSION 2
 
 typedef struct sb_ctx sb_ctx;
 
@@ -169,8 +169,13 @@ typedef struct sb_pair_result {
     double shift[2];          /* skimage's float64 sub-pixel shift (row, col), rebuilt from indices */
     int32_t coarse[2];        /* argmax |ifft2(P)| (row, col), first maximum in C order             */
     int32_t fine[2];          /* argmax of the upsampled-DFT window (row, col); -1 if upsample == 1 */
-    float peak, runner_up;    /* |cc| at the coarse peak and the best value outside its 3x3 neighbourhood */
-    float fine_peak;
+    float peak;               /* |cc| at the coarse peak                                                        */
+    float second;             /* second-largest |cc| at any other pixel (for a half-pixel shift: the neighbour) */
+    float runner_up;          /* largest |cc| outside the band of three lines centred on the peak, the lines
+                                 being positions along the strip's LONG axis (image rows for horizontal pairs,
+                                 image columns for vertical pairs), wrapping around: a confidence measure      */
+    float fine_peak;          /* |.| at the maximum of the upsampled-DFT window (0 if upsample == 1)             */
+    float fine_second;        /* second-largest value of that window                                            */
     int32_t ref_min, ref_max, mov_min, mov_max;   /* whole-tile min/max used by normalize_image     */
     int32_t precision;        /* SB_PREC_F32 or SB_PREC_F64: arithmetic that produced this result   */
 } sb_pair_result;
@@ -184,7 +189,11 @@ typedef struct sb_register_job {
     int32_t max_overlap_x;    /* strip width of horizontal pairs (max_x_overlap, :608) */
     int32_t max_overlap_y;    /* strip height of vertical pairs (max_y_overlap, :609)  */
     int32_t upsample_factor;  /* reference: 10 (:684, :707) */
-    int32_t precision;        /* SB_PREC_* ; AUTO = f32, pairs with a thin peak margin redone in f64 */
+    int32_t precision;        /* SB_PREC_* ; AUTO = f32, then pairs are repeated in f64 (the reference's arithmetic)
+                                 when (a) peak <= 4 x the expected noise maximum sqrt(2 ln N / N) or peak <=
+                                 1.5 x runner_up (low confidence), or (b) peak - second <= 1e-4 peak, or
+                                 fine_peak - fine_second <= 1e-4 fine_peak (near-tie: float32 could pick another
+                                 index than complex128).  sb_pair_result.precision says which arithmetic won. */
     int32_t lane;             /* stream to run on (ordered after that lane's earlier copies); the call
                                  still returns only when the results are on the host                  */
 } sb_register_job;
@@ -222,6 +231,16 @@ int sb_estimate_flatfield(sb_ctx* ctx, const void* const* tiles, int32_t n_tiles
 int64_t sb_pyramid_elems(int32_t n_planes, int32_t height, int32_t width, int32_t n_levels);
 int sb_pyramid(sb_ctx* ctx, const void* src, int src_mem, int32_t n_planes, int32_t height, int32_t width,
                int64_t src_row_pitch, int dtype, int32_t n_levels, void* out, int out_mem, int lane);
+
+/* ------------------------------------------------------------------ test hook
+ * Exhaustive on-device proofs of the two primitives whose exactness the parity claims rest on (tests/test_exhaustive_gpu.py):
+ *   SB_SELFTEST_STRETCH, arg = 255 | 65535: the integer form of normalize_image (:844-855) fused into the strip load
+ *       equals the float64 expression for every (v - min, max - min) pair of that pixel range;
+ *   SB_SELFTEST_DIVIDE, arg = e in [-5, 19]: the packed float32 divide + truncation / rounding of the paste kernels
+ *       equals IEEE a / b and trunc(clip(.)) (:838-841) for every uint16 a and every float32 b in [2^e, 2^(e+1)).
+ * out[0] = cases checked, out[1] = mismatches, out[2] = smallest mismatching case key (or ~0). */
+enum { SB_SELFTEST_STRETCH = 0, SB_SELFTEST_DIVIDE = 1 };
+int sb_selftest(sb_ctx* ctx, int which, int64_t arg, uint64_t* out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,41 @@
+"""Exhaustive on-device proofs of the two primitives the bit-exactness claims rest on.
+
+* ``stretch_px`` -- the integer form of ``normalize_image`` (stitcher_process.py:844-855) that the registration
+  kernels fuse into the strip load -- against the float64 expression, for EVERY (v - min, max - min) pair;
+* ``div2_rn`` + ``trunc_sat_pack`` / ``round_sat_pack`` -- the packed float32 divide and truncation of the paste kernels
+  (``apply_flatfield_correction``, :828-842) -- against IEEE ``a / b`` and ``trunc(clip(.))`` for every uint16 numerator
+  and every float32 flat value of a binade, at the two ends of the accepted field range and around 1."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from image_stitcher_b200 import _ffi
+    c = _ffi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("maxval", [255, 65535])
+def test_integer_stretch_equals_float64_for_every_pixel_and_range(ctx, maxval):
+    checked, bad, first = ctx.selftest(0, maxval)
+    assert checked == maxval * (maxval + 3) // 2              # 2 147 581 950 pairs for uint16
+    assert bad == 0, f"{bad} mismatches, first at b={first >> 32}, a={first & 0xffffffff}"
+
+
+@pytest.mark.parametrize("expo", [-5, -1, 0, 19])
+def test_packed_divide_equals_ieee_for_every_numerator_and_mantissa(ctx, expo):
+    checked, bad, first = ctx.selftest(1, expo)
+    assert checked == (1 << 23) * 65536
+    assert bad == 0, f"{bad} mismatches, first at mantissa={first >> 16}, a={first & 0xffff}"
+
+
+def test_selftest_rejects_unknown_requests(ctx):
+    with pytest.raises(RuntimeError):
+        ctx.selftest(7, 0)
+    with pytest.raises(RuntimeError):
+        ctx.selftest(0, 1000)
+    with pytest.raises(RuntimeError):
+        ctx.selftest(1, -9)

@@ -35,7 +35,7 @@ def test_library_loads_and_exports_every_header_symbol():
     missing = [s for s in _header_functions() if not hasattr(lib, s)]
     assert not missing, missing
     h = _ffi.load_library()
-    assert h.sb_version() == 1
+    assert h.sb_version() == 2
     assert h.sb_canvas_pitch(3891) == 3904 and h.sb_canvas_pitch(64) == 64
     assert h.sb_chunked_plane_elems(3891, 3891, 2048, 2048) == 4 * 2048 * 2048
 
