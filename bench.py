@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the host-buffer leg (default min(steps, 2))")
     ap.add_argument("--host-wells", type=int, default=6, help="distinct wells kept in pinned host memory for e2e")
     ap.add_argument("--fuse-lanes", type=int, default=3, help="library lanes (streams) the per-well fusion launches rotate over")
+    ap.add_argument("--per-well-fusion", action="store_true",
+                    help="one sb_fuse_region launch per well (round-1 behaviour) instead of one sb_fuse_regions launch per plate")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-wells", type=int, default=0, help="wells in the CPU sample (0 = one per host core)")
@@ -246,7 +248,7 @@ def workload_name(spec, use_flat, blend):
 def run_b200(args, rank, world, local_rank):
     import torch
     from image_stitcher_b200 import _ffi
-    from image_stitcher_b200.plate import FusePlan, PlateSpec, make_plate, well_fuse_tiles, well_pairs
+    from image_stitcher_b200.plate import FuseBatchPlan, FusePlan, PlateSpec, make_plate, well_fuse_tiles, well_pairs
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; the hot path has no CPU fallback")
@@ -302,6 +304,7 @@ def run_b200(args, rank, world, local_rank):
         all_pairs += well_pairs(spec, dev_ptr(w))[0]
     n_pairs = len(all_pairs)
     px_per_step = spec.wells * planes * Hc * Wc
+    batch = None if args.per_well_fusion else FuseBatchPlan(ctx, plans)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     reg_ms, fuse_ms = [], []
@@ -313,14 +316,17 @@ def run_b200(args, rank, world, local_rank):
         e0.record(stream)
         last_reg = ctx.register_pairs(all_pairs, (spec.tile_h, spec.tile_w), ovx, ovy, mem=_ffi.SB_MEM_DEVICE, lane=0)
         e1.record(stream)
-        for st_ in streams[1:]:
-            st_.wait_event(e1)                           # fork: the other lanes start after registration
-        for i, p in enumerate(plans):
-            p.run(i % nl)
-        for st_ in streams[1:]:                          # join: lane 0 waits for the other lanes' last launch
-            j = torch.cuda.Event()
-            j.record(st_)
-            stream.wait_event(j)
+        if batch is not None:
+            batch.run(0)                                 # every well of the plate in one launch, channel by channel
+        else:
+            for st_ in streams[1:]:
+                st_.wait_event(e1)                       # fork: the other lanes start after registration
+            for i, p in enumerate(plans):
+                p.run(i % nl)
+            for st_ in streams[1:]:                      # join: lane 0 waits for the other lanes' last launch
+                j = torch.cuda.Event()
+                j.record(st_)
+                stream.wait_event(j)
         e2.record(stream)
         if record is not None:
             record.append((e0, e1, e2))
@@ -381,12 +387,16 @@ def run_b200(args, rank, world, local_rank):
         with open(tpath) as f:
             tj = json.load(f)
         traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
-    n_fuse = spec.wells * args.steps
+    wells_per_launch = spec.wells if batch is not None else 1
+    n_fuse = (1 if batch is not None else spec.wells) * args.steps
     fuse_launch_ms = fuse_sum / n_fuse
     if args.blend == "paste":
         alg_bytes = 4.0 * planes * Hc * Wc                      # 2 B winning source px + 2 B written, all px covered
     else:
         alg_bytes = 2.0 * spec.tiles_per_well * spec.tile_h * spec.tile_w + 2.0 * planes * Hc * Wc
+    alg_bytes *= wells_per_launch
+    if traffic is not None:
+        traffic *= wells_per_launch
     achieved = alg_bytes / (fuse_launch_ms * 1e-3) / 1e9
     Sh_h, Sw_h = spec.tile_h - 2 * int(spec.tile_h * 0.25), ovx
     reg_bytes = spec.wells * (spec.rows * spec.cols * 2.0 * spec.tile_h * spec.tile_w) + n_pairs * 4.0 * Sh_h * Sw_h
@@ -415,6 +425,7 @@ def run_b200(args, rank, world, local_rank):
                      "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": "profiles/fusion_traffic.json (ncu --set full, per launch)" if traffic else None,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fuse_launch_ms,
+                     "regions_per_launch": wells_per_launch,
                      "frac_of_spec_8000": achieved / 8000.0},
         "roofline_registration": {"bound": "hbm", "achieved": reg_achieved, "peak": peak_gbs, "unit": "GB/s",
                                   "frac": reg_achieved / peak_gbs, "algorithmic_bytes_per_step": reg_bytes},

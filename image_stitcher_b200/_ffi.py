@@ -28,7 +28,7 @@ EXPORTS = [
     "sb_version", "sb_create", "sb_destroy", "sb_last_error", "sb_kernel_launches", "sb_num_lanes",
     "sb_device_sm_count", "sb_host_alloc", "sb_host_free", "sb_device_alloc", "sb_device_free",
     "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_memcpy_async", "sb_set_flatfield", "sb_set_darkfield", "sb_clear_fields",
-    "sb_flatfield_apply", "sb_fuse_region", "sb_sync", "sb_lane_mark", "sb_lane_wait_mark", "sb_set_lane_stream", "sb_canvas_pitch",
+    "sb_flatfield_apply", "sb_fuse_region", "sb_fuse_regions", "sb_sync", "sb_lane_mark", "sb_lane_wait_mark", "sb_set_lane_stream", "sb_canvas_pitch",
     "sb_chunked_plane_elems", "sb_register_pairs", "sb_register_pairs_async", "sb_normalize",
     "sb_pyramid_elems", "sb_pyramid", "sb_estimate_flatfield", "sb_selftest",
 ]
@@ -106,6 +106,7 @@ def load_library(path: Optional[str] = None):
     lib.sb_clear_fields.argtypes = [vp]
     lib.sb_flatfield_apply.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, i32]
     lib.sb_fuse_region.argtypes = [vp, C.POINTER(SbFuseJob), i32]
+    lib.sb_fuse_regions.argtypes = [vp, C.POINTER(SbFuseJob), i32, i32]
     lib.sb_sync.argtypes = [vp, i32]
     lib.sb_set_lane_stream.argtypes = [vp, i32, vp]
     lib.sb_lane_mark.argtypes = [vp, i32]
@@ -278,6 +279,32 @@ class Context:
                         int(bool(apply_flatfield)), int(blend), int(blend_ov[0]), int(blend_ov[1]),
                         _ptr(out), out_mem, layout, int(out_row_pitch), int(chunk[0]), int(chunk[1]))
         self._check(self.lib.sb_fuse_region(self.handle, C.byref(job), lane), "sb_fuse_region")
+
+    def fuse_regions(self, jobs: Sequence[dict], *, lane=-1):
+        """``sb_fuse_regions``: every element of ``jobs`` holds the keyword arguments of :meth:`fuse_region`
+        (``tiles``, ``tile_shape``, ``canvas_shape``, ``out`` ...).  Regions of one geometry in device memory are fused by
+        one launch; anything else region by region."""
+        arrs, cjobs = [], []
+        for kw in jobs:
+            kw = dict(kw)
+            tiles = kw.pop("tiles")
+            n = len(tiles)
+            arr = (SbTile * max(n, 1))()
+            for i, (px, x, y, c, z, ct, cb, cl, cr) in enumerate(tiles):
+                arr[i] = SbTile(_ptr(px), int(x), int(y), int(c), int(z), int(ct), int(cb), int(cl), int(cr))
+            arrs.append(arr)
+            ts, cs, out = kw.pop("tile_shape"), kw.pop("canvas_shape"), kw.pop("out")
+            dtype = kw.get("dtype")
+            if dtype is None:
+                dtype = _pixel_dtype(tiles[0][0] if n else out, _pixel_dtype(out))
+            bo, ch = kw.get("blend_ov", (0, 0)), kw.get("chunk", (0, 0))
+            cjobs.append(SbFuseJob(arr, n, int(ts[0]), int(ts[1]), int(dtype), kw.get("tile_mem", SB_MEM_HOST), int(cs[0]), int(cs[1]),
+                                   int(cs[2]), int(cs[3]), int(bool(kw.get("apply_flatfield", False))),
+                                   int(kw.get("blend", SB_BLEND_PASTE)), int(bo[0]), int(bo[1]), _ptr(out),
+                                   kw.get("out_mem", SB_MEM_HOST), kw.get("layout", SB_LAYOUT_ROWMAJOR),
+                                   int(kw.get("out_row_pitch", 0)), int(ch[0]), int(ch[1])))
+        cj = (SbFuseJob * max(len(cjobs), 1))(*cjobs)
+        self._check(self.lib.sb_fuse_regions(self.handle, cj, len(cjobs), lane), "sb_fuse_regions")
 
     # ------------------------------------------------------------------ registration
     def device_alloc(self, nbytes: int) -> int:

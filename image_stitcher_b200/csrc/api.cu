@@ -318,6 +318,27 @@ int sb_fuse_region(sb_ctx* ctx, const sb_fuse_job* job, int lane) {
     return rc;
 }
 
+int sb_fuse_regions(sb_ctx* ctx, const sb_fuse_job* jobs, int32_t n_jobs, int lane) {
+    if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
+    if (lane >= SB_NUM_LANES) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
+    if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return sb_fail(ctx, SB_ERR_INVALID, "bad job list");
+    if (n_jobs == 0) return SB_OK;
+    if (n_jobs > 1) {
+        bool batched = false;
+        const int rc = sb_fuse_regions_impl(ctx, jobs, n_jobs, lane, &batched);
+        if (rc || batched) {
+            sb_lane(ctx, lane < 0 ? 0 : lane)->resident = ResidentCanvas();
+            return rc;
+        }
+    }
+    for (int j = 0; j < n_jobs; ++j) {                     // not one geometry / not device-resident: region by region
+        const int rc = sb_fuse_region(ctx, &jobs[j], lane);
+        if (rc) return rc;
+    }
+    return SB_OK;
+}
+
 int sb_estimate_flatfield(sb_ctx* ctx, const void* const* tiles, int32_t n_tiles, int32_t tile_h, int32_t tile_w, int dtype,
                           int mem, int32_t grid, double sigma, float* field_out, int out_mem) {
     if (!ctx) return SB_ERR_INVALID;

@@ -116,74 +116,6 @@ __device__ __forceinline__ void pass_radix2(const T2* __restrict__ a, T2* __rest
     }
 }
 
-#ifdef SB_FFT_RADIX16
-// EXPERIMENTAL (round-2 groundwork, off by default, never run on a GPU yet): radix-16 Stockham pass with the butterfly
-// built from two radix-4 stages in registers -- r = 4 r1 + r2, q = q1 + 4 q2:
-//     y[r2][q1] = sum_r1 x[4 r1 + r2] W4^(r1 q1);   y[r2][q1] *= W16^(r2 q1);   X[q1 + 4 q2] = sum_r2 y[r2][q1] W4^(r2 q2)
-// (algebra and shared-memory write conflicts pinned by scratch/stockham_radix16.py: a 1024-point line as 4 . 16 . 16 costs
-// 768 wavefronts and 3 barriers against 1024 and 5 for 4^5).  One thread per (line, butterfly): a line has only N / 16
-// butterflies, so the twiddles are not shared between lines.  Compile check (-DSB_FFT_RADIX16): under the 80-register cap
-// of 3 blocks per SM the 16 complex values spill (cols_xpower_kernel<float, 2>: 320 bytes) -- try it with SB_REG_CTAS=2 or a
-// per-kernel cap first.
-template <typename T2>
-__device__ __forceinline__ void dft4_inplace(T2& a, T2& b, T2& c, T2& d, bool inverse) {
-    const T2 s02 = mk2<T2>(a.x + c.x, a.y + c.y), d02 = mk2<T2>(a.x - c.x, a.y - c.y);
-    const T2 s13 = mk2<T2>(b.x + d.x, b.y + d.y), d13 = mk2<T2>(b.x - d.x, b.y - d.y);
-    a = mk2<T2>(s02.x + s13.x, s02.y + s13.y);
-    c = mk2<T2>(s02.x - s13.x, s02.y - s13.y);
-    if (!inverse) {                                  // q = 1: d02 - i d13, q = 3: d02 + i d13 (as in pass_radix4)
-        b = mk2<T2>(d02.x + d13.y, d02.y - d13.x);
-        d = mk2<T2>(d02.x - d13.y, d02.y + d13.x);
-    } else {
-        b = mk2<T2>(d02.x - d13.y, d02.y + d13.x);
-        d = mk2<T2>(d02.x + d13.y, d02.y - d13.x);
-    }
-}
-
-template <typename T2>
-__device__ __forceinline__ void pass_radix16(const T2* __restrict__ a, T2* __restrict__ b, const T2* __restrict__ tw, int N, int Ns,
-                                             int M, int tstep, unsigned mM, unsigned mNs, int nlines, bool inverse) {
-    using T = decltype(T2::x);
-    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, hh = (T)0.70710678118654752440;
-    const T sg = inverse ? (T)1 : (T)-1;             // sign of the imaginary part: forward W16^m = exp(-2 pi i m / 16)
-    const T2 w1 = mk2<T2>(c1, sg * s1), w2 = mk2<T2>(hh, sg * hh), w3 = mk2<T2>(s1, sg * c1);
-    const T2 w6 = mk2<T2>(-hh, sg * hh), w9 = mk2<T2>(-c1, -sg * s1);
-    const int items = M * nlines;
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int l = fastdiv(it, mM), j = it - l * M;
-        const int jq = fastdiv(j, mNs), k = j - jq * Ns;
-        const T2* in = a + (size_t)l * N + j;
-        const int ks = k * tstep;
-        T2 x[16];
-        x[0] = in[0];
-#pragma unroll
-        for (int r = 1; r < 16; ++r) {
-            T2 w = tw[r * ks];
-            if (inverse) w.y = -w.y;
-            x[r] = cmul(in[r * M], w);
-        }
-#pragma unroll
-        for (int r2 = 0; r2 < 4; ++r2) dft4_inplace(x[r2], x[4 + r2], x[8 + r2], x[12 + r2], inverse);   // x[4 q1 + r2] = y[r2][q1]
-        x[5] = cmul(x[5], w1);
-        x[6] = cmul(x[6], w2);
-        x[7] = cmul(x[7], w3);
-        x[9] = cmul(x[9], w2);
-        x[10] = inverse ? mk2<T2>(-x[10].y, x[10].x) : mk2<T2>(x[10].y, -x[10].x);                     // W16^4 = -+i
-        x[11] = cmul(x[11], w6);
-        x[13] = cmul(x[13], w3);
-        x[14] = cmul(x[14], w6);
-        x[15] = cmul(x[15], w9);
-#pragma unroll
-        for (int q1 = 0; q1 < 4; ++q1) dft4_inplace(x[4 * q1], x[4 * q1 + 1], x[4 * q1 + 2], x[4 * q1 + 3], inverse);  // x[4 q1 + q2] = X[q1 + 4 q2]
-        T2* out = b + (size_t)l * N + jq * Ns * 16 + k;
-#pragma unroll
-        for (int q1 = 0; q1 < 4; ++q1)
-#pragma unroll
-            for (int q2 = 0; q2 < 4; ++q2) out[(q1 + 4 * q2) * Ns] = x[4 * q1 + q2];
-    }
-}
-#endif  // SB_FFT_RADIX16
-
 template <typename T2, int LB, int QT>
 __device__ __forceinline__ void pass_generic(const T2* __restrict__ a, T2* __restrict__ b, const T2* __restrict__ tw, int N, int Ns,
                                              int R, int groups, bool inverse) {
@@ -556,9 +488,6 @@ __device__ T2* fft_lines(T2* buf0, T2* buf1, const T2* __restrict__ tw, const Ff
         bool in_place = false;
         if (R == 4) pass_radix4<T2, LB>(a, b, tw, N, Ns, plan.M[f], plan.tstep[f], plan.mM[f], plan.mNs[f], groups, inverse);
         else if (R == 2) pass_radix2<T2, LB>(a, b, tw, N, Ns, plan.M[f], plan.tstep[f], plan.mM[f], plan.mNs[f], groups, inverse);
-#ifdef SB_FFT_RADIX16
-        else if (R == 16) pass_radix16<T2>(a, b, tw, N, Ns, plan.M[f], plan.tstep[f], plan.mM[f], plan.mNs[f], nlines, inverse);
-#endif
         else if (ctab != nullptr && R == plan.gemm_radix && (nlines & 3) == 0 &&
                  OddGemm<T2>::run(a, b, tw, ctab, N, Ns, R, nlines, inverse)) in_place = true;
         else if (R & 1) pass_odd_sym<T2, LB, (sizeof(T2) == 8 ? (LB >= 4 ? 4 : 8) : (LB >= 4 ? 2 : 4))>(a, b, tw, N, Ns, R, groups, inverse);

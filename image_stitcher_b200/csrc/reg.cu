@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(32) updft_final_kernel(int rs, int swap, const
 
 // ------------------------------------------------------------------------------------------ host side
 
-FftPlan make_plan(int n, bool allow16 = false) {
+FftPlan make_plan(int n) {
     // prime factors, twos merged into fours, largest radix first (the order is free for Stockham)
     std::vector<int> f;
     int m = n, twos = 0;
@@ -673,22 +673,9 @@ FftPlan make_plan(int n, bool allow16 = false) {
     for (int p = 3; (long long)p * p <= m; p += 2)
         while (m % p == 0) { f.push_back(p); m /= p; }
     if (m > 1) f.push_back(m);
-#ifdef SB_FFT_RADIX16
-    // EXPERIMENTAL: float32 lines with at least 2^6 take radix-16 passes AFTER a leading radix-4 pass (the first pass of a
-    // Stockham transform writes with stride R: 4-way conflicted for R = 4, 16-way for R = 16; scratch/stockham_radix16.py)
-    std::sort(f.begin(), f.end(), [](int a, int b) { return a > b; });
-    if (allow16 && twos >= 6) {
-        f.push_back(4);
-        for (twos -= 2; twos >= 4; twos -= 4) f.push_back(16);
-    }
-    for (; twos >= 2; twos -= 2) f.push_back(4);
-    if (twos) f.push_back(2);
-#else
-    (void)allow16;
     for (; twos >= 2; twos -= 2) f.push_back(4);
     if (twos) f.push_back(2);
     std::sort(f.begin(), f.end(), [](int a, int b) { return a > b; });
-#endif
     FftPlan pl;
     pl.n = n;
     pl.nfac = 0;
@@ -792,7 +779,7 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     const int swap = group_swapped(g) ? 1 : 0;
     const int Sh = swap ? g.Sw : g.Sh, Sw = swap ? g.Sh : g.Sw;
     const size_t strip = (size_t)Sh * Sw;
-    const FftPlan plan_x = make_plan(Sw, sizeof(T) == 4), plan_y = make_plan(Sh, sizeof(T) == 4);
+    const FftPlan plan_x = make_plan(Sw), plan_y = make_plan(Sh);
     const T2 *tw_x = nullptr, *tw_y = nullptr;
     int rc = get_twiddles<T>(ctx, Sw, &tw_x);
     if (rc) return rc;

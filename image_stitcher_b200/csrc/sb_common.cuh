@@ -57,9 +57,9 @@ struct Lane {
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // extra streams of the lane: registration sub-batches rotate over them
     cudaEvent_t aux_fork = nullptr, aux_join[3] = {nullptr, nullptr, nullptr};
     std::vector<int32_t> rect_pieces;   // cached rectangle decomposition of the rectangle-streaming paste kernel ...
-    uint64_t rect_sig = 0;              // ... and the geometry signature it was computed for
+    std::vector<int32_t> rect_key;      // ... and the geometry it was computed for (compared in full)
     std::vector<int32_t> blend_cells;   // cached cell decomposition of the blend modes (10 ints per cell) ...
-    uint64_t blend_sig = 0;             // ... and its geometry signature
+    std::vector<int32_t> blend_key;     // ... and its geometry
     std::vector<int32_t> perm;      // cached block-row order of the paste kernel (fuse.cu) ...
     uint64_t perm_sig = 0;          // ... and the geometry signature it was computed for
 };
@@ -100,6 +100,7 @@ static inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m 
 
 // entry points implemented in fuse.cu / reg.cu, called from api.cu
 int sb_fuse_region_impl(sb_ctx* ctx, const sb_fuse_job* job, int lane);
+int sb_fuse_regions_impl(sb_ctx* ctx, const sb_fuse_job* jobs, int n_jobs, int lane, bool* batched);
 int sb_flatfield_apply_impl(sb_ctx* ctx, int channel, const void* tiles, void* out, int n_tiles, int tile_h,
                             int tile_w, int dtype, int mem);
 // maxval: iinfo(dtype).max of the caller's pixels (65535, or 255 when the tiles were widened from uint8)

@@ -147,6 +147,20 @@ class FusePlan:
             self.ctx._check(rc, "sb_fuse_region")
 
 
+class FuseBatchPlan:
+    """The regions of a plate in ONE ``sb_fuse_regions`` call (prebuilt ctypes job array; the per-region plans are kept
+    alive because the jobs point into their tile arrays)."""
+
+    def __init__(self, ctx: _ffi.Context, plans: List[FusePlan]):
+        self.ctx, self.plans = ctx, list(plans)
+        self.jobs = (_ffi.SbFuseJob * max(len(self.plans), 1))(*[p.job for p in self.plans])
+
+    def run(self, lane: int = 0):
+        rc = self.ctx.lib.sb_fuse_regions(self.ctx.handle, self.jobs, len(self.plans), lane)
+        if rc != 0:
+            self.ctx._check(rc, "sb_fuse_regions")
+
+
 def well_fuse_tiles(spec: PlateSpec, tile_ptr, lattice: Optional[geo.Lattice] = None):
     """sb_tile tuples of one well in the reference's paste order.
 

@@ -136,6 +136,12 @@ typedef struct sb_fuse_job {
 /* lane < 0: run and wait.  lane in [0, sb_num_lanes): enqueue H2D -> kernels -> D2H on that
  * lane's stream and return; sb_sync(lane) waits.  Buffers must stay valid until then. */
 int sb_fuse_region(sb_ctx* ctx, const sb_fuse_job* job, int lane);
+/* Batched form for plates: n_jobs regions (wells) in one call.  When the regions share one geometry (same tile
+ * lattice, crops, canvas and layout -- true for the wells of a plate) and tiles and canvases are device memory, they
+ * are pasted by ONE kernel launch, channel by channel across the regions, so that a single flat-field is live in L2
+ * at a time (stitch_region is called once per region by the reference, :1990; the result per region is identical).
+ * Anything else is fused region by region, exactly like n_jobs calls of sb_fuse_region on that lane. */
+int sb_fuse_regions(sb_ctx* ctx, const sb_fuse_job* jobs, int32_t n_jobs, int lane);
 int sb_sync(sb_ctx* ctx, int lane);      /* lane < 0: all lanes */
 /* Cross-lane ordering for pipelines: sb_lane_mark records a marker at the current end of `lane`'s stream;
  * sb_lane_wait_mark makes everything enqueued on `lane` afterwards wait for `other`'s latest marker (no host wait).

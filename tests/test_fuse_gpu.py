@@ -309,3 +309,89 @@ def test_two_contexts_on_two_devices_in_one_process():
             c1.close()
     finally:
         c0.close()
+
+
+# ------------------------------------------------------------------------------------------ sb_fuse_regions (batched)
+def _plate_jobs(spec, plate, canvases, **kw):
+    from image_stitcher_b200 import _ffi
+    from image_stitcher_b200.plate import well_fuse_tiles
+    Wc, Hc = spec.canvas_size()
+    jobs = []
+    for w in range(spec.wells):
+        ptr = lambda r, c, ch, z, w=w: plate.pool[w, r, c, ch, z].data_ptr()
+        jobs.append(dict(tiles=well_fuse_tiles(spec, ptr), tile_shape=(spec.tile_h, spec.tile_w),
+                         canvas_shape=(spec.channels, spec.num_z, Hc, Wc), out=canvases[w], tile_mem=_ffi.SB_MEM_DEVICE,
+                         out_mem=_ffi.SB_MEM_DEVICE, dtype=_ffi.SB_U16, **kw))
+    return jobs
+
+
+@pytest.mark.parametrize("layout", ["rowmajor", "chunked"])
+def test_fuse_regions_batch_equals_region_by_region_and_oracle(ctx, layout):
+    """One launch over all wells (channel-major) == one sb_fuse_region per well == the oracle, bit for bit."""
+    import torch
+    from image_stitcher_b200 import _ffi
+    from image_stitcher_b200.plate import PlateSpec, make_plate
+    from oracle import stitch_ref as sr
+    spec = PlateSpec(wells=5, rows=3, cols=2, tile_h=192, tile_w=256, channels=3, num_z=2, jitter=2, seed=11)
+    plate = make_plate(spec, device="cuda:0")
+    ctx.clear_fields()
+    for c in (0, 2):                                             # channel 1 has no field: passes through
+        ctx.set_flatfield(c, plate.flat[c], mem=_ffi.SB_MEM_DEVICE)
+    Wc, Hc = spec.canvas_size()
+    planes = spec.channels * spec.num_z
+    if layout == "rowmajor":
+        pitch = _ffi.canvas_pitch(Wc)
+        shape, kw = (spec.wells, planes, Hc, pitch), {}
+    else:
+        ch, cw = 128, 256
+        ncy, ncx = -(-Hc // ch), -(-Wc // cw)
+        shape, kw = (spec.wells, planes, ncy, ncx, ch, cw), dict(layout=_ffi.SB_LAYOUT_CHUNKED, chunk=(ch, cw))
+    batch = torch.full(shape, 0x5A5A, dtype=torch.int16, device="cuda:0")
+    single = torch.full(shape, 0x1111, dtype=torch.int16, device="cuda:0")
+    torch.cuda.synchronize()
+    launches0 = ctx.kernel_launches
+    ctx.fuse_regions(_plate_jobs(spec, plate, batch, apply_flatfield=True, **kw))
+    assert ctx.kernel_launches - launches0 == 1                  # the whole batch is one kernel launch
+    for job in _plate_jobs(spec, plate, single, apply_flatfield=True, **kw):
+        tiles = job.pop("tiles"); ts = job.pop("tile_shape"); cs = job.pop("canvas_shape")
+        ctx.fuse_region(tiles, ts, cs, **job)
+    assert torch.equal(batch, single)
+    names = [f"ch{c}" for c in range(spec.channels)]
+    xs, ys = spec.stage_positions()
+    flats = {c: plate.flat[c].cpu().numpy() for c in (0, 2)}
+    for w in (0, spec.wells - 1):
+        host = plate.pool[w].cpu().numpy().view(np.uint16)
+        st = sr.RegionState(tile_h=spec.tile_h, tile_w=spec.tile_w, pixel_size_um=spec.pixel_size_um, num_z=spec.num_z,
+                            monochrome_channels=names, channel_names=names, apply_flatfield=True, flatfields=flats)
+        recs = []
+        for fov in sorted(range(spec.rows * spec.cols), key=str):
+            r, c = divmod(fov, spec.cols)
+            for z in range(spec.num_z):
+                for chn in range(spec.channels):
+                    recs.append(sr.TileRec(x_mm=xs[c], y_mm=ys[r], z_level=z, channel=names[chn], pixels=host[r, c, chn, z], fov=fov))
+        exp = sr.stitch_region(st, recs)[0].reshape(planes, Hc, Wc)
+        got = batch[w].cpu().numpy().view(np.uint16)
+        if layout == "chunked":
+            got = got.transpose(0, 1, 3, 2, 4).reshape(planes, ncy * ch, ncx * cw)
+            assert not got[:, Hc:].any() and not got[:, :, Wc:].any()          # edge chunks are zero padded
+        assert np.array_equal(got[:, :Hc, :Wc], exp)
+    ctx.clear_fields()
+
+
+def test_fuse_regions_falls_back_region_by_region(ctx):
+    """Regions with different geometry (or host memory) are not batched: same results as separate calls."""
+    rng = np.random.default_rng(21)
+    th, tw, C, Z, Hc, Wc = 64, 96, 1, 1, 200, 260
+    ctx.clear_fields()
+    jobs, exp = [], []
+    for k in range(3):
+        job = random_job(rng, 7, th, tw, C, Z, Hc, Wc)
+        out = np.zeros((1, C, Z, Hc, Wc), np.uint16)
+        ref = np.zeros_like(out)
+        ctx.fuse_region(job, (th, tw), (C, Z, Hc, Wc), out=ref)
+        jobs.append(dict(tiles=job, tile_shape=(th, tw), canvas_shape=(C, Z, Hc, Wc), out=out))
+        exp.append(ref)
+    ctx.fuse_regions(jobs)
+    for j, e in zip(jobs, exp):
+        assert np.array_equal(j["out"], e)
+    ctx.fuse_regions([])
