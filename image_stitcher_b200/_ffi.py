@@ -394,10 +394,10 @@ class Context:
         return out
 
     def selftest(self, which: int, arg: int):
-        """Test hook (``sb_selftest``): returns ``(cases_checked, mismatches, first_mismatch_key)``."""
+        """Test hook (``sb_selftest``): returns ``(cases_checked, mismatches, first_mismatch_key | max_error, flag)``."""
         out = (C.c_uint64 * 4)()
         self._check(self.lib.sb_selftest(self.handle, int(which), int(arg), out), "sb_selftest")
-        return int(out[0]), int(out[1]), int(out[2])
+        return int(out[0]), int(out[1]), int(out[2]), int(out[3])
 
     @staticmethod
     def pyramid_shapes(canvas_shape, n_levels: int):

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libstitchb200.so")
-SOURCES = ["api.cu", "fuse.cu", "reg.cu", "u8.cu", "pyramid.cu", "flatfield.cu"]
+SOURCES = ["api.cu", "fuse.cu", "reg.cu", "reg_tc.cu", "u8.cu", "pyramid.cu", "flatfield.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
 

@@ -364,6 +364,7 @@ int sb_selftest(sb_ctx* ctx, int which, int64_t arg, uint64_t* out) {
     SB_CHECK(ctx, out != nullptr, "out is NULL");
     if (which == SB_SELFTEST_STRETCH) return sb_selftest_stretch_impl(ctx, (int)arg, out);
     if (which == SB_SELFTEST_DIVIDE) return sb_selftest_div_impl(ctx, (int)arg, out);
+    if (which == SB_SELFTEST_UMMA) return sb_selftest_umma_impl(ctx, (int)arg, out);
     return sb_fail(ctx, SB_ERR_INVALID, "unknown self-test %d", which);
 }
 

@@ -21,6 +21,7 @@
 // Arithmetic is float32 or float64 (template); SB_PREC_AUTO redoes low-confidence pairs in float64.
 #include "sb_common.cuh"
 #include "fft.cuh"
+#include "reg_common.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -31,30 +32,6 @@
 #endif
 
 namespace {
-
-constexpr double kInScale = 1.0 / 65536.0;                       // exact power-of-two input scaling
-constexpr double kClamp = 100.0 * 2.220446049250313e-16 * kInScale * kInScale;   // 100*eps64, same scaling as P
-
-struct PairDesc {            // device-side description of one pair of a batch
-    const uint16_t* a;       // first pixel of the reference strip
-    const uint16_t* b;       // first pixel of the moving strip
-    int32_t a_tile, b_tile;  // indices into the min/max table
-};
-
-struct CtaBest {             // block-local first maximum and the second-largest value; double keeps the float64 path's resolution
-    double val;
-    double second;           // largest |cc| of the block at any OTHER pixel (may equal val)
-    int32_t idx;
-    int32_t pad;
-};
-
-struct PeakOut {             // per pair, written by the device, read back by the host
-    int32_t coarse_y, coarse_x;
-    int32_t fine_y, fine_x;
-    float peak, second, runner_up;     // see sb_pair_result
-    float fine_peak, fine_second;
-    int32_t pad;
-};
 
 // ------------------------------------------------------------------------------------------ K0
 __global__ void __launch_bounds__(256) minmax_init_kernel(int2* mm, int n) {
@@ -107,34 +84,6 @@ __global__ void __launch_bounds__(256) tile_minmax_kernel(const uint16_t* const*
         atomicMin(&mm[blockIdx.y].x, (int)lo);
         atomicMax(&mm[blockIdx.y].y, (int)hi);
     }
-}
-
-// normalize_image (:844-855): ((v - min) / (max - min)) * 65535 in float64, truncating cast.
-// `maxval` = iinfo(dtype).max of the caller's pixels: 65535, or 255 for (widened) uint8 tiles (:854).
-__device__ __forceinline__ int stretch_px_f64(unsigned v, int mn, int mx, int maxval) {
-    if (mx <= mn) return 0;                       // 0/0 -> NaN -> undefined cast in the reference; defined as 0
-    const double q = __ddiv_rn((double)((int)v - mn), (double)(mx - mn));
-    return (int)(q * (double)maxval);
-}
-
-// The same value without the float64 divide.  With a = v - min, b = max - min the exact quotient a * 65535 / b is
-// rational with denominator b <= 65535, so unless it is an integer it lies at least 1 / 65535 away from the next
-// one, while the float64 evaluation is off by at most 65535 * 2^-52: trunc() of both agree.  When b divides
-// a * 65535 the float64 result can land on either side of the integer -- only then the float64 sequence is run.
-// `inv` = maxval / b as float (computed once per tile).
-__device__ __forceinline__ int stretch_px(unsigned v, int mn, int mx, float inv, int maxval) {
-    if (mx <= mn) return 0;
-    const unsigned b = (unsigned)(mx - mn);
-    // full-range tile (saturated pixels next to a zero): every quotient is exact, and float64 gives (a / maxval) * maxval
-    // == a for all a <= maxval (checked exhaustively for 255 and 65535) -- skip the float64 sequence for the whole tile
-    if (b == (unsigned)maxval) return (int)v - mn;
-    const unsigned num = (unsigned)((int)v - mn) * (unsigned)maxval;       // < 2^32
-    unsigned k = (unsigned)__float2int_rz(__uint2float_rn((unsigned)((int)v - mn)) * inv);
-    unsigned rem = num - k * b;                                            // k is off by at most one either way
-    if ((int)rem < 0) { --k; rem += b; }
-    else if (rem >= b) { ++k; rem -= b; }
-    if (rem == 0 && k != 0) return stretch_px_f64(v, mn, mx, maxval);      // exact quotient (rare): reproduce float64 rounding
-    return (int)k;
 }
 
 __global__ void __launch_bounds__(256) normalize_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
@@ -341,22 +290,6 @@ __global__ void __launch_bounds__(256, SB_REG_CTAS) cols_xpower_kernel(int Sh, i
 }
 
 // ------------------------------------------------------------------------------------------ K3
-template <typename V>
-__device__ __forceinline__ void best_update(V& bv, int& bi, V v, int i) {
-    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-}
-// first maximum (ties -> lowest index) plus the largest value at any other position
-template <typename V>
-__device__ __forceinline__ void top2_update(V& bv, int& bi, V& b2, V v, int i) {
-    if (v > bv || (v == bv && i < bi)) { b2 = bv; bv = v; bi = i; }
-    else if (v > b2) b2 = v;
-}
-template <typename V>
-__device__ __forceinline__ void top2_merge(V& bv, int& bi, V& b2, V ov, int oi, V o2) {
-    if (ov > bv || (ov == bv && oi < bi)) { b2 = bv > o2 ? bv : o2; bv = ov; bi = oi; }
-    else if (ov > b2) b2 = ov;
-}
-
 template <typename T, int LB>
 __global__ void __launch_bounds__(256, SB_REG_CTAS) rows_inv_argmax_kernel(int Sh, int Sw, int lpb, int nrb, int swap,
                                                               const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,

@@ -117,6 +117,7 @@ int sb_normalize_u8(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, int 
 // test hooks (sb_selftest): exhaustive device-side proofs of the two "exact by construction" primitives
 int sb_selftest_div_impl(sb_ctx* ctx, int expo, uint64_t* out);        // fuse.cu
 int sb_selftest_stretch_impl(sb_ctx* ctx, int maxval, uint64_t* out);  // reg.cu
+int sb_selftest_umma_impl(sb_ctx* ctx, int variant, uint64_t* out);    // reg_tc.cu
 // flatfield.cu
 int sb_estimate_flatfield_impl(sb_ctx* ctx, const void* const* tiles, int n_tiles, int tile_h, int tile_w, int dtype, int mem,
                                int grid, double sigma, float* field_out, int out_mem);

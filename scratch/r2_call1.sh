@@ -18,5 +18,9 @@ timeout 300 python bench.py --no-e2e --no-cpu-baseline --no-flatfield > $O/c1_be
 CMD="python bench.py --wells 24 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
 timeout 300 $CMD > $O/c1_plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/c1_launches.csv $CMD > $O/c1_ncu1.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"rows_fwd|cols_xpower|rows_inv|updft_rows|paste_rect" -s 50 -c 26 -o $O/c1_prof $CMD > $O/c1_ncu2.log 2>&1
+timeout 1200 ncu --set full --clock-control none -k regex:"rows_fwd|cols_xpower|rows_inv|updft_rows|paste_rect" -s 50 -c 26 -o /tmp/c1_prof $CMD > $O/c1_ncu2.log 2>&1
+ncu -i /tmp/c1_prof.ncu-rep --page raw --csv > $O/c1_prof_raw.csv 2>/dev/null
+python scripts/summarize_launches.py $O/c1_launches.csv $O/c1_launches_own > $O/c1_sum.log 2>&1; rm -f $O/c1_launches.csv
+rm -f $O/c1_launches.csv.bak
+du -sh $O
 ls -la $O | tail -20

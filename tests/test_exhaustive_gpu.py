@@ -20,16 +20,29 @@ def ctx():
 
 @pytest.mark.parametrize("maxval", [255, 65535])
 def test_integer_stretch_equals_float64_for_every_pixel_and_range(ctx, maxval):
-    checked, bad, first = ctx.selftest(0, maxval)
+    checked, bad, first, _ = ctx.selftest(0, maxval)
     assert checked == maxval * (maxval + 3) // 2              # 2 147 581 950 pairs for uint16
     assert bad == 0, f"{bad} mismatches, first at b={first >> 32}, a={first & 0xffffffff}"
 
 
 @pytest.mark.parametrize("expo", [-5, -1, 0, 19])
 def test_packed_divide_equals_ieee_for_every_numerator_and_mantissa(ctx, expo):
-    checked, bad, first = ctx.selftest(1, expo)
+    checked, bad, first, _ = ctx.selftest(1, expo)
     assert checked == (1 << 23) * 65536
     assert bad == 0, f"{bad} mismatches, first at mantissa={first >> 16}, a={first & 0xffff}"
+
+
+def test_tensor_core_building_blocks(ctx):
+    """tcgen05.mma.kind::tf32 with the 3-term split, operands in the K-major no-swizzle layout the registration kernels
+    write, accumulators read back from TMEM: float32-grade agreement with a float64 product.  The single-term variant
+    shows what the split buys (errors ~2^-11 instead of ~2^-21)."""
+    checked, bad, err3, flag = ctx.selftest(2, 0)
+    assert flag == 0, "tensor pipeline did not complete"
+    assert checked == 128 * 112 and bad == 0, f"{bad} elements off, max error {err3 * 1e-12:.3e}"
+    _, bad1, err1, flag1 = ctx.selftest(2, 2)
+    assert flag1 == 0 and bad1 == 0
+    print(f"3 x tf32 max error {err3 * 1e-12:.2e}; 1 x tf32 max error {err1 * 1e-12:.2e}")
+    assert err3 * 50 < err1
 
 
 def test_selftest_rejects_unknown_requests(ctx):
