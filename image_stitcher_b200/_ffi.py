@@ -30,7 +30,7 @@ EXPORTS = [
     "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_memcpy_async", "sb_set_flatfield", "sb_set_darkfield", "sb_clear_fields",
     "sb_flatfield_apply", "sb_fuse_region", "sb_fuse_regions", "sb_sync", "sb_lane_mark", "sb_lane_wait_mark", "sb_set_lane_stream", "sb_canvas_pitch",
     "sb_chunked_plane_elems", "sb_register_pairs", "sb_register_pairs_async", "sb_normalize",
-    "sb_pyramid_elems", "sb_pyramid", "sb_estimate_flatfield", "sb_selftest",
+    "sb_pyramid_elems", "sb_pyramid", "sb_estimate_flatfield", "sb_selftest", "sb_debug_read",
 ]
 
 
@@ -123,6 +123,8 @@ def load_library(path: Optional[str] = None):
     lib.sb_pyramid_elems.restype = i64
     lib.sb_pyramid.argtypes = [vp, vp, i32, i32, i32, i32, i64, i32, i32, vp, i32, i32]
     lib.sb_selftest.argtypes = [vp, i32, i64, C.POINTER(C.c_uint64)]
+    lib.sb_debug_read.argtypes = [vp, i32, i32, vp, i64]
+    lib.sb_debug_read.restype = i64
     if path == LIB_PATH:
         _lib = lib
     return lib
@@ -392,6 +394,14 @@ class Context:
                                                    int(dtype), mem, int(grid), float(sigma), _ptr(out), SB_MEM_HOST),
                     "sb_estimate_flatfield")
         return out
+
+    def debug_read(self, lane: int, which: int, max_elems: int) -> np.ndarray:
+        """Test hook (``sb_debug_read``): complex64 intermediates of the lane's last float32 registration group."""
+        out = np.empty(int(max_elems), np.complex64)
+        n = int(self.lib.sb_debug_read(self.handle, lane, which, _ptr(out), out.nbytes))
+        if n < 0:
+            raise RuntimeError(f"sb_debug_read failed [{n}]: {self.lib.sb_last_error(self.handle).decode()}")
+        return out[:n // 8]
 
     def selftest(self, which: int, arg: int):
         """Test hook (``sb_selftest``): returns ``(cases_checked, mismatches, first_mismatch_key | max_error, flag)``."""

@@ -2,6 +2,7 @@
 // flat/dark-field storage.  The compute entry points forward to fuse.cu / reg.cu.
 #include "sb_common.cuh"
 
+#include <algorithm>
 #include <mutex>
 
 static thread_local std::string g_create_error;
@@ -366,6 +367,18 @@ int sb_selftest(sb_ctx* ctx, int which, int64_t arg, uint64_t* out) {
     if (which == SB_SELFTEST_DIVIDE) return sb_selftest_div_impl(ctx, (int)arg, out);
     if (which == SB_SELFTEST_UMMA) return sb_selftest_umma_impl(ctx, (int)arg, out);
     return sb_fail(ctx, SB_ERR_INVALID, "unknown self-test %d", which);
+}
+
+int64_t sb_debug_read(sb_ctx* ctx, int lane, int which, void* out, int64_t max_bytes) {
+    if (!ctx) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
+    Lane* l = sb_lane(ctx, lane);
+    if (!l || which < 0 || which > 2 || !out) return sb_fail(ctx, SB_ERR_INVALID, "sb_debug_read: bad arguments");
+    cudaDeviceSynchronize();
+    const size_t nbytes = std::min<size_t>(l->dbg_bytes[which], max_bytes < 0 ? 0 : (size_t)max_bytes);
+    if (nbytes && cudaMemcpy(out, l->dbg_ptr[which], nbytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return sb_fail(ctx, SB_ERR_CUDA, "sb_debug_read: copy failed");
+    return (int64_t)nbytes;
 }
 
 int sb_sync(sb_ctx* ctx, int lane) {

@@ -22,6 +22,7 @@
 #include "sb_common.cuh"
 #include "fft.cuh"
 #include "reg_common.cuh"
+#include "reg_tc.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -112,7 +113,8 @@ __global__ void __launch_bounds__(256, SB_REG_CTAS) rows_fwd_kernel(const PairDe
                                                        int tile_w, int Sh, int Sw, int lpb, int nrb, int swap, int maxval,
                                                        const typename Vec2<T>::type* __restrict__ tw_g, FftPlan plan,
                                                        const float* __restrict__ ctab_g, int ctab_n,
-                                                       typename Vec2<T>::type* __restrict__ Z, int* __restrict__ nonzero) {
+                                                       typename Vec2<T>::type* __restrict__ Z, int* __restrict__ nonzero,
+                                                       unsigned long long* __restrict__ strip_sum) {
     using T2 = typename Vec2<T>::type;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     T2* buf0 = reinterpret_cast<T2*>(smem_raw);
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(256, SB_REG_CTAS) rows_fwd_kernel(const PairDe
     const int y0 = rb * lpb;
     const PairDesc pd = pairs[p];
     int seen = 0;                                // bit 0: strip a has a non-zero pixel, bit 1: strip b
+    unsigned sum_a = 0, sum_b = 0;               // strip sums of this thread (a few dozen 16-bit values each)
     const int2 ma = mm[pd.a_tile], mb = mm[pd.b_tile];
     const float inva = ma.y > ma.x ? (float)maxval / (float)(ma.y - ma.x) : 0.f;
     const float invb = mb.y > mb.x ? (float)maxval / (float)(mb.y - mb.x) : 0.f;
@@ -153,6 +156,8 @@ __global__ void __launch_bounds__(256, SB_REG_CTAS) rows_fwd_kernel(const PairDe
                     if (x < Sw) {
                         const int na = stretch_px(av[u], ma.x, ma.y, inva, maxval), nb = stretch_px(bv[u], mb.x, mb.y, invb, maxval);
                         seen |= (na != 0 ? 1 : 0) | (nb != 0 ? 2 : 0);
+                        sum_a += (unsigned)na;
+                        sum_b += (unsigned)nb;
                         row[x] = mk2<T2, T>((T)(na * kInScale), (T)(nb * kInScale));
                     }
                 }
@@ -188,6 +193,8 @@ __global__ void __launch_bounds__(256, SB_REG_CTAS) rows_fwd_kernel(const PairDe
                             na = stretch_px(av[u], ma.x, ma.y, inva, maxval);
                             nb = stretch_px(bv[u], mb.x, mb.y, invb, maxval);
                             seen |= (na != 0 ? 1 : 0) | (nb != 0 ? 2 : 0);
+                            sum_a += (unsigned)na;
+                            sum_b += (unsigned)nb;
                         }
                         row[x] = mk2<T2, T>((T)(na * kInScale), (T)(nb * kInScale));
                     }
@@ -199,6 +206,15 @@ __global__ void __launch_bounds__(256, SB_REG_CTAS) rows_fwd_kernel(const PairDe
     // the packed transform only gets it to rounding noise, so record the fact instead.
     const int any_a = __syncthreads_or(seen & 1), any_b = __syncthreads_or(seen & 2);   // predicate OR, not bitwise
     if (threadIdx.x == 0 && (any_a || any_b)) atomicOr(&nonzero[p], (any_a ? 1 : 0) | (any_b ? 2 : 0));
+    // Strip sums: the two strips share ONE complex transform (z = a + i b), so a strip much fainter than its partner is
+    // recovered from the packed spectrum by cancellation and loses float32 digits in proportion to the ratio of their
+    // magnitudes; SB_PREC_AUTO repeats such pairs in float64 (see reg_complete).
+    sum_a = __reduce_add_sync(0xffffffffu, sum_a);
+    sum_b = __reduce_add_sync(0xffffffffu, sum_b);
+    if ((threadIdx.x & 31) == 0 && (sum_a | sum_b)) {
+        if (sum_a) atomicAdd(&strip_sum[2 * p], (unsigned long long)sum_a);
+        if (sum_b) atomicAdd(&strip_sum[2 * p + 1], (unsigned long long)sum_b);
+    }
     T2* res = fft_lines<T2, LB>(buf0, buf1, tw, plan, lpb, false, ctab);
     // Z is kept TRANSPOSED (Zt[kx][y], y fastest) so that the column pass reads and writes whole contiguous lines;
     // here the lpb rows of this block are lpb consecutive y of every kx: runs of 8 * lpb contiguous bytes.
@@ -393,13 +409,24 @@ __global__ void __launch_bounds__(256, SB_REG_CTAS) rows_inv_argmax_kernel(int S
 // transposed frame), so the band removes the peak's own line and its two neighbours.
 __global__ void __launch_bounds__(32) peak_final_kernel(const CtaBest* __restrict__ best, int nrb, int Sh, int Sw, int swap,
                                                         const float* __restrict__ rowmax, const int* __restrict__ nonzero,
-                                                        PeakOut* out) {
+                                                        const int* __restrict__ fault,
+                                                        const unsigned long long* __restrict__ strip_sum, PeakOut* out) {
     const int p = blockIdx.x;
+    if (*fault) {                                // the tensor pipeline of an earlier kernel timed out: poison the result
+        if (threadIdx.x == 0) {
+            out[p].coarse_y = out[p].coarse_x = -999;
+            out[p].fine_y = out[p].fine_x = -1;
+            out[p].peak = out[p].second = out[p].runner_up = out[p].fine_peak = out[p].fine_second = 0.f;
+            out[p].skew = 1.f;
+        }
+        return;
+    }
     if (nonzero[p] != 3) {                       // a strip is identically zero: cc == 0 everywhere, first index wins
         if (threadIdx.x == 0) {
             out[p].coarse_y = out[p].coarse_x = 0;
             out[p].peak = out[p].second = out[p].runner_up = out[p].fine_peak = out[p].fine_second = 0.f;
             out[p].fine_y = out[p].fine_x = -1;
+            out[p].skew = 1.f;
         }
         return;
     }
@@ -435,6 +462,12 @@ __global__ void __launch_bounds__(32) peak_final_kernel(const CtaBest* __restric
         out[p].runner_up = ru;
         out[p].fine_y = out[p].fine_x = -1;
         out[p].fine_peak = out[p].fine_second = 0.f;
+        float skew = 1.f;                               // ratio of the strip magnitudes (packed transform only)
+        if (strip_sum != nullptr) {
+            const double sa = (double)strip_sum[2 * p], sb = (double)strip_sum[2 * p + 1];
+            skew = (float)(fmax(sa, sb) / fmax(fmin(sa, sb), 1.0));
+        }
+        out[p].skew = skew;
     }
 }
 
@@ -712,6 +745,13 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     const int swap = group_swapped(g) ? 1 : 0;
     const int Sh = swap ? g.Sw : g.Sh, Sw = swap ? g.Sh : g.Sw;
     const size_t strip = (size_t)Sh * Sw;
+    // float32 frames with a 1024-long axis: the forward short-axis transform runs on the tensor cores and the column pass
+    // as warp-level register FFTs (reg_tc.cu); everything else -- and float64 -- stays on the radix engine below
+    TcPlan tc;
+    if (sizeof(T) == 4) {
+        const int rc_tc = sb_tc_plan(ctx, Sh, Sw, &tc);
+        if (rc_tc) return rc_tc;
+    }
     const FftPlan plan_x = make_plan(Sw), plan_y = make_plan(Sh);
     const T2 *tw_x = nullptr, *tw_y = nullptr;
     int rc = get_twiddles<T>(ctx, Sw, &tw_x);
@@ -793,11 +833,13 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     const size_t o_best = carve((size_t)B * nrb_inv * sizeof(CtaBest));
     const size_t o_mag = carve((size_t)B * rs * rs * sizeof(double));
     const size_t o_rmax = carve((size_t)B * Sh * sizeof(float));
+    const size_t o_Zh = carve(tc.ok ? sb_tc_zh_bytes(tc, B) : 0);
     const size_t way_bytes = off;                           // everything above exists once per concurrent sub-batch
     off = way_bytes * ways;
     const size_t o_peaks = carve((size_t)n * sizeof(PeakOut));
     const size_t o_pairs = carve((size_t)n * sizeof(PairDesc));
-    const size_t o_nz = carve((size_t)n * sizeof(int));
+    const size_t o_nz = carve((size_t)(n + 1) * sizeof(int));      // + the tensor pipeline's fault flag
+    const size_t o_sums = carve((size_t)2 * n * sizeof(unsigned long long));
     rc = sb_reserve(ctx, lane->reg_work, off);
     if (rc) return rc;
     uint8_t* w = (uint8_t*)lane->reg_work.p;
@@ -812,7 +854,12 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     PeakOut* peaks = (PeakOut*)(w + o_peaks);
     PairDesc* d_pairs = (PairDesc*)(w + o_pairs);
     int* d_nz = (int*)(w + o_nz);
-    SB_CUDA(ctx, cudaMemsetAsync(d_nz, 0, (size_t)n * sizeof(int), st));
+    int* d_fault = d_nz + n;
+    unsigned long long* d_sums = (unsigned long long*)(w + o_sums);
+    SB_CUDA(ctx, cudaMemsetAsync(d_nz, 0, (o_sums - o_nz) + (size_t)2 * n * sizeof(unsigned long long), st));
+    lane->dbg_ptr[0] = tc.ok ? w + o_Zh : nullptr;  lane->dbg_bytes[0] = tc.ok ? sb_tc_zh_bytes(tc, std::min(B, n)) : 0;
+    lane->dbg_ptr[1] = w + o_Z;                     lane->dbg_bytes[1] = (size_t)std::min(B, n) * strip * sizeof(T2);
+    lane->dbg_ptr[2] = w + o_R;                     lane->dbg_bytes[2] = (size_t)std::min(B, n) * strip * sizeof(T2);
     // Descriptors go up from PINNED memory when the caller provides it: a copy from pageable memory synchronises the
     // stream first, i.e. the host would wait for everything already enqueued on this lane (uploads, earlier groups).
     const PairDesc* h_pairs = pairs.data();
@@ -858,10 +905,19 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
         CtaBest* bestw = (CtaBest*)((uint8_t*)best + wo);
         double* magw = (double*)((uint8_t*)mag2 + wo);
         float* rmaxw = (float*)((uint8_t*)rowmax + wo);
-        k1<<<nb * nrb_fwd, 256, smem_x, ws>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, swap, maxval, tw_x, px_plan, cx, cxn, Zw, d_nz + p0);
-        k2<<<nb * ncg, 256, smem_y, ws>>>(Sh, Sw, ncg, tw_y, py_plan, cy, cyn, Zw, Rw);
+        if (tc.ok) {
+            void* Zhw = w + o_Zh + wo;
+            rc = sb_tc_forward(ctx, ws, tc, d_pairs + p0, nb, d_mm, tile_w, swap, maxval, Zhw, d_nz + p0, d_fault);
+            if (rc) return rc;
+            rc = sb_tc_columns(ctx, ws, tc, nb, Zhw, Rw, Zw, Sw, 1);
+            if (rc) return rc;
+            ctx->launches -= 2;                          // (counted below with the other two)
+        } else {
+            k1<<<nb * nrb_fwd, 256, smem_x, ws>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, swap, maxval, tw_x, px_plan, cx, cxn, Zw, d_nz + p0, d_sums + 2 * p0);
+            k2<<<nb * ncg, 256, smem_y, ws>>>(Sh, Sw, ncg, tw_y, py_plan, cy, cyn, Zw, Rw);
+        }
         k3<<<nb * nrb_inv, 256, smem_x, ws>>>(Sh, Sw, lpbx, nrb_inv, swap, tw_x, px_plan, cx, cxn, Zw, bestw, rmaxw);
-        peak_final_kernel<<<nb, 32, 0, ws>>>(bestw, nrb_inv, Sh, Sw, swap, rmaxw, d_nz + p0, peaks + p0);
+        peak_final_kernel<<<nb, 32, 0, ws>>>(bestw, nrb_inv, Sh, Sw, swap, rmaxw, d_nz + p0, d_fault, tc.ok ? nullptr : d_sums + 2 * p0, peaks + p0);
         ctx->launches += 4;
         if (uf > 1) {
             updft_twiddle_kernel<T><<<dim3(8, nb), 256, 0, ws>>>(peaks + p0, Sh, Sw, uf, rs, dftshift, Exw, Eyw);
@@ -1079,6 +1135,8 @@ static int reg_complete(sb_ctx* ctx, Lane* lane, RegPending& pr) {
         const GroupGeom& g = grp.g;
         std::vector<PeakOut> res(pr.h_peaks + grp.first, pr.h_peaks + grp.first + grp.ids.size());
         std::vector<int> prec(grp.ids.size(), first_prec);
+        for (const PeakOut& q : res)
+            if (q.coarse_y == -999) return sb_fail(ctx, SB_ERR_CUDA, "registration: the tensor-core pipeline did not complete (timeout)");
         if (job->precision == SB_PREC_AUTO) {
             // Two reasons to repeat a pair in float64, the arithmetic the reference uses:
             //  (1) low confidence -- the peak does not stand clear of the correlation noise floor (rms 1/sqrt(N), expected
@@ -1101,7 +1159,10 @@ static int reg_complete(sb_ctx* ctx, Lane* lane, RegPending& pr) {
                 const bool low = !(q.peak > 4.0 * floor_max) || !(q.peak > 1.5f * q.runner_up);
                 const bool tie_c = !(q.peak - q.second > kTie * q.peak);
                 const bool tie_f = job->upsample_factor > 1 && !(q.fine_peak - q.fine_second > kTie * q.fine_peak);
-                if (!zero && (low || tie_c || tie_f)) {
+                // (3) strips of very different magnitude through the PACKED transform of the radix path: float32 error grows
+                //     with their ratio (4e-8 of the peak at 1:1, 2e-4 at 1:20000 -- measured); 32 keeps it below 1e-5
+                const bool skewed = q.skew > 32.f;
+                if (!zero && (low || tie_c || tie_f || skewed)) {
                     redo.push_back(grp.pd[k]);
                     redo_k.push_back((int)k);
                 }

@@ -27,7 +27,7 @@ struct PeakOut {             // per pair, written by the device, read back by th
     int32_t fine_y, fine_x;
     float peak, second, runner_up;     // see sb_pair_result
     float fine_peak, fine_second;
-    int32_t pad;
+    float skew;                        // max / min of the two strips' sums when they shared one packed transform, else 1
 };
 
 // normalize_image (:844-855): ((v - min) / (max - min)) * 65535 in float64, truncating cast.

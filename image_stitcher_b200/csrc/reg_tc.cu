@@ -1,12 +1,304 @@
 // Tensor-core (tcgen05) stages of the registration chain -- see umma.cuh for the operand layout and the 3-term tf32
 // split, reg.cu for the chain itself.
 #include "sb_common.cuh"
+#include "reg_common.cuh"
+#include "reg_tc.cuh"
 #include "umma.cuh"
+#include "fft_warp.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
 namespace {
+
+// ==========================================================================================================
+// T1  fwd_x_tc_kernel: real DFT of the strip rows along the SHORT axis (length n, any n) on the tensor cores.
+//
+// For a real row x[0..n) the half spectrum X[k], k = 0..n/2, is two real matrix products of the row folded about its
+// centre -- e[j] = x[j] + x[n-j], o[j] = x[j] - x[n-j] (e[0] = x[0], e[n/2] = x[n/2] for even n):
+//         Re X[k] =  sum_j e[j] cos(2 pi j k / n)            Im X[k] = -sum_j o[j] sin(2 pi j k / n)
+// A block owns 128 rows (M) of one strip image; K = j runs in chunks of 8 through an STAGES-deep ring of shared-memory
+// operand stages: the A sub-tiles (e / o, tf32 hi / lo) are produced by 8 warps from the stretched strip rows staged in
+// shared memory (crop + normalize_image's stretch fused into the coalesced load, as in the radix path), the B sub-tiles
+// (cos / -sin tables, hi / lo, laid out on the host exactly as the tensor core reads them) arrive by 1-D bulk copies.
+// One thread issues 6 tcgen05.mma.kind::tf32 per chunk (3-term split x {Re, Im}) into TMEM columns [0, NP) / [NP, 2 NP).
+// The epilogue reads the accumulators back (one row per thread) and stores the spectrum TRANSPOSED -- Zh[img][k][y],
+// y fastest -- which is a whole 256-byte warp store per k because TMEM lane == strip row.
+// ==========================================================================================================
+constexpr int kTcThreads = 288;          // warps 0-7: operand producers + epilogue; warp 8: bulk copies + MMA issue
+constexpr int kTcStages = 3;
+constexpr int kAStage = 4 * 128 * 32;    // e_hi | e_lo | o_hi | o_lo, each 128 rows x 8 k (K-major, LBO 2048, SBO 128)
+
+struct TcSmem {                          // offsets into dynamic shared memory
+    int a_off, b_off, stg_off, bar_off, total;
+    int b_stage;                         // bytes of one B stage: 4 sub-tiles of NP rows x 8 k
+};
+__host__ __device__ inline TcSmem tc_smem_layout(int NP, int pitch_w) {
+    TcSmem L;
+    L.b_stage = 4 * NP * 32;
+    L.a_off = 0;
+    L.b_off = kTcStages * kAStage;
+    L.stg_off = L.b_off + kTcStages * L.b_stage;
+    L.bar_off = L.stg_off + 128 * pitch_w * 4;
+    L.total = L.bar_off + 128;
+    return L;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+fwd_x_tc_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm, int tile_w, int Sh, int n, int NP, int nchunks,
+                int pitch_w, int swap, int maxval, const uint8_t* __restrict__ Bmat, float2* __restrict__ Zh,
+                int* __restrict__ nonzero, int* __restrict__ fault) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const TcSmem L = tc_smem_layout(NP, pitch_w);
+    uint8_t* a_st = smem + L.a_off;
+    uint8_t* b_st = smem + L.b_off;
+    uint16_t* stg = reinterpret_cast<uint16_t*>(smem + L.stg_off);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off);          // [kTcStages]
+    uint64_t* empty = full + kTcStages;                                       // [kTcStages]
+    uint64_t* done = empty + kTcStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int tiles = Sh >> 7;
+    const int mt = blockIdx.x % tiles, img = (blockIdx.x / tiles) & 1, p = blockIdx.x / (2 * tiles);
+    const int y0 = mt << 7;
+    const int nb = n / 2 + 1, nh = n / 2, no = (n - 1) / 2;
+    const int pitch_h = pitch_w * 2;
+    const uint32_t tmem_cols = 2 * NP <= 32 ? 32 : 2 * NP <= 64 ? 64 : 2 * NP <= 128 ? 128 : 2 * NP <= 256 ? 256 : 512;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int s = 0; s < kTcStages; ++s) {
+                umma::mbar_init(full + s, 9);             // 8 producer warps + the bulk copy's expect_tx arrival
+                umma::mbar_init(empty + s, 1);            // tcgen05.commit
+            }
+            umma::mbar_init(done, 1);
+            umma::mbar_init_fence();
+        }
+        __syncwarp();
+        umma::tmem_alloc(tmem_slot, tmem_cols);
+        umma::tmem_relinquish();
+        if (lane == 0)
+            for (int c = 0; c < kTcStages && c < nchunks; ++c) {              // the first B stages need no free slot
+                umma::mbar_expect_tx(full + c, (uint32_t)L.b_stage);
+                umma::bulk_g2s(b_st + c * L.b_stage, Bmat + (size_t)c * L.b_stage, (uint32_t)L.b_stage, full + c);
+            }
+    } else {
+        // ---- strip rows -> shared memory: crop + stretch fused into the load (normalize_image, :844-855)
+        const PairDesc pd = pairs[p];
+        const uint16_t* src = img ? pd.b : pd.a;
+        const int2 m = mm[img ? pd.b_tile : pd.a_tile];
+        const float inv = m.y > m.x ? (float)maxval / (float)(m.y - m.x) : 0.f;
+        int seen = 0;
+        if (!swap) {
+            for (int r = warp; r < 128; r += 8) {
+                const uint16_t* row = src + (size_t)(y0 + r) * tile_w;
+                uint16_t* dst = stg + r * pitch_h;
+                for (int x0 = lane; x0 < n; x0 += 128) {
+                    unsigned v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = x0 + 32 * u < n ? row[x0 + 32 * u] : 0u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (x0 + 32 * u < n) {
+                            const int s = stretch_px(v[u], m.x, m.y, inv, maxval);
+                            seen |= s;
+                            dst[x0 + 32 * u] = (uint16_t)s;
+                        }
+                }
+            }
+        } else {
+            // transposed frame: frame row r is image column y0 + r (contiguous in memory), frame column x is image row x
+            for (int x0 = warp; x0 < n; x0 += 16) {
+                unsigned v[2][4];
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        v[u][q] = x0 + 8 * u < n ? src[(size_t)(x0 + 8 * u) * tile_w + y0 + lane + 32 * q] : 0u;
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (x0 + 8 * u < n) {
+                            const int s = stretch_px(v[u][q], m.x, m.y, inv, maxval);
+                            seen |= s;
+                            stg[(lane + 32 * q) * pitch_h + x0 + 8 * u] = (uint16_t)s;
+                        }
+            }
+        }
+        // an all-zero strip has an exactly zero spectrum in the reference: record whether this one has a non-zero pixel
+        seen = __reduce_or_sync(0xffffffffu, (unsigned)seen);
+        if (lane == 0 && seen) atomicOr(&nonzero[p], img ? 2 : 1);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_tf32(128, NP);
+            const uint32_t a0 = umma::smem_addr(a_st), b0 = umma::smem_addr(b_st);
+            const uint32_t bsub = (uint32_t)NP * 32, blbo = (uint32_t)NP * 16;
+            bool ok = true;
+            for (int c = 0; c < nchunks && ok; ++c) {
+                const int s = c % kTcStages, u = c / kTcStages;
+                ok = umma::mbar_wait(full + s, u & 1);
+                umma::fence_after_sync();
+                const uint32_t as = a0 + s * kAStage, bs = b0 + s * L.b_stage;
+                const uint64_t eh = umma::desc_kmajor(as, 2048, 128), el = umma::desc_kmajor(as + 4096, 2048, 128);
+                const uint64_t oh = umma::desc_kmajor(as + 8192, 2048, 128), ol = umma::desc_kmajor(as + 12288, 2048, 128);
+                const uint64_t ch = umma::desc_kmajor(bs, blbo, 128), cl = umma::desc_kmajor(bs + bsub, blbo, 128);
+                const uint64_t sh = umma::desc_kmajor(bs + 2 * bsub, blbo, 128), sl = umma::desc_kmajor(bs + 3 * bsub, blbo, 128);
+                const uint32_t acc = c > 0 ? 1u : 0u;
+                umma::mma_tf32(tb, eh, ch, idesc, acc);
+                umma::mma_tf32(tb, el, ch, idesc, 1);
+                umma::mma_tf32(tb, eh, cl, idesc, 1);
+                umma::mma_tf32(tb + NP, oh, sh, idesc, acc);
+                umma::mma_tf32(tb + NP, ol, sh, idesc, 1);
+                umma::mma_tf32(tb + NP, oh, sl, idesc, 1);
+                umma::mma_commit(empty + s);
+                // refill the stage used ONE chunk ago (its MMAs have had a whole chunk to finish)
+                const int cp = c - 1 + kTcStages;
+                if (c >= 1 && cp < nchunks) {
+                    const int sp = (c - 1) % kTcStages, up = (c - 1) / kTcStages;
+                    ok = ok && umma::mbar_wait(empty + sp, up & 1);
+                    umma::mbar_expect_tx(full + sp, (uint32_t)L.b_stage);
+                    umma::bulk_g2s(b_st + sp * L.b_stage, Bmat + (size_t)cp * L.b_stage, (uint32_t)L.b_stage, full + sp);
+                }
+            }
+            umma::mma_commit(done);
+            if (!ok) atomicExch(fault, 1);
+        }
+    } else {
+        // ---- operand producers: thread = (row, half): four consecutive j of one row per chunk
+        const int row = t & 127, half = t >> 7;
+        const uint16_t* srow = stg + row * pitch_h;
+        bool ok = true;
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % kTcStages, u = c / kTcStages;
+            if (u >= 1) ok = umma::mbar_wait(empty + s, (u - 1) & 1) && ok;
+            float eh[4], el[4], oh[4], ol[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = 8 * c + 4 * half + i;
+                const int xa = j <= nh ? (int)srow[j] : 0;
+                const bool paired = j >= 1 && j <= no;
+                const int xb = paired ? (int)srow[n - j] : 0;
+                const float e = (float)(xa + xb) * (float)kInScale, o = paired ? (float)(xa - xb) * (float)kInScale : 0.f;
+                umma::split_tf32(e, eh[i], el[i]);
+                umma::split_tf32(o, oh[i], ol[i]);
+            }
+            uint8_t* dst = a_st + s * kAStage + half * 2048 + row * 16;
+            *reinterpret_cast<float4*>(dst) = make_float4(eh[0], eh[1], eh[2], eh[3]);
+            *reinterpret_cast<float4*>(dst + 4096) = make_float4(el[0], el[1], el[2], el[3]);
+            *reinterpret_cast<float4*>(dst + 8192) = make_float4(oh[0], oh[1], oh[2], oh[3]);
+            *reinterpret_cast<float4*>(dst + 12288) = make_float4(ol[0], ol[1], ol[2], ol[3]);
+            umma::fence_smem_to_async();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(full + s);
+        }
+        // ---- epilogue: TMEM -> registers -> Zh[img][k][y]
+        ok = umma::mbar_wait(done, 0) && ok;
+        umma::fence_after_sync();
+        if (!ok) {
+            if (lane == 0) atomicExch(fault, 1);
+        } else {
+            const int q = warp & 3, hcol = warp >> 2;
+            const int kbeg = hcol * (NP >> 1), kend = kbeg + (NP >> 1);
+            float2* zp = Zh + ((size_t)(p * 2 + img) * nb) * Sh + y0 + 32 * q + lane;
+            for (int k0 = kbeg; k0 < kend; k0 += 8) {
+                uint32_t re[8], im[8];
+                umma::tmem_ld8(tb + ((uint32_t)(32 * q) << 16) + k0, re);
+                umma::tmem_ld8(tb + ((uint32_t)(32 * q) << 16) + NP + k0, im);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (k0 + i < nb) zp[(size_t)(k0 + i) * Sh] = make_float2(__uint_as_float(re[i]), __uint_as_float(im[i]));
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 8) umma::tmem_dealloc(tb, tmem_cols);
+}
+
+// ==========================================================================================================
+// T2  cols_warp_kernel: the column pass on lines of 1024 -- FFT of the two half spectra, normalised cross-power,
+// inverse FFT -- one warp per column, everything between the global load and the global stores in registers
+// (fft_warp.cuh).  Only the n/2 + 1 columns of the half spectrum are transformed; the mirrored columns of the full
+// arrays the radix kernels downstream read (R for the upsampled DFT, Y for the inverse row pass) are their
+// conjugates: R[ky][n-kx] = conj(R[-ky][kx]), Y[y][n-kx] = conj(Y[y][kx]).
+// ==========================================================================================================
+struct ColsSmem {
+    wfft::WarpBuf buf;
+    float park_re[1024];
+    float park_im[1024];
+};
+
+__global__ void __launch_bounds__(128) cols_warp_kernel(int n_cols, int nb, int n, int lines_out, int mirror,
+                                                         const float2* __restrict__ tw_g, const float2* __restrict__ Zh,
+                                                         float2* __restrict__ Rout, float2* __restrict__ Yout) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float2* tw = reinterpret_cast<float2*>(smem);                                     // [k2][l]: W1024^(l k2)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ColsSmem& sm = *reinterpret_cast<ColsSmem*>(smem + 1024 * sizeof(float2) + (size_t)warp * sizeof(ColsSmem));
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) tw[i] = tw_g[i];
+    __syncthreads();
+    constexpr int N = 1024;
+    // max(|P|, 100 eps) with the inputs scaled by 2^-16: the clamp (5.2e-24) squared underflows float32, so it only
+    // catches |P|^2 == 0 -- an exactly zero product, which the division by the clamp leaves at zero
+    const float clamp2 = 0.f;
+    for (int col = blockIdx.x * 4 + warp; col < n_cols; col += gridDim.x * 4) {
+        const int p = col / nb, kx = col - p * nb;
+        const float2* la = Zh + ((size_t)(p * 2) * nb + kx) * N;
+        const float2* lb = Zh + ((size_t)(p * 2 + 1) * nb + kx) * N;
+        float2 x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = la[lane + 32 * j];
+        wfft::fft1024<false>(x, sm.buf, tw, lane);
+#pragma unroll
+        for (int s = 0; s < 32; ++s) {
+            sm.park_re[s * 32 + lane] = x[s].x;
+            sm.park_im[s * 32 + lane] = x[s].y;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = lb[lane + 32 * j];
+        wfft::fft1024<false>(x, sm.buf, tw, lane);
+        // R = A conj(B) / max(|A conj(B)|, 100 eps): slot s holds ky = lane + 32 brev5(s) in both transforms
+        float2* rl = Rout + ((size_t)p * lines_out + kx) * N;
+        const bool mir = mirror && kx >= 1 && kx <= (n - 1) / 2;
+        float2* rm = Rout + ((size_t)p * lines_out + (n - kx)) * N;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) {
+            const float ax = sm.park_re[s * 32 + lane], ay = sm.park_im[s * 32 + lane];
+            const float bx = x[s].x, by = x[s].y;
+            float px = ax * bx + ay * by, py = ay * bx - ax * by;
+            const float m2 = px * px + py * py;
+            const float inv = m2 > clamp2 ? rsqrtf(m2) : (float)(1.0 / kClamp);
+            px *= inv;
+            py *= inv;
+            x[s] = make_float2(px, py);
+            const int ky = lane + 32 * wfft::brev5(s);
+            rl[ky] = x[s];
+            if (mir) rm[(N - ky) & (N - 1)] = make_float2(px, -py);
+        }
+        float2 y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = x[wfft::brev5(j)];                      // natural order for the inverse
+        wfft::fft1024<true>(y, sm.buf, tw, lane);
+        float2* yl = Yout + ((size_t)p * lines_out + kx) * N;
+        float2* ym = Yout + ((size_t)p * lines_out + (n - kx)) * N;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) {
+            const int yy = lane + 32 * wfft::brev5(s);
+            yl[yy] = y[s];
+            if (mir) ym[yy] = make_float2(y[s].x, -y[s].y);
+        }
+    }
+}
+
 
 // ------------------------------------------------------------------------------------------ self-test (test hook)
 // D[128 x N] = A[128 x K] . B[N x K]^T through the exact device functions the registration kernels use (descriptor
@@ -103,6 +395,115 @@ __global__ void __launch_bounds__(128) selftest_umma_check_kernel(const float* _
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------------------------------ host side
+static void split_tf32_host(float v, float& hi, float& lo) {
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;                 // round to nearest, ties away (cvt.rna.tf32.f32)
+    memcpy(&hi, &u, 4);
+    lo = v - hi;
+}
+
+size_t sb_tc_zh_bytes(const TcPlan& plan, int n_pairs) { return (size_t)n_pairs * 2 * plan.nb * plan.Sh * sizeof(float2); }
+
+int sb_tc_plan(sb_ctx* ctx, int Sh, int n, TcPlan* plan) {
+    *plan = TcPlan();
+    static const bool off = getenv("SB_REG_NO_TC") != nullptr;
+    if (off || Sh != 1024 || n < 8 || n > 400) return SB_OK;
+    plan->Sh = Sh;
+    plan->n = n;
+    plan->nb = n / 2 + 1;
+    plan->NP = (plan->nb + 15) & ~15;
+    plan->nchunks = (plan->nb + 7) / 8;
+    plan->pitch_w = ((n + 1) / 2) | 1;
+    const TcSmem L = tc_smem_layout(plan->NP, plan->pitch_w);
+    plan->smem_fwd = L.total;
+    if (L.total > 227 * 1024) return SB_OK;
+    const int nb = plan->nb, NP = plan->NP, nh = n / 2, no = (n - 1) / 2;
+    // forward tables: per chunk [cos_hi | cos_lo | -sin_hi | -sin_lo], each NP rows (output bin k) x 8 (input j), K-major
+    const uint64_t key = ((uint64_t)2 << 40) | (uint64_t)n;
+    auto it = ctx->twiddle_cache.find(key);
+    if (it == ctx->twiddle_cache.end()) {
+        std::vector<float> img((size_t)plan->nchunks * 4 * NP * 8, 0.0f);
+        const long double tau = 6.283185307179586476925286766559L;
+        for (int c = 0; c < plan->nchunks; ++c)
+            for (int k = 0; k < nb; ++k)
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int j = 8 * c + jj;
+                    const long double ang = tau * (long double)(((long long)j * k) % n) / (long double)n;
+                    const float cv = j <= nh ? (float)cosl(ang) : 0.0f;
+                    const float sv = (j >= 1 && j <= no) ? (float)(-sinl(ang)) : 0.0f;
+                    float ch, cl, sh, sl;
+                    split_tf32_host(cv, ch, cl);
+                    split_tf32_host(sv, sh, sl);
+                    const size_t base = (size_t)c * 4 * NP * 8, e = (size_t)(jj / 4) * NP * 4 + (size_t)k * 4 + (jj % 4);
+                    img[base + e] = ch;
+                    img[base + (size_t)NP * 8 + e] = cl;
+                    img[base + (size_t)2 * NP * 8 + e] = sh;
+                    img[base + (size_t)3 * NP * 8 + e] = sl;
+                }
+        DevBuf b;
+        int rc = sb_reserve(ctx, b, img.size() * sizeof(float));
+        if (rc) return rc;
+        SB_CUDA(ctx, cudaMemcpy(b.p, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+        it = ctx->twiddle_cache.emplace(key, b).first;
+    }
+    plan->Bfwd = reinterpret_cast<const uint8_t*>(it->second.p);
+    // column-pass twiddles: tw[k2][l] = exp(-2 pi i l k2 / 1024)
+    const uint64_t key2 = ((uint64_t)3 << 40) | 1024u;
+    auto it2 = ctx->twiddle_cache.find(key2);
+    if (it2 == ctx->twiddle_cache.end()) {
+        std::vector<float2> tw(1024);
+        const long double tau = 6.283185307179586476925286766559L;
+        for (int k2 = 0; k2 < 32; ++k2)
+            for (int l = 0; l < 32; ++l) {
+                const long double a = -tau * (long double)(l * k2) / 1024.0L;
+                tw[(size_t)k2 * 32 + l] = make_float2((float)cosl(a), (float)sinl(a));
+            }
+        DevBuf b;
+        int rc = sb_reserve(ctx, b, tw.size() * sizeof(float2));
+        if (rc) return rc;
+        SB_CUDA(ctx, cudaMemcpy(b.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        it2 = ctx->twiddle_cache.emplace(key2, b).first;
+    }
+    plan->tw1024 = it2->second.p;
+    plan->ok = true;
+    return SB_OK;
+}
+
+int sb_tc_forward(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, const void* d_pairs, int n_pairs, const int2* d_mm, int tile_w,
+                  int swap, int maxval, void* Zh, int* d_nonzero, int* d_fault) {
+    static bool configured = false;
+    if (!configured) {
+        SB_CUDA(ctx, cudaFuncSetAttribute(fwd_x_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    const int grid = n_pairs * 2 * (plan.Sh >> 7);
+    fwd_x_tc_kernel<<<grid, kTcThreads, plan.smem_fwd, st>>>(static_cast<const PairDesc*>(d_pairs), d_mm, tile_w, plan.Sh, plan.n, plan.NP,
+                                                             plan.nchunks, plan.pitch_w, swap, maxval, plan.Bfwd,
+                                                             static_cast<float2*>(Zh), d_nonzero, d_fault);
+    ctx->launches++;
+    SB_CUDA(ctx, cudaGetLastError());
+    return SB_OK;
+}
+
+int sb_tc_columns(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs, const void* Zh, void* R, void* Y, int lines_out,
+                  int mirror) {
+    const int smem = (int)(1024 * sizeof(float2) + 4 * sizeof(ColsSmem));
+    static bool configured = false;
+    if (!configured) {
+        SB_CUDA(ctx, cudaFuncSetAttribute(cols_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const int n_cols = n_pairs * plan.nb;
+    const int grid = std::max(1, std::min((n_cols + 3) / 4, ctx->sm_count * 3));
+    cols_warp_kernel<<<grid, 128, smem, st>>>(n_cols, plan.nb, plan.n, lines_out, mirror, static_cast<const float2*>(plan.tw1024),
+                                              static_cast<const float2*>(Zh), static_cast<float2*>(R), static_cast<float2*>(Y));
+    ctx->launches++;
+    SB_CUDA(ctx, cudaGetLastError());
+    return SB_OK;
+}
 
 // out[0] = elements checked, out[1] = elements off by more than the tolerance, out[2] = largest |error| * 1e12,
 // out[3] = 0xDEAD if the MMA pipeline never signalled completion (bounded wait).

@@ -1,0 +1,30 @@
+// Interface between reg.cu (the registration chain) and reg_tc.cu (its tensor-core / warp-FFT stages).
+#pragma once
+
+#include "sb_common.cuh"
+
+
+
+struct TcPlan {
+    bool ok = false;       // this strip shape takes the tensor-core path
+    int Sh = 0, n = 0;     // frame: long axis (1024), short axis
+    int nb = 0;            // n / 2 + 1 bins of the half spectrum
+    int NP = 0;            // nb rounded up to 16: accumulator columns per part
+    int nchunks = 0;       // K chunks of 8 (nb rounded up to 8, / 8)
+    int pitch_w = 0;       // 32-bit words per staged strip row (odd: conflict-free column reads)
+    int smem_fwd = 0;      // dynamic shared memory of fwd_x_tc_kernel
+    const uint8_t* Bfwd = nullptr;   // cos / -sin operand images of the forward transform (device)
+    const void* tw1024 = nullptr;    // [k2][l] table of W1024^(l k2) (device, float2)
+};
+
+// Decides whether a frame of Sh x n (after the transposed-frame swap) takes the tensor-core path and builds / caches
+// its tables.  Returns SB_OK with plan->ok == false when it does not.
+int sb_tc_plan(sb_ctx* ctx, int Sh, int n, TcPlan* plan);
+// Zh[p][img][k][y] <- half spectra along the short axis of both strips of `n_pairs` pairs (d_pairs: PairDesc[]).
+int sb_tc_forward(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, const void* d_pairs, int n_pairs, const int2* d_mm, int tile_w,
+                  int swap, int maxval, void* Zh, int* d_nonzero, int* d_fault);
+// Column pass: FFT along the long axis, cross-power, inverse FFT.  R / Y are the full [x][y] arrays of the radix chain
+// (mirror = 1: the conjugate columns are written too) or half arrays of nb lines (mirror = 0, lines_out = nb).
+int sb_tc_columns(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs, const void* Zh, void* R, void* Y, int lines_out,
+                  int mirror);
+size_t sb_tc_zh_bytes(const TcPlan& plan, int n_pairs);

@@ -199,7 +199,9 @@ typedef struct sb_register_job {
                                  when (a) peak <= 4 x the expected noise maximum sqrt(2 ln N / N) or peak <=
                                  1.5 x runner_up (low confidence), or (b) peak - second <= 1e-4 peak, or
                                  fine_peak - fine_second <= 1e-4 fine_peak (near-tie: float32 could pick another
-                                 index than complex128).  sb_pair_result.precision says which arithmetic won. */
+                                 index than complex128), or (c) the radix path packed two strips whose sums differ
+                                 by more than 32 x into one transform (float32 digits are lost in proportion).
+                                 sb_pair_result.precision says which arithmetic won. */
     int32_t lane;             /* stream to run on (ordered after that lane's earlier copies); the call
                                  still returns only when the results are on the host                  */
 } sb_register_job;
@@ -250,6 +252,11 @@ int sb_pyramid(sb_ctx* ctx, const void* src, int src_mem, int32_t n_planes, int3
  * out[0] = cases checked, out[1] = mismatches, out[2] = smallest mismatching case key (or ~0).  out holds 4 values. */
 enum { SB_SELFTEST_STRETCH = 0, SB_SELFTEST_DIVIDE = 1, SB_SELFTEST_UMMA = 2 };
 int sb_selftest(sb_ctx* ctx, int which, int64_t arg, uint64_t* out);
+/* Test hook: intermediates of the lane's last float32 registration group (first sub-batch), as left in its workspace:
+ * which = 0: half spectra along the short strip axis Zh[pair][image][k][y] (tensor-core path only), 1: the inverse
+ * column transform Y[pair][x][y], 2: the normalised cross-power R[pair][x][y]; complex64, y (the strip's long axis)
+ * fastest.  Returns the bytes copied (<= max_bytes) or a negative status. */
+int64_t sb_debug_read(sb_ctx* ctx, int lane, int which, void* out, int64_t max_bytes);
 
 #ifdef __cplusplus
 }

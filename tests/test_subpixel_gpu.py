@@ -121,10 +121,10 @@ def test_fractional_shifts_small_odd_strips(ctx, uf):
     print("fractional small:", stats)
 
 
-def _tie_tiles(H, W, ov, bump, direction, seed):
-    """Two tiles whose strips are s and K * (s + roll(s, 1)) with one pixel raised by ``bump``: in exact arithmetic the
-    cross-power phase is that of a half-pixel shift (two EQUAL peaks on neighbouring pixels for an odd extent); the
-    bump separates them by ~1e-7 .. 1e-5 of the peak -- far above complex128 rounding, at or below float32's.
+def _tie_tiles(H, W, ov, bump, direction, seed, scale_a=20000):
+    """Two tiles whose strips are scale_a * s and K * (s + roll(s, 1)) with one pixel raised by ``bump``: in exact
+    arithmetic the cross-power phase is that of a half-pixel shift (two EQUAL peaks on neighbouring pixels for an odd
+    extent); the bump separates them by ~1e-7 .. 1e-5 of the peak -- far above complex128 rounding, at or below float32's.
     Both tiles hold a 0 and a 65535 outside the strips, so normalize_image is the identity on them."""
     rng = np.random.default_rng(seed)
     m = int((H if direction == H_DIR else W) * 0.25)
@@ -132,6 +132,7 @@ def _tie_tiles(H, W, ov, bump, direction, seed):
     s = rng.integers(0, 2, (n_long, ov)).astype(np.int64)
     t = 30000 * (s + np.roll(s, 1, axis=1))
     t[5, 7] += bump
+    s = s * scale_a
     A = np.zeros((H, W), np.uint16)
     B = np.zeros((H, W), np.uint16)
     if direction == H_DIR:
@@ -165,6 +166,19 @@ def test_auto_repeats_coarse_near_ties_in_float64(ctx, bump):
     # plain float32 reports the same thin margin (so a caller can see it) even if it picks the other pixel
     for r in ctx.register_pairs(job, (H, W), ov, ov, precision=F32):
         assert r["precision"] == F32 and r["peak"] - r["second"] <= TIE * r["peak"]
+
+
+def test_auto_repeats_pairs_with_strips_of_very_different_magnitude(ctx):
+    """The radix path transforms both strips as ONE complex array (a + i b); a strip 30000 x fainter than its partner is
+    then recovered by cancellation and float32 keeps ~3 digits of its spectrum -- the correlation is off by ~2e-4 of the
+    peak, more than the near-tie threshold can see.  AUTO detects the magnitude ratio itself and repeats the pair."""
+    H = W = 256
+    ov = 33
+    job = [_tie_tiles(H, W, ov, 300, d, seed=11, scale_a=1) + (d,) for d in (H_DIR, V_DIR)]
+    exp = [oracle(a, b, ov, d, 10) for a, b, d in job]
+    for r, (ints, shift, det) in zip(ctx.register_pairs(job, (H, W), ov, ov, precision=AUTO), exp):
+        assert r["precision"] == F64
+        assert r["coarse"] == det["coarse"] and r["fine"] == det["fine"] and (r["dy"], r["dx"]) == ints
 
 
 def test_runner_up_excludes_the_peak_band(ctx):
