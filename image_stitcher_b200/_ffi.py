@@ -153,6 +153,16 @@ def _ptr(a) -> int:
     raise TypeError(f"cannot take the address of {type(a)}")
 
 
+def _check_tile(a, tile_shape, i):
+    """The library reads tile_h * tile_w pixels from every tile pointer: an ndarray of another shape, or a
+    non-contiguous one, must not be handed over (raw addresses and device tensors are the caller's responsibility)."""
+    if isinstance(a, np.ndarray):
+        if tuple(a.shape) != (int(tile_shape[0]), int(tile_shape[1])):
+            raise ValueError(f"tile {i}: shape {a.shape} != tile_shape {tuple(tile_shape)}")
+        if not a.flags.c_contiguous:
+            raise ValueError(f"tile {i}: array is not C-contiguous")
+
+
 class Context:
     """One ``sb_ctx``: create it lazily inside the worker process (after fork), one per device."""
 
@@ -271,6 +281,7 @@ class Context:
         arr = (SbTile * max(n, 1))()
         for i, t in enumerate(tiles):
             px, x, y, c, z, ct, cb, cl, cr = t
+            _check_tile(px, tile_shape, i)
             arr[i] = SbTile(_ptr(px), int(x), int(y), int(c), int(z), int(ct), int(cb), int(cl), int(cr))
         if dtype is None:                      # pixel dtype: from the first tile (or the canvas) when they are arrays
             dtype = _pixel_dtype(tiles[0][0] if n else out, _pixel_dtype(out))
@@ -292,10 +303,11 @@ class Context:
             tiles = kw.pop("tiles")
             n = len(tiles)
             arr = (SbTile * max(n, 1))()
+            ts, cs, out = kw.pop("tile_shape"), kw.pop("canvas_shape"), kw.pop("out")
             for i, (px, x, y, c, z, ct, cb, cl, cr) in enumerate(tiles):
+                _check_tile(px, ts, i)
                 arr[i] = SbTile(_ptr(px), int(x), int(y), int(c), int(z), int(ct), int(cb), int(cl), int(cr))
             arrs.append(arr)
-            ts, cs, out = kw.pop("tile_shape"), kw.pop("canvas_shape"), kw.pop("out")
             dtype = kw.get("dtype")
             if dtype is None:
                 dtype = _pixel_dtype(tiles[0][0] if n else out, _pixel_dtype(out))
@@ -337,6 +349,8 @@ class Context:
             dtype = _pixel_dtype(pairs[0][0])
         arr = (SbPair * n)()
         for i, (ref, mov, d) in enumerate(pairs):
+            _check_tile(ref, tile_shape, i)
+            _check_tile(mov, tile_shape, i)
             arr[i] = SbPair(_ptr(ref), _ptr(mov), int(d), 0)
         res = (SbPairResult * n)()
         job = SbRegisterJob(arr, n, int(tile_shape[0]), int(tile_shape[1]), int(dtype), mem, int(max_overlap_x),

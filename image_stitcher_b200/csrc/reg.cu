@@ -830,7 +830,7 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     const size_t o_Ex = carve((size_t)B * rs * Sw * sizeof(T2));
     const size_t o_Ey = carve((size_t)B * rs * Sh * sizeof(T2));
     const size_t o_T = carve((size_t)B * rs * Sh * sizeof(T2));
-    const size_t o_best = carve((size_t)B * nrb_inv * sizeof(CtaBest));
+    const size_t o_best = carve((size_t)B * std::max(nrb_inv, Sh >> 7) * sizeof(CtaBest));
     const size_t o_mag = carve((size_t)B * rs * rs * sizeof(double));
     const size_t o_rmax = carve((size_t)B * Sh * sizeof(float));
     const size_t o_Zh = carve(tc.ok ? sb_tc_zh_bytes(tc, B) : 0);
@@ -916,8 +916,14 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
             k1<<<nb * nrb_fwd, 256, smem_x, ws>>>(d_pairs + p0, d_mm, tile_w, Sh, Sw, lpbx, nrb_fwd, swap, maxval, tw_x, px_plan, cx, cxn, Zw, d_nz + p0, d_sums + 2 * p0);
             k2<<<nb * ncg, 256, smem_y, ws>>>(Sh, Sw, ncg, tw_y, py_plan, cy, cyn, Zw, Rw);
         }
-        k3<<<nb * nrb_inv, 256, smem_x, ws>>>(Sh, Sw, lpbx, nrb_inv, swap, tw_x, px_plan, cx, cxn, Zw, bestw, rmaxw);
-        peak_final_kernel<<<nb, 32, 0, ws>>>(bestw, nrb_inv, Sh, Sw, swap, rmaxw, d_nz + p0, d_fault, tc.ok ? nullptr : d_sums + 2 * p0, peaks + p0);
+        if (tc.ok && tc.inverse) {
+            rc = sb_tc_inverse(ctx, ws, tc, nb, Zw, Sw, swap, bestw, rmaxw, d_fault);
+            if (rc) return rc;
+            ctx->launches--;
+        } else {
+            k3<<<nb * nrb_inv, 256, smem_x, ws>>>(Sh, Sw, lpbx, nrb_inv, swap, tw_x, px_plan, cx, cxn, Zw, bestw, rmaxw);
+        }
+        peak_final_kernel<<<nb, 32, 0, ws>>>(bestw, (tc.ok && tc.inverse) ? (Sh >> 7) : nrb_inv, Sh, Sw, swap, rmaxw, d_nz + p0, d_fault, tc.ok ? nullptr : d_sums + 2 * p0, peaks + p0);
         ctx->launches += 4;
         if (uf > 1) {
             updft_twiddle_kernel<T><<<dim3(8, nb), 256, 0, ws>>>(peaks + p0, Sh, Sw, uf, rs, dftshift, Exw, Eyw);

@@ -13,28 +13,35 @@
 namespace {
 
 // ==========================================================================================================
-// T1  fwd_x_tc_kernel: real DFT of the strip rows along the SHORT axis (length n, any n) on the tensor cores.
+// T1 / T3  xdft_tc_kernel: the transforms along the SHORT strip axis (length n, ANY n) on the tensor cores.
 //
-// For a real row x[0..n) the half spectrum X[k], k = 0..n/2, is two real matrix products of the row folded about its
-// centre -- e[j] = x[j] + x[n-j], o[j] = x[j] - x[n-j] (e[0] = x[0], e[n/2] = x[n/2] for even n):
+// MODE 0 (forward, T1).  For a real row x[0..n) the half spectrum X[k], k = 0..n/2, is two real matrix products of the
+// row folded about its centre -- e[j] = x[j] + x[n-j], o[j] = x[j] - x[n-j] (e[0] = x[0], e[n/2] = x[n/2] for even n):
 //         Re X[k] =  sum_j e[j] cos(2 pi j k / n)            Im X[k] = -sum_j o[j] sin(2 pi j k / n)
-// A block owns 128 rows (M) of one strip image; K = j runs in chunks of 8 through an STAGES-deep ring of shared-memory
-// operand stages: the A sub-tiles (e / o, tf32 hi / lo) are produced by 8 warps from the stretched strip rows staged in
-// shared memory (crop + normalize_image's stretch fused into the coalesced load, as in the radix path), the B sub-tiles
+// MODE 1 (inverse + argmax, T3).  The correlation row cc[y][x] from the half spectrum Y[y][k] of a REAL signal, folded
+// on the output side: with c_0 = c_{n/2} = 1, c_k = 2 otherwise,
+//         P[x] = sum_k Re Y[k] c_k cos(2 pi k x / n)         Q[x] = -sum_k Im Y[k] c_k sin(2 pi k x / n)
+//         cc[x] = P[x] + Q[x],   cc[n - x] = P[x] - Q[x]     (x = 0 .. n/2)
+//
+// A block owns 128 rows (M) of one strip image / one pair; K runs in chunks of 8 through a kTcStages-deep ring of
+// shared-memory operand stages: the A sub-tiles (part 0 / part 1, tf32 hi / lo) are produced by 8 warps -- MODE 0 from
+// the stretched strip rows staged in shared memory (crop + normalize_image's stretch fused into the coalesced load, as
+// in the radix path), MODE 1 straight from the column pass's output (one row per lane: coalesced) -- the B sub-tiles
 // (cos / -sin tables, hi / lo, laid out on the host exactly as the tensor core reads them) arrive by 1-D bulk copies.
-// One thread issues 6 tcgen05.mma.kind::tf32 per chunk (3-term split x {Re, Im}) into TMEM columns [0, NP) / [NP, 2 NP).
-// The epilogue reads the accumulators back (one row per thread) and stores the spectrum TRANSPOSED -- Zh[img][k][y],
-// y fastest -- which is a whole 256-byte warp store per k because TMEM lane == strip row.
+// One thread issues 6 tcgen05.mma.kind::tf32 per chunk (3-term split x 2 parts) into TMEM columns [0, NP) / [NP, 2 NP).
+// Epilogue, one row per thread (TMEM lane == strip row): MODE 0 stores the spectrum TRANSPOSED, Zh[img][k][y] -- a whole
+// 256-byte warp store per k; MODE 1 folds P, Q into |cc| and keeps the first maximum, the second-largest value and the
+// row maximum (what rows_inv_argmax_kernel of the radix path emits).
 // ==========================================================================================================
 constexpr int kTcThreads = 288;          // warps 0-7: operand producers + epilogue; warp 8: bulk copies + MMA issue
 constexpr int kTcStages = 3;
-constexpr int kAStage = 4 * 128 * 32;    // e_hi | e_lo | o_hi | o_lo, each 128 rows x 8 k (K-major, LBO 2048, SBO 128)
+constexpr int kAStage = 4 * 128 * 32;    // part0_hi | part0_lo | part1_hi | part1_lo, each 128 rows x 8 k (K-major, LBO 2048, SBO 128)
 
 struct TcSmem {                          // offsets into dynamic shared memory
     int a_off, b_off, stg_off, bar_off, total;
     int b_stage;                         // bytes of one B stage: 4 sub-tiles of NP rows x 8 k
 };
-__host__ __device__ inline TcSmem tc_smem_layout(int NP, int pitch_w) {
+__host__ __device__ inline TcSmem tc_smem_layout(int NP, int pitch_w) {   // pitch_w = 0: no staged strip rows (MODE 1)
     TcSmem L;
     L.b_stage = 4 * NP * 32;
     L.a_off = 0;
@@ -45,12 +52,29 @@ __host__ __device__ inline TcSmem tc_smem_layout(int NP, int pitch_w) {
     return L;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
-fwd_x_tc_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm, int tile_w, int Sh, int n, int NP, int nchunks,
-                int pitch_w, int swap, int maxval, const uint8_t* __restrict__ Bmat, float2* __restrict__ Zh,
-                int* __restrict__ nonzero, int* __restrict__ fault) {
+struct TcArgs {
+    // geometry
+    int Sh, n, NP, nchunks, pitch_w, swap;
+    const uint8_t* Bmat;                 // operand images of this mode's tables
+    int* fault;
+    // MODE 0
+    const PairDesc* pairs;
+    const int2* mm;
+    int tile_w, maxval;
+    float2* Zh;
+    int* nonzero;
+    // MODE 1
+    const float2* Y;                     // [pair][line][y], the first n/2 + 1 lines of every pair are read
+    int lines_in;                        // lines per pair in Y
+    CtaBest* best;                       // [pair][Sh / 128]
+    float* rowmax;                       // [pair][Sh]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const TcSmem L = tc_smem_layout(NP, pitch_w);
+    const int Sh = g.Sh, n = g.n, NP = g.NP, nchunks = g.nchunks;
+    const TcSmem L = tc_smem_layout(NP, MODE == 0 ? g.pitch_w : 0);
     uint8_t* a_st = smem + L.a_off;
     uint8_t* b_st = smem + L.b_off;
     uint16_t* stg = reinterpret_cast<uint16_t*>(smem + L.stg_off);
@@ -58,12 +82,17 @@ fwd_x_tc_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm,
     uint64_t* empty = full + kTcStages;                                       // [kTcStages]
     uint64_t* done = empty + kTcStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    __shared__ float s_row[128];                                              // MODE 1: row maxima / block reduction
+    __shared__ double s_val[8], s_sec[8];
+    __shared__ int s_idx[8];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int tiles = Sh >> 7;
-    const int mt = blockIdx.x % tiles, img = (blockIdx.x / tiles) & 1, p = blockIdx.x / (2 * tiles);
+    const int mt = blockIdx.x % tiles;
+    const int img = MODE == 0 ? (blockIdx.x / tiles) & 1 : 0;
+    const int p = MODE == 0 ? blockIdx.x / (2 * tiles) : blockIdx.x / tiles;
     const int y0 = mt << 7;
     const int nb = n / 2 + 1, nh = n / 2, no = (n - 1) / 2;
-    const int pitch_h = pitch_w * 2;
+    const int pitch_h = g.pitch_w * 2;
     const uint32_t tmem_cols = 2 * NP <= 32 ? 32 : 2 * NP <= 64 ? 64 : 2 * NP <= 128 ? 128 : 2 * NP <= 256 ? 256 : 512;
 
     if (warp == 8) {
@@ -81,16 +110,17 @@ fwd_x_tc_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm,
         if (lane == 0)
             for (int c = 0; c < kTcStages && c < nchunks; ++c) {              // the first B stages need no free slot
                 umma::mbar_expect_tx(full + c, (uint32_t)L.b_stage);
-                umma::bulk_g2s(b_st + c * L.b_stage, Bmat + (size_t)c * L.b_stage, (uint32_t)L.b_stage, full + c);
+                umma::bulk_g2s(b_st + c * L.b_stage, g.Bmat + (size_t)c * L.b_stage, (uint32_t)L.b_stage, full + c);
             }
-    } else {
+    } else if (MODE == 0) {
         // ---- strip rows -> shared memory: crop + stretch fused into the load (normalize_image, :844-855)
-        const PairDesc pd = pairs[p];
+        const PairDesc pd = g.pairs[p];
         const uint16_t* src = img ? pd.b : pd.a;
-        const int2 m = mm[img ? pd.b_tile : pd.a_tile];
+        const int2 m = g.mm[img ? pd.b_tile : pd.a_tile];
+        const int maxval = g.maxval, tile_w = g.tile_w;
         const float inv = m.y > m.x ? (float)maxval / (float)(m.y - m.x) : 0.f;
         int seen = 0;
-        if (!swap) {
+        if (!g.swap) {
             for (int r = warp; r < 128; r += 8) {
                 const uint16_t* row = src + (size_t)(y0 + r) * tile_w;
                 uint16_t* dst = stg + r * pitch_h;
@@ -129,7 +159,9 @@ fwd_x_tc_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm,
         }
         // an all-zero strip has an exactly zero spectrum in the reference: record whether this one has a non-zero pixel
         seen = __reduce_or_sync(0xffffffffu, (unsigned)seen);
-        if (lane == 0 && seen) atomicOr(&nonzero[p], img ? 2 : 1);
+        if (lane == 0 && seen) atomicOr(&g.nonzero[p], img ? 2 : 1);
+    } else {
+        if (t < 128) s_row[t] = 0.f;
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -165,57 +197,137 @@ fwd_x_tc_kernel(const PairDesc* __restrict__ pairs, const int2* __restrict__ mm,
                     const int sp = (c - 1) % kTcStages, up = (c - 1) / kTcStages;
                     ok = ok && umma::mbar_wait(empty + sp, up & 1);
                     umma::mbar_expect_tx(full + sp, (uint32_t)L.b_stage);
-                    umma::bulk_g2s(b_st + sp * L.b_stage, Bmat + (size_t)cp * L.b_stage, (uint32_t)L.b_stage, full + sp);
+                    umma::bulk_g2s(b_st + sp * L.b_stage, g.Bmat + (size_t)cp * L.b_stage, (uint32_t)L.b_stage, full + sp);
                 }
             }
             umma::mma_commit(done);
-            if (!ok) atomicExch(fault, 1);
+            if (!ok) atomicExch(g.fault, 1);
         }
     } else {
-        // ---- operand producers: thread = (row, half): four consecutive j of one row per chunk
+        // ---- operand producers: thread = (row, half): four consecutive k of one row per chunk
         const int row = t & 127, half = t >> 7;
         const uint16_t* srow = stg + row * pitch_h;
+        const float2* yrow = MODE == 1 ? g.Y + (size_t)p * g.lines_in * Sh + y0 + row : nullptr;
+        float2 nxt[4];                                             // MODE 1: the next chunk's values, already in flight
+        if (MODE == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = 4 * half + i;
+                nxt[i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
+            }
+        }
         bool ok = true;
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % kTcStages, u = c / kTcStages;
-            if (u >= 1) ok = umma::mbar_wait(empty + s, (u - 1) & 1) && ok;
-            float eh[4], el[4], oh[4], ol[4];
+            float ph[4], pl[4], qh[4], ql[4];
+            if (MODE == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int j = 8 * c + 4 * half + i;
-                const int xa = j <= nh ? (int)srow[j] : 0;
-                const bool paired = j >= 1 && j <= no;
-                const int xb = paired ? (int)srow[n - j] : 0;
-                const float e = (float)(xa + xb) * (float)kInScale, o = paired ? (float)(xa - xb) * (float)kInScale : 0.f;
-                umma::split_tf32(e, eh[i], el[i]);
-                umma::split_tf32(o, oh[i], ol[i]);
+                for (int i = 0; i < 4; ++i) {
+                    const int j = 8 * c + 4 * half + i;
+                    const int xa = j <= nh ? (int)srow[j] : 0;
+                    const bool paired = j >= 1 && j <= no;
+                    const int xb = paired ? (int)srow[n - j] : 0;
+                    const float e = (float)(xa + xb) * (float)kInScale, o = paired ? (float)(xa - xb) * (float)kInScale : 0.f;
+                    umma::split_tf32(e, ph[i], pl[i]);
+                    umma::split_tf32(o, qh[i], ql[i]);
+                }
+            } else {
+                float2 cur[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+                if (c + 1 < nchunks) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = 8 * (c + 1) + 4 * half + i;
+                        nxt[i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    umma::split_tf32(cur[i].x, ph[i], pl[i]);
+                    umma::split_tf32(cur[i].y, qh[i], ql[i]);
+                }
             }
+            if (u >= 1) ok = umma::mbar_wait(empty + s, (u - 1) & 1) && ok;
             uint8_t* dst = a_st + s * kAStage + half * 2048 + row * 16;
-            *reinterpret_cast<float4*>(dst) = make_float4(eh[0], eh[1], eh[2], eh[3]);
-            *reinterpret_cast<float4*>(dst + 4096) = make_float4(el[0], el[1], el[2], el[3]);
-            *reinterpret_cast<float4*>(dst + 8192) = make_float4(oh[0], oh[1], oh[2], oh[3]);
-            *reinterpret_cast<float4*>(dst + 12288) = make_float4(ol[0], ol[1], ol[2], ol[3]);
+            *reinterpret_cast<float4*>(dst) = make_float4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<float4*>(dst + 4096) = make_float4(pl[0], pl[1], pl[2], pl[3]);
+            *reinterpret_cast<float4*>(dst + 8192) = make_float4(qh[0], qh[1], qh[2], qh[3]);
+            *reinterpret_cast<float4*>(dst + 12288) = make_float4(ql[0], ql[1], ql[2], ql[3]);
             umma::fence_smem_to_async();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(full + s);
         }
-        // ---- epilogue: TMEM -> registers -> Zh[img][k][y]
+        // ---- epilogue: TMEM -> registers
         ok = umma::mbar_wait(done, 0) && ok;
         umma::fence_after_sync();
+        const int q = warp & 3, hcol = warp >> 2;
+        const int kbeg = hcol * (NP >> 1), kend = kbeg + (NP >> 1);
+        const uint32_t trow = tb + ((uint32_t)(32 * q) << 16);
         if (!ok) {
-            if (lane == 0) atomicExch(fault, 1);
-        } else {
-            const int q = warp & 3, hcol = warp >> 2;
-            const int kbeg = hcol * (NP >> 1), kend = kbeg + (NP >> 1);
-            float2* zp = Zh + ((size_t)(p * 2 + img) * nb) * Sh + y0 + 32 * q + lane;
+            if (lane == 0) atomicExch(g.fault, 1);
+        } else if (MODE == 0) {
+            float2* zp = g.Zh + ((size_t)(p * 2 + img) * nb) * Sh + y0 + 32 * q + lane;
             for (int k0 = kbeg; k0 < kend; k0 += 8) {
                 uint32_t re[8], im[8];
-                umma::tmem_ld8(tb + ((uint32_t)(32 * q) << 16) + k0, re);
-                umma::tmem_ld8(tb + ((uint32_t)(32 * q) << 16) + NP + k0, im);
+                umma::tmem_ld8(trow + k0, re);
+                umma::tmem_ld8(trow + NP + k0, im);
                 umma::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     if (k0 + i < nb) zp[(size_t)(k0 + i) * Sh] = make_float2(__uint_as_float(re[i]), __uint_as_float(im[i]));
+            }
+        }
+        if (MODE == 1) {
+            // |cc| of this thread's row over its half of the folded columns: first maximum (ties -> lowest index in the C
+            // order of the ORIGINAL strip), second-largest value, row maximum
+            const int y = y0 + 32 * q + lane;
+            float bv = -1.f, b2 = -1.f, rm = 0.f;
+            int bi = 0x7fffffff;
+            if (ok) {
+                for (int x0 = kbeg; x0 < kend; x0 += 8) {
+                    uint32_t pr[8], qr[8];
+                    umma::tmem_ld8(trow + x0, pr);
+                    umma::tmem_ld8(trow + NP + x0, qr);
+                    umma::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int x = x0 + i;
+                        const float P = __uint_as_float(pr[i]), Q = __uint_as_float(qr[i]);
+                        if (x <= nh) {
+                            const float v = fabsf(P + Q);
+                            top2_update<float>(bv, bi, b2, v, g.swap ? x * Sh + y : y * n + x);
+                            rm = fmaxf(rm, v);
+                        }
+                        if (x >= 1 && x <= no) {
+                            const float v = fabsf(P - Q);
+                            const int xm = n - x;
+                            top2_update<float>(bv, bi, b2, v, g.swap ? xm * Sh + y : y * n + xm);
+                            rm = fmaxf(rm, v);
+                        }
+                    }
+                }
+                atomicMax(reinterpret_cast<int*>(&s_row[32 * q + lane]), __float_as_int(rm));   // non-negative floats order as ints
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const float o2 = __shfl_xor_sync(0xffffffffu, b2, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                top2_merge<float>(bv, bi, b2, ov, oi, o2);
+            }
+            if (lane == 0) { s_val[warp] = (double)bv; s_sec[warp] = (double)b2; s_idx[warp] = bi; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");             // warps 0-7 only (warp 8 waits at the final barrier)
+            const double sc = 1.0 / ((double)Sh * (double)n);
+            if (t < 128) g.rowmax[(size_t)p * Sh + y0 + t] = (float)((double)s_row[t] * sc);
+            if (t == 0) {
+                double b = s_val[0], c2 = s_sec[0];
+                int i0 = s_idx[0];
+                for (int w = 1; w < 8; ++w) top2_merge<double>(b, i0, c2, s_val[w], s_idx[w], s_sec[w]);
+                CtaBest& o = g.best[(size_t)p * tiles + mt];
+                o.val = b * sc;
+                o.second = c2 > 0.0 ? c2 * sc : 0.0;
+                o.idx = i0;
             }
         }
     }
@@ -450,6 +562,41 @@ int sb_tc_plan(sb_ctx* ctx, int Sh, int n, TcPlan* plan) {
         it = ctx->twiddle_cache.emplace(key, b).first;
     }
     plan->Bfwd = reinterpret_cast<const uint8_t*>(it->second.p);
+    // inverse tables: per chunk [c cos_hi | c cos_lo | -c sin_hi | -c sin_lo], NP rows (output column x) x 8 (bin k);
+    // c_k = 1 for k = 0 and the Nyquist bin, 2 otherwise (the conjugate half of the spectrum folded in)
+    const uint64_t keyi = ((uint64_t)4 << 40) | (uint64_t)n;
+    auto iti = ctx->twiddle_cache.find(keyi);
+    if (iti == ctx->twiddle_cache.end()) {
+        std::vector<float> img((size_t)plan->nchunks * 4 * NP * 8, 0.0f);
+        const long double tau = 6.283185307179586476925286766559L;
+        for (int c = 0; c < plan->nchunks; ++c)
+            for (int x = 0; x <= nh; ++x)
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int k = 8 * c + kk;
+                    if (k > nh) continue;
+                    const long double ck = (k == 0 || 2 * k == n) ? 1.0L : 2.0L;
+                    const long double ang = tau * (long double)(((long long)k * x) % n) / (long double)n;
+                    const float cv = (float)(ck * cosl(ang));
+                    const float sv = (x >= 1 && x <= no && k >= 1 && k <= no) ? (float)(-ck * sinl(ang)) : 0.0f;
+                    float ch, cl, sh, sl;
+                    split_tf32_host(cv, ch, cl);
+                    split_tf32_host(sv, sh, sl);
+                    const size_t base = (size_t)c * 4 * NP * 8, e = (size_t)(kk / 4) * NP * 4 + (size_t)x * 4 + (kk % 4);
+                    img[base + e] = ch;
+                    img[base + (size_t)NP * 8 + e] = cl;
+                    img[base + (size_t)2 * NP * 8 + e] = sh;
+                    img[base + (size_t)3 * NP * 8 + e] = sl;
+                }
+        DevBuf b;
+        int rc = sb_reserve(ctx, b, img.size() * sizeof(float));
+        if (rc) return rc;
+        SB_CUDA(ctx, cudaMemcpy(b.p, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+        iti = ctx->twiddle_cache.emplace(keyi, b).first;
+    }
+    plan->Binv = reinterpret_cast<const uint8_t*>(iti->second.p);
+    plan->smem_inv = tc_smem_layout(NP, 0).total;
+    static const bool no_inv = getenv("SB_REG_NO_TC_INV") != nullptr;
+    plan->inverse = !no_inv;
     // column-pass twiddles: tw[k2][l] = exp(-2 pi i l k2 / 1024)
     const uint64_t key2 = ((uint64_t)3 << 40) | 1024u;
     auto it2 = ctx->twiddle_cache.find(key2);
@@ -476,13 +623,35 @@ int sb_tc_forward(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, const void* 
                   int swap, int maxval, void* Zh, int* d_nonzero, int* d_fault) {
     static bool configured = false;
     if (!configured) {
-        SB_CUDA(ctx, cudaFuncSetAttribute(fwd_x_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SB_CUDA(ctx, cudaFuncSetAttribute(xdft_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
+    TcArgs g = {};
+    g.Sh = plan.Sh; g.n = plan.n; g.NP = plan.NP; g.nchunks = plan.nchunks; g.pitch_w = plan.pitch_w; g.swap = swap;
+    g.Bmat = plan.Bfwd; g.fault = d_fault;
+    g.pairs = static_cast<const PairDesc*>(d_pairs); g.mm = d_mm; g.tile_w = tile_w; g.maxval = maxval;
+    g.Zh = static_cast<float2*>(Zh); g.nonzero = d_nonzero;
     const int grid = n_pairs * 2 * (plan.Sh >> 7);
-    fwd_x_tc_kernel<<<grid, kTcThreads, plan.smem_fwd, st>>>(static_cast<const PairDesc*>(d_pairs), d_mm, tile_w, plan.Sh, plan.n, plan.NP,
-                                                             plan.nchunks, plan.pitch_w, swap, maxval, plan.Bfwd,
-                                                             static_cast<float2*>(Zh), d_nonzero, d_fault);
+    xdft_tc_kernel<0><<<grid, kTcThreads, plan.smem_fwd, st>>>(g);
+    ctx->launches++;
+    SB_CUDA(ctx, cudaGetLastError());
+    return SB_OK;
+}
+
+int sb_tc_inverse(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs, const void* Y, int lines_in, int swap, void* best,
+                  float* rowmax, int* d_fault) {
+    static bool configured = false;
+    if (!configured) {
+        SB_CUDA(ctx, cudaFuncSetAttribute(xdft_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    TcArgs g = {};
+    g.Sh = plan.Sh; g.n = plan.n; g.NP = plan.NP; g.nchunks = plan.nchunks; g.pitch_w = 0; g.swap = swap;
+    g.Bmat = plan.Binv; g.fault = d_fault;
+    g.Y = static_cast<const float2*>(Y); g.lines_in = lines_in;
+    g.best = static_cast<CtaBest*>(best); g.rowmax = rowmax;
+    const int grid = n_pairs * (plan.Sh >> 7);
+    xdft_tc_kernel<1><<<grid, kTcThreads, plan.smem_inv, st>>>(g);
     ctx->launches++;
     SB_CUDA(ctx, cudaGetLastError());
     return SB_OK;

@@ -14,6 +14,9 @@ struct TcPlan {
     int pitch_w = 0;       // 32-bit words per staged strip row (odd: conflict-free column reads)
     int smem_fwd = 0;      // dynamic shared memory of fwd_x_tc_kernel
     const uint8_t* Bfwd = nullptr;   // cos / -sin operand images of the forward transform (device)
+    const uint8_t* Binv = nullptr;   // ... and of the inverse transform
+    int smem_inv = 0;
+    bool inverse = false;            // the inverse short-axis transform + argmax runs on the tensor cores too
     const void* tw1024 = nullptr;    // [k2][l] table of W1024^(l k2) (device, float2)
 };
 
@@ -27,4 +30,8 @@ int sb_tc_forward(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, const void* 
 // (mirror = 1: the conjugate columns are written too) or half arrays of nb lines (mirror = 0, lines_out = nb).
 int sb_tc_columns(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs, const void* Zh, void* R, void* Y, int lines_out,
                   int mirror);
+// Inverse short-axis transform of the half spectrum Y (first nb of `lines_in` lines per pair) fused with the argmax:
+// best[pair][Sh / 128] (CtaBest) and rowmax[pair][Sh], the outputs of rows_inv_argmax_kernel.
+int sb_tc_inverse(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs, const void* Y, int lines_in, int swap, void* best,
+                  float* rowmax, int* d_fault);
 size_t sb_tc_zh_bytes(const TcPlan& plan, int n_pairs);

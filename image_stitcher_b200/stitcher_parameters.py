@@ -36,6 +36,8 @@ class StitchingParameters:
     registration_precision: str = "auto"
     placement: str = "lattice"            # 'lattice' = the reference's single (h_shift, v_shift) model; 'global' = every
                                           # adjacent pair of every region registered, least-squares tile positions
+    visualize_registration: bool = False  # write <out>/horizontal.png / vertical.png like the reference's visualize_image
+                                          # side effect (stitcher_process.py:681, 704, 857-881); off: it costs a host round trip
     device: int = 0
     rank: int = 0                         # multi-GPU: this worker stitches regions rank, rank + world, ...
     world: int = 1

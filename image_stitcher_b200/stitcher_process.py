@@ -71,6 +71,7 @@ class StitcherProcess(Process):
         self.upsample_factor = int(getattr(params, "upsample_factor", 10))
         self.registration_precision = getattr(params, "registration_precision", "auto")
         self.placement = getattr(params, "placement", "lattice")
+        self.visualize_registration = bool(getattr(params, "visualize_registration", False))
         self.tile_positions: Dict[tuple, Dict[tuple, tuple]] = {}     # (t, region) -> {(x_mm, y_mm): (x_px, y_px)}
         self.device = int(getattr(params, "device", 0))
         self.decode_threads = max(1, min(16, os.cpu_count() or 1))
@@ -350,12 +351,46 @@ class StitcherProcess(Process):
         return {"auto": _ffi.SB_PREC_AUTO, "float32": _ffi.SB_PREC_F32, "float64": _ffi.SB_PREC_F64}[self.registration_precision]
 
     def _register(self, pairs, max_x_overlap, max_y_overlap):
-        shape = pairs[0][0].shape
+        shape = tuple(pairs[0][0].shape)
         dt = self._pixel_np()
-        return self.ctx.register_pairs([(np.ascontiguousarray(a, dtype=dt), np.ascontiguousarray(b, dtype=dt), d)
-                                        for a, b, d in pairs],
-                                       shape, max_x_overlap, max_y_overlap, upsample_factor=self.upsample_factor,
+        for a, b, _ in pairs:
+            # the C ABI reads tile_h * tile_w pixels from every pointer: a tile of another shape (different ROI, truncated
+            # file, RGB plane) must not reach it
+            if np.ndim(a) != 2 or tuple(a.shape) != shape or tuple(b.shape) != shape:
+                raise ValueError(f"registration tiles must be 2-D and share one shape: {np.shape(a)} / {np.shape(b)} vs {shape}")
+        job = [(np.ascontiguousarray(a, dtype=dt), np.ascontiguousarray(b, dtype=dt), d) for a, b, d in pairs]
+        if self.visualize_registration:
+            self._visualize_pairs(job, max_x_overlap, max_y_overlap)
+        return self.ctx.register_pairs(job, shape, max_x_overlap, max_y_overlap, upsample_factor=self.upsample_factor,
                                        precision=self._precision())
+
+    def _visualize_pairs(self, job, max_x_overlap, max_y_overlap):
+        """The reference's debug side effect (:681, :704): the normalised overlap strips of the LAST horizontal and the
+        last vertical pair, side by side, as <out>/horizontal.png and <out>/vertical.png."""
+        last = {}
+        for a, b, d in job:
+            last[d] = (a, b)
+        for d, (a, b) in last.items():
+            na, nb = self.normalize_image(a), self.normalize_image(b)
+            if d == _ffi.SB_DIR_HORIZONTAL:
+                m = int(a.shape[0] * 0.25)
+                self.visualize_image(na[m:-m, -max_x_overlap:], nb[m:-m, :max_x_overlap], "horizontal")
+            else:
+                m = int(a.shape[1] * 0.25)
+                self.visualize_image(na[-max_y_overlap:, m:-m], nb[:max_y_overlap, m:-m], "vertical")
+
+    def visualize_image(self, img1, img2, title):
+        """(:857-881) the two strips stacked (side by side for 'horizontal') as an 8-bit PNG in the output folder."""
+        try:
+            import cv2
+            img1, img2 = np.asarray(img1), np.asarray(img2)
+            combined = np.hstack((img1, img2)) if title == "horizontal" else np.vstack((img1, img2))
+            combined8 = (combined / np.iinfo(self.dtype).max * 255).astype(np.uint8)
+            os.makedirs(self.output_folder, exist_ok=True)
+            cv2.imwrite(f"{self.output_folder}/{title}.png", combined8)
+            print(f"Saved {title}.png successfully")
+        except Exception as e:
+            print(f"Error in visualize_image: {e}")
 
     def calculate_horizontal_shift(self, img_left, img_right, max_overlap):
         """(:664-685) -> ``(round(shift[0]), round(shift[1] - strip_width))``."""
@@ -517,6 +552,11 @@ class StitcherProcess(Process):
                     p = geo.place_tile(info["x"], info["y"], self.input_width, self.input_height, xs, ys,
                                        self.pixel_size_um, lattice)
                 for c, plane in self._tile_planes(tile, key[4]):
+                    if plane.shape != (self.input_height, self.input_width):
+                        # the C ABI reads input_height x input_width pixels per tile: skip what does not have them
+                        self.emit_status(f"Error Loading Image {info['filepath']}: shape {plane.shape} != "
+                                         f"{(self.input_height, self.input_width)}")
+                        continue
                     plane = np.ascontiguousarray(plane, dtype=self._pixel_np())
                     keep.append(plane)
                     job.append((plane, p.x, p.y, c, key[3], p.crop_t, p.crop_b, p.crop_l, p.crop_r))
@@ -587,6 +627,13 @@ class StitcherProcess(Process):
         """Same sequence as the reference's ``run`` (:1959-2037)."""
         stime = time.time()
         try:
+            # requests this build does not serve are refused BEFORE any decode / GPU work (ADVICE r1)
+            if not self.output_format.endswith(".zarr"):
+                raise RuntimeError("OME-TIFF output relies on the reference's third-party writers "
+                                   "(out of scope, SURVEY.md section 2); use .ome.zarr")
+            if self.merge_timepoints or self.merge_hcs_regions:
+                self.emit_status("Warning: merge_timepoints / merge_hcs_regions are not implemented (the reference marks its "
+                                 "merges 'not ready', SURVEY.md section 2.3): writing one OME-Zarr per region instead")
             self.emit_status("Extracting Acquisition Metadata...")
             self.get_timepoints()
             self.extract_acquisition_parameters()
@@ -601,9 +648,6 @@ class StitcherProcess(Process):
             from concurrent.futures import ThreadPoolExecutor
             from .shard import wells_for_rank
             my_regions = [self.regions[i] for i in wells_for_rank(len(self.regions), self.world, self.rank)]
-            if not self.output_format.endswith(".zarr"):
-                raise RuntimeError("OME-TIFF output relies on the reference's third-party writers "
-                                   "(out of scope, SURVEY.md section 2); use .ome.zarr")
             work = [(t, r) for t in self.timepoints for r in my_regions]
             for timepoint in self.timepoints:
                 os.makedirs(os.path.join(self.output_folder, f"{timepoint}_stitched"), exist_ok=True)

@@ -42,6 +42,8 @@ def parse_args(argv=None) -> argparse.Namespace:
                    help="lattice = the reference's single shift pair; global = all pairs of every region + least squares")
     p.add_argument("--upsample-factor", type=int, default=10)
     p.add_argument("--registration-precision", choices=["auto", "float32", "float64"], default="auto")
+    p.add_argument("--visualize-registration", action="store_true",
+                   help="write horizontal.png / vertical.png of the registered overlap strips (the reference always does)")
     p.add_argument("--device", type=int, default=0, help="CUDA device index")
     p.add_argument("--devices", default="", help="comma-separated CUDA devices: one worker process per device, regions "
                                                  "(wells) split round-robin, no inter-process exchange needed")
@@ -58,7 +60,8 @@ def create_params(args: argparse.Namespace) -> StitchingParameters:
         "scan_pattern": args.scan_pattern, "merge_timepoints": args.merge_timepoints,
         "merge_hcs_regions": args.merge_hcs_regions, "dynamic_registration": args.dynamic_registration,
         "blend_mode": args.blend_mode, "placement": args.placement, "upsample_factor": args.upsample_factor,
-        "registration_precision": args.registration_precision, "device": args.device})
+        "registration_precision": args.registration_precision, "device": args.device,
+        "visualize_registration": args.visualize_registration})
 
 
 def monitor_process(proc, progress_queue, status_queue, complete_queue, stop_event, poll_s: float = 0.1) -> int:
