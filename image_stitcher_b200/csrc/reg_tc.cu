@@ -33,28 +33,39 @@ namespace {
 // 256-byte warp store per k; MODE 1 folds P, Q into |cc| and keeps the first maximum, the second-largest value and the
 // row maximum (what rows_inv_argmax_kernel of the radix path emits).
 // ==========================================================================================================
-constexpr int kTcThreads = 288;          // warps 0-7: operand producers + epilogue; warp 8: bulk copies + MMA issue
-constexpr int kTcStages = 3;
+// The kernel is PERSISTENT (one block per SM) and warp-specialised, every hand-over an mbarrier:
+//     warps 0-3   loaders      (MODE 0) strip rows of tile i+1 -> stretched uint16 rows in shared memory (2 buffers)
+//     warps 4-7   converters   rows -> A operand stages (fold / split), or Y -> A stages straight from global (MODE 1)
+//     warp  8     one thread   B stages by bulk copy, tcgen05.mma issue, tcgen05.commit
+//     warps 9-12  epilogue     TMEM accumulators of tile i-1 (2 accumulator buffers) -> global
+// so the load of one tile, the operand conversion and the MMAs of the next and the read-back of the previous overlap
+// (the first version ran the three phases one after the other in one-tile blocks: tensor pipe 6 % busy, issue 22 %).
+constexpr int kTcThreads = 13 * 32;
+constexpr int kTcStages = 3;             // operand ring depth (A + B)
 constexpr int kAStage = 4 * 128 * 32;    // part0_hi | part0_lo | part1_hi | part1_lo, each 128 rows x 8 k (K-major, LBO 2048, SBO 128)
 
 struct TcSmem {                          // offsets into dynamic shared memory
     int a_off, b_off, stg_off, bar_off, total;
     int b_stage;                         // bytes of one B stage: 4 sub-tiles of NP rows x 8 k
+    int stg_bytes;                       // bytes of one staged tile (MODE 0): 128 rows of pitch_w words
 };
-__host__ __device__ inline TcSmem tc_smem_layout(int NP, int pitch_w) {   // pitch_w = 0: no staged strip rows (MODE 1)
+__host__ __device__ inline TcSmem tc_smem_layout(int NP, int pitch_w, int stg_bufs) {   // stg_bufs = 0: MODE 1
     TcSmem L;
     L.b_stage = 4 * NP * 32;
+    L.stg_bytes = 128 * pitch_w * 4;
     L.a_off = 0;
     L.b_off = kTcStages * kAStage;
     L.stg_off = L.b_off + kTcStages * L.b_stage;
-    L.bar_off = L.stg_off + 128 * pitch_w * 4;
-    L.total = L.bar_off + 128;
+    L.bar_off = L.stg_off + stg_bufs * L.stg_bytes;
+    L.total = L.bar_off + 256;
     return L;
 }
 
 struct TcArgs {
     // geometry
     int Sh, n, NP, nchunks, pitch_w, swap;
+    int n_tiles;                         // tiles of 128 rows in this launch
+    int stg_bufs, acc_bufs;              // staged-tile buffers (MODE 0: 1 or 2), TMEM accumulator buffers (1 or 2)
     const uint8_t* Bmat;                 // operand images of this mode's tables
     int* fault;
     // MODE 0
@@ -74,263 +85,321 @@ template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int Sh = g.Sh, n = g.n, NP = g.NP, nchunks = g.nchunks;
-    const TcSmem L = tc_smem_layout(NP, MODE == 0 ? g.pitch_w : 0);
+    const TcSmem L = tc_smem_layout(NP, g.pitch_w, MODE == 0 ? g.stg_bufs : 0);
     uint8_t* a_st = smem + L.a_off;
     uint8_t* b_st = smem + L.b_off;
-    uint16_t* stg = reinterpret_cast<uint16_t*>(smem + L.stg_off);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off);          // [kTcStages]
-    uint64_t* empty = full + kTcStages;                                       // [kTcStages]
-    uint64_t* done = empty + kTcStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
-    __shared__ float s_row[128];                                              // MODE 1: row maxima / block reduction
-    __shared__ double s_val[8], s_sec[8];
-    __shared__ int s_idx[8];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    uint64_t* stg_full = bars;                  // [2] loaders -> converters
+    uint64_t* stg_empty = bars + 2;             // [2] converters -> loaders
+    uint64_t* ab_full = bars + 4;               // [kTcStages] converters + bulk copy -> MMA
+    uint64_t* ab_empty = bars + 4 + kTcStages;  // [kTcStages] tcgen05.commit -> converters, bulk copy
+    uint64_t* acc_full = bars + 4 + 2 * kTcStages;   // [2] tcgen05.commit -> epilogue
+    uint64_t* acc_empty = acc_full + 2;         // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    __shared__ double s_val[4], s_sec[4];       // MODE 1: block reduction of the epilogue warps
+    __shared__ int s_idx[4];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int tiles = Sh >> 7;
-    const int mt = blockIdx.x % tiles;
-    const int img = MODE == 0 ? (blockIdx.x / tiles) & 1 : 0;
-    const int p = MODE == 0 ? blockIdx.x / (2 * tiles) : blockIdx.x / tiles;
-    const int y0 = mt << 7;
+    const int tiles = Sh >> 7;                  // tiles per strip image
     const int nb = n / 2 + 1, nh = n / 2, no = (n - 1) / 2;
     const int pitch_h = g.pitch_w * 2;
-    const uint32_t tmem_cols = 2 * NP <= 32 ? 32 : 2 * NP <= 64 ? 64 : 2 * NP <= 128 ? 128 : 2 * NP <= 256 ? 256 : 512;
+    const int acc_cols = 2 * NP;
+    const uint32_t want_cols = (uint32_t)(g.acc_bufs * acc_cols);
+    const uint32_t tmem_cols = want_cols <= 32 ? 32 : want_cols <= 64 ? 64 : want_cols <= 128 ? 128 : want_cols <= 256 ? 256 : 512;
+    const int my_tiles = blockIdx.x < g.n_tiles ? (g.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int my_chunks = my_tiles * nchunks;
 
     if (warp == 8) {
         if (lane == 0) {
-            for (int s = 0; s < kTcStages; ++s) {
-                umma::mbar_init(full + s, 9);             // 8 producer warps + the bulk copy's expect_tx arrival
-                umma::mbar_init(empty + s, 1);            // tcgen05.commit
+            for (int i = 0; i < 2; ++i) {
+                umma::mbar_init(stg_full + i, 4);
+                umma::mbar_init(stg_empty + i, 4);
+                umma::mbar_init(acc_full + i, 1);
+                umma::mbar_init(acc_empty + i, 4);
             }
-            umma::mbar_init(done, 1);
+            for (int s = 0; s < kTcStages; ++s) {
+                umma::mbar_init(ab_full + s, 5);          // 4 converter warps + the bulk copy's expect_tx arrival
+                umma::mbar_init(ab_empty + s, 1);         // tcgen05.commit
+            }
             umma::mbar_init_fence();
         }
         __syncwarp();
         umma::tmem_alloc(tmem_slot, tmem_cols);
         umma::tmem_relinquish();
         if (lane == 0)
-            for (int c = 0; c < kTcStages && c < nchunks; ++c) {              // the first B stages need no free slot
-                umma::mbar_expect_tx(full + c, (uint32_t)L.b_stage);
-                umma::bulk_g2s(b_st + c * L.b_stage, g.Bmat + (size_t)c * L.b_stage, (uint32_t)L.b_stage, full + c);
+            for (int c = 0; c < kTcStages && c < my_chunks; ++c) {           // the first B stages need no free slot
+                umma::mbar_expect_tx(ab_full + c, (uint32_t)L.b_stage);
+                umma::bulk_g2s(b_st + c * L.b_stage, g.Bmat + (size_t)(c % nchunks) * L.b_stage, (uint32_t)L.b_stage, ab_full + c);
             }
-    } else if (MODE == 0) {
-        // ---- strip rows -> shared memory: crop + stretch fused into the load (normalize_image, :844-855)
-        const PairDesc pd = g.pairs[p];
-        const uint16_t* src = img ? pd.b : pd.a;
-        const int2 m = g.mm[img ? pd.b_tile : pd.a_tile];
-        const int maxval = g.maxval, tile_w = g.tile_w;
-        const float inv = m.y > m.x ? (float)maxval / (float)(m.y - m.x) : 0.f;
-        int seen = 0;
-        if (!g.swap) {
-            for (int r = warp; r < 128; r += 8) {
-                const uint16_t* row = src + (size_t)(y0 + r) * tile_w;
-                uint16_t* dst = stg + r * pitch_h;
-                for (int x0 = lane; x0 < n; x0 += 128) {
-                    unsigned v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) v[u] = x0 + 32 * u < n ? row[x0 + 32 * u] : 0u;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (x0 + 32 * u < n) {
-                            const int s = stretch_px(v[u], m.x, m.y, inv, maxval);
-                            seen |= s;
-                            dst[x0 + 32 * u] = (uint16_t)s;
-                        }
-                }
-            }
-        } else {
-            // transposed frame: frame row r is image column y0 + r (contiguous in memory), frame column x is image row x
-            for (int x0 = warp; x0 < n; x0 += 16) {
-                unsigned v[2][4];
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        v[u][q] = x0 + 8 * u < n ? src[(size_t)(x0 + 8 * u) * tile_w + y0 + lane + 32 * q] : 0u;
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (x0 + 8 * u < n) {
-                            const int s = stretch_px(v[u][q], m.x, m.y, inv, maxval);
-                            seen |= s;
-                            stg[(lane + 32 * q) * pitch_h + x0 + 8 * u] = (uint16_t)s;
-                        }
-            }
-        }
-        // an all-zero strip has an exactly zero spectrum in the reference: record whether this one has a non-zero pixel
-        seen = __reduce_or_sync(0xffffffffu, (unsigned)seen);
-        if (lane == 0 && seen) atomicOr(&g.nonzero[p], img ? 2 : 1);
-    } else {
-        if (t < 128) s_row[t] = 0.f;
     }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tb = *tmem_slot;
+    bool ok = true;
 
-    if (warp == 8) {
+    if (warp < 4) {
+        // =========================================================================== loaders (MODE 0)
+        if (MODE == 0) {
+            const int maxval = g.maxval, tile_w = g.tile_w;
+            for (int it = 0; it < my_tiles && ok; ++it) {
+                const int tile = blockIdx.x + it * gridDim.x;
+                const int mt = tile % tiles, img = (tile / tiles) & 1, p = tile / (2 * tiles);
+                const int y0 = mt << 7;
+                const int b = it % g.stg_bufs, u = it / g.stg_bufs;
+                if (u >= 1) ok = umma::mbar_wait(stg_empty + b, (u - 1) & 1);
+                uint16_t* stg = reinterpret_cast<uint16_t*>(smem + L.stg_off + b * L.stg_bytes);
+                const PairDesc pd = g.pairs[p];
+                const uint16_t* src = img ? pd.b : pd.a;
+                const int2 m = g.mm[img ? pd.b_tile : pd.a_tile];
+                const float inv = m.y > m.x ? (float)maxval / (float)(m.y - m.x) : 0.f;
+                int seen = 0;
+                if (!g.swap) {
+                    // crop + stretch fused into the load (normalize_image, :844-855): 4 rows x 4 column slices in flight per lane
+                    for (int r0 = warp * 32; r0 < warp * 32 + 32; r0 += 4) {
+                        for (int x0 = lane; x0 < n; x0 += 128) {
+                            unsigned v[4][4];
+#pragma unroll
+                            for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                                for (int uu = 0; uu < 4; ++uu)
+                                    v[rr][uu] = x0 + 32 * uu < n ? src[(size_t)(y0 + r0 + rr) * tile_w + x0 + 32 * uu] : 0u;
+#pragma unroll
+                            for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                                for (int uu = 0; uu < 4; ++uu)
+                                    if (x0 + 32 * uu < n) {
+                                        const int sv = stretch_px(v[rr][uu], m.x, m.y, inv, maxval);
+                                        seen |= sv;
+                                        stg[(r0 + rr) * pitch_h + x0 + 32 * uu] = (uint16_t)sv;
+                                    }
+                        }
+                    }
+                } else {
+                    // transposed frame: frame row r is image column y0 + r (contiguous in memory), frame column x is image row x.
+                    // Warp w takes image rows x = w, w + 4, ...; a lane the four frame rows lane + 32 q.
+                    for (int x0 = warp; x0 < n; x0 += 16) {
+                        unsigned v[4][4];
+#pragma unroll
+                        for (int uu = 0; uu < 4; ++uu)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                v[uu][q] = x0 + 4 * uu < n ? src[(size_t)(x0 + 4 * uu) * tile_w + y0 + lane + 32 * q] : 0u;
+#pragma unroll
+                        for (int uu = 0; uu < 4; ++uu)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (x0 + 4 * uu < n) {
+                                    const int sv = stretch_px(v[uu][q], m.x, m.y, inv, maxval);
+                                    seen |= sv;
+                                    stg[(lane + 32 * q) * pitch_h + x0 + 4 * uu] = (uint16_t)sv;
+                                }
+                    }
+                }
+                // an all-zero strip has an exactly zero spectrum in the reference: record whether this one has a non-zero pixel
+                seen = __reduce_or_sync(0xffffffffu, (unsigned)seen);
+                if (lane == 0 && seen) atomicOr(&g.nonzero[p], img ? 2 : 1);
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(stg_full + b);
+            }
+        }
+    } else if (warp < 8) {
+        // =========================================================================== converters: one row per thread
+        const int row = t - 128;
+        int gc = 0;                                                // chunks produced so far (ring position)
+        for (int it = 0; it < my_tiles && ok; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int mt = tile % tiles;
+            const int p = MODE == 0 ? tile / (2 * tiles) : tile / tiles;
+            const int y0 = mt << 7;
+            const int b = MODE == 0 ? it % g.stg_bufs : 0, u = MODE == 0 ? it / g.stg_bufs : 0;
+            const uint16_t* srow = nullptr;
+            const float2* yrow = nullptr;
+            float2 nxt[8];
+            if (MODE == 0) {
+                ok = umma::mbar_wait(stg_full + b, u & 1);
+                srow = reinterpret_cast<const uint16_t*>(smem + L.stg_off + b * L.stg_bytes) + row * pitch_h;
+            } else {
+                yrow = g.Y + (size_t)p * g.lines_in * Sh + y0 + row;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) nxt[i] = i < nb ? yrow[(size_t)i * Sh] : make_float2(0.f, 0.f);
+            }
+            for (int c = 0; c < nchunks && ok; ++c, ++gc) {
+                const int s = gc % kTcStages, use = gc / kTcStages;
+                float ph[8], pl[8], qh[8], ql[8];
+                if (MODE == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int j = 8 * c + i;
+                        const int xa = j <= nh ? (int)srow[j] : 0;
+                        const bool paired = j >= 1 && j <= no;
+                        const int xb = paired ? (int)srow[n - j] : 0;
+                        const float e = (float)(xa + xb) * (float)kInScale, o = paired ? (float)(xa - xb) * (float)kInScale : 0.f;
+                        umma::split_tf32(e, ph[i], pl[i]);
+                        umma::split_tf32(o, qh[i], ql[i]);
+                    }
+                } else {
+                    float2 cur[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+                    if (c + 1 < nchunks) {                         // the next chunk's values are in flight while this one is split
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int k = 8 * (c + 1) + i;
+                            nxt[i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        umma::split_tf32(cur[i].x, ph[i], pl[i]);
+                        umma::split_tf32(cur[i].y, qh[i], ql[i]);
+                    }
+                }
+                if (use >= 1) ok = umma::mbar_wait(ab_empty + s, (use - 1) & 1);
+                uint8_t* dst = a_st + s * kAStage + row * 16;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    *reinterpret_cast<float4*>(dst + h * 2048) = make_float4(ph[4 * h], ph[4 * h + 1], ph[4 * h + 2], ph[4 * h + 3]);
+                    *reinterpret_cast<float4*>(dst + h * 2048 + 4096) = make_float4(pl[4 * h], pl[4 * h + 1], pl[4 * h + 2], pl[4 * h + 3]);
+                    *reinterpret_cast<float4*>(dst + h * 2048 + 8192) = make_float4(qh[4 * h], qh[4 * h + 1], qh[4 * h + 2], qh[4 * h + 3]);
+                    *reinterpret_cast<float4*>(dst + h * 2048 + 12288) = make_float4(ql[4 * h], ql[4 * h + 1], ql[4 * h + 2], ql[4 * h + 3]);
+                }
+                umma::fence_smem_to_async();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(ab_full + s);
+            }
+            if (MODE == 0) {                                       // every read of the staged tile is done
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(stg_empty + b);
+            }
+        }
+    } else if (warp == 8) {
+        // =========================================================================== MMA issue + B stages (one thread)
         if (lane == 0) {
             const uint32_t idesc = umma::idesc_tf32(128, NP);
             const uint32_t a0 = umma::smem_addr(a_st), b0 = umma::smem_addr(b_st);
             const uint32_t bsub = (uint32_t)NP * 32, blbo = (uint32_t)NP * 16;
-            bool ok = true;
-            for (int c = 0; c < nchunks && ok; ++c) {
-                const int s = c % kTcStages, u = c / kTcStages;
-                ok = umma::mbar_wait(full + s, u & 1);
-                umma::fence_after_sync();
-                const uint32_t as = a0 + s * kAStage, bs = b0 + s * L.b_stage;
-                const uint64_t eh = umma::desc_kmajor(as, 2048, 128), el = umma::desc_kmajor(as + 4096, 2048, 128);
-                const uint64_t oh = umma::desc_kmajor(as + 8192, 2048, 128), ol = umma::desc_kmajor(as + 12288, 2048, 128);
-                const uint64_t ch = umma::desc_kmajor(bs, blbo, 128), cl = umma::desc_kmajor(bs + bsub, blbo, 128);
-                const uint64_t sh = umma::desc_kmajor(bs + 2 * bsub, blbo, 128), sl = umma::desc_kmajor(bs + 3 * bsub, blbo, 128);
-                const uint32_t acc = c > 0 ? 1u : 0u;
-                umma::mma_tf32(tb, eh, ch, idesc, acc);
-                umma::mma_tf32(tb, el, ch, idesc, 1);
-                umma::mma_tf32(tb, eh, cl, idesc, 1);
-                umma::mma_tf32(tb + NP, oh, sh, idesc, acc);
-                umma::mma_tf32(tb + NP, ol, sh, idesc, 1);
-                umma::mma_tf32(tb + NP, oh, sl, idesc, 1);
-                umma::mma_commit(empty + s);
-                // refill the stage used ONE chunk ago (its MMAs have had a whole chunk to finish)
-                const int cp = c - 1 + kTcStages;
-                if (c >= 1 && cp < nchunks) {
-                    const int sp = (c - 1) % kTcStages, up = (c - 1) / kTcStages;
-                    ok = ok && umma::mbar_wait(empty + sp, up & 1);
-                    umma::mbar_expect_tx(full + sp, (uint32_t)L.b_stage);
-                    umma::bulk_g2s(b_st + sp * L.b_stage, g.Bmat + (size_t)cp * L.b_stage, (uint32_t)L.b_stage, full + sp);
+            int gc = 0;
+            for (int it = 0; it < my_tiles && ok; ++it) {
+                const int acc = it % g.acc_bufs, ua = it / g.acc_bufs;
+                if (ua >= 1) {
+                    ok = umma::mbar_wait(acc_empty + acc, (ua - 1) & 1);
+                    umma::fence_after_sync();
                 }
+                const uint32_t d0 = tb + (uint32_t)(acc * acc_cols);
+                for (int c = 0; c < nchunks && ok; ++c, ++gc) {
+                    const int s = gc % kTcStages, use = gc / kTcStages;
+                    ok = umma::mbar_wait(ab_full + s, use & 1);
+                    umma::fence_after_sync();
+                    const uint32_t as = a0 + s * kAStage, bs = b0 + s * L.b_stage;
+                    const uint64_t eh = umma::desc_kmajor(as, 2048, 128), el = umma::desc_kmajor(as + 4096, 2048, 128);
+                    const uint64_t oh = umma::desc_kmajor(as + 8192, 2048, 128), ol = umma::desc_kmajor(as + 12288, 2048, 128);
+                    const uint64_t ch = umma::desc_kmajor(bs, blbo, 128), cl = umma::desc_kmajor(bs + bsub, blbo, 128);
+                    const uint64_t sh = umma::desc_kmajor(bs + 2 * bsub, blbo, 128), sl = umma::desc_kmajor(bs + 3 * bsub, blbo, 128);
+                    const uint32_t accum = c > 0 ? 1u : 0u;
+                    umma::mma_tf32(d0, eh, ch, idesc, accum);
+                    umma::mma_tf32(d0, el, ch, idesc, 1);
+                    umma::mma_tf32(d0, eh, cl, idesc, 1);
+                    umma::mma_tf32(d0 + NP, oh, sh, idesc, accum);
+                    umma::mma_tf32(d0 + NP, ol, sh, idesc, 1);
+                    umma::mma_tf32(d0 + NP, oh, sl, idesc, 1);
+                    umma::mma_commit(ab_empty + s);
+                    // refill the B stage used ONE chunk ago (its MMAs have had a whole chunk to finish)
+                    const int g2 = gc - 1 + kTcStages;
+                    if (gc >= 1 && g2 < my_chunks) {
+                        const int sp = (gc - 1) % kTcStages, up = (gc - 1) / kTcStages;
+                        ok = ok && umma::mbar_wait(ab_empty + sp, up & 1);
+                        umma::mbar_expect_tx(ab_full + sp, (uint32_t)L.b_stage);
+                        umma::bulk_g2s(b_st + sp * L.b_stage, g.Bmat + (size_t)(g2 % nchunks) * L.b_stage, (uint32_t)L.b_stage, ab_full + sp);
+                    }
+                }
+                umma::mma_commit(acc_full + acc);
             }
-            umma::mma_commit(done);
-            if (!ok) atomicExch(g.fault, 1);
         }
     } else {
-        // ---- operand producers: thread = (row, half): four consecutive k of one row per chunk
-        const int row = t & 127, half = t >> 7;
-        const uint16_t* srow = stg + row * pitch_h;
-        const float2* yrow = MODE == 1 ? g.Y + (size_t)p * g.lines_in * Sh + y0 + row : nullptr;
-        float2 nxt[4];                                             // MODE 1: the next chunk's values, already in flight
-        if (MODE == 1) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int k = 4 * half + i;
-                nxt[i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
-            }
-        }
-        bool ok = true;
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c % kTcStages, u = c / kTcStages;
-            float ph[4], pl[4], qh[4], ql[4];
+        // =========================================================================== epilogue: one row per thread
+        const int q = warp & 3;                                    // TMEM lane quadrant this warp may read
+        const int ew = warp - 9;
+        for (int it = 0; it < my_tiles && ok; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int mt = tile % tiles;
+            const int img = MODE == 0 ? (tile / tiles) & 1 : 0;
+            const int p = MODE == 0 ? tile / (2 * tiles) : tile / tiles;
+            const int y0 = mt << 7;
+            const int acc = it % g.acc_bufs, ua = it / g.acc_bufs;
+            ok = umma::mbar_wait(acc_full + acc, ua & 1);
+            umma::fence_after_sync();
+            const uint32_t trow = tb + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * acc_cols);
+            const int y = y0 + 32 * q + lane;
             if (MODE == 0) {
+                if (ok) {
+                    float2* zp = g.Zh + ((size_t)(p * 2 + img) * nb) * Sh + y;
+                    for (int k0 = 0; k0 < NP; k0 += 8) {
+                        uint32_t re[8], im[8];
+                        umma::tmem_ld8(trow + k0, re);
+                        umma::tmem_ld8(trow + NP + k0, im);
+                        umma::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int j = 8 * c + 4 * half + i;
-                    const int xa = j <= nh ? (int)srow[j] : 0;
-                    const bool paired = j >= 1 && j <= no;
-                    const int xb = paired ? (int)srow[n - j] : 0;
-                    const float e = (float)(xa + xb) * (float)kInScale, o = paired ? (float)(xa - xb) * (float)kInScale : 0.f;
-                    umma::split_tf32(e, ph[i], pl[i]);
-                    umma::split_tf32(o, qh[i], ql[i]);
+                        for (int i = 0; i < 8; ++i)
+                            if (k0 + i < nb) zp[(size_t)(k0 + i) * Sh] = make_float2(__uint_as_float(re[i]), __uint_as_float(im[i]));
+                    }
                 }
             } else {
-                float2 cur[4];
+                // |cc| of this thread's row: first maximum (ties -> lowest index in the C order of the ORIGINAL strip),
+                // second-largest value, row maximum -- what rows_inv_argmax_kernel of the radix path emits
+                float bv = -1.f, b2 = -1.f, rm = 0.f;
+                int bi = 0x7fffffff;
+                if (ok) {
+                    for (int x0 = 0; x0 < NP; x0 += 8) {
+                        uint32_t pr[8], qr[8];
+                        umma::tmem_ld8(trow + x0, pr);
+                        umma::tmem_ld8(trow + NP + x0, qr);
+                        umma::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-                if (c + 1 < nchunks) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int k = 8 * (c + 1) + 4 * half + i;
-                        nxt[i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
+                        for (int i = 0; i < 8; ++i) {
+                            const int x = x0 + i;
+                            const float P = __uint_as_float(pr[i]), Q = __uint_as_float(qr[i]);
+                            if (x <= nh) {
+                                const float v = fabsf(P + Q);
+                                top2_update<float>(bv, bi, b2, v, g.swap ? x * Sh + y : y * n + x);
+                                rm = fmaxf(rm, v);
+                            }
+                            if (x >= 1 && x <= no) {
+                                const float v = fabsf(P - Q);
+                                const int xm = n - x;
+                                top2_update<float>(bv, bi, b2, v, g.swap ? xm * Sh + y : y * n + xm);
+                                rm = fmaxf(rm, v);
+                            }
+                        }
                     }
                 }
+                const double sc = 1.0 / ((double)Sh * (double)n);
+                g.rowmax[(size_t)p * Sh + y] = (float)((double)rm * sc);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    umma::split_tf32(cur[i].x, ph[i], pl[i]);
-                    umma::split_tf32(cur[i].y, qh[i], ql[i]);
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const float o2 = __shfl_xor_sync(0xffffffffu, b2, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    top2_merge<float>(bv, bi, b2, ov, oi, o2);
                 }
+                if (lane == 0) { s_val[ew] = (double)bv; s_sec[ew] = (double)b2; s_idx[ew] = bi; }
+                asm volatile("bar.sync 2, 128;" ::: "memory");         // the four epilogue warps
+                if (ew == 0 && lane == 0) {
+                    double bb = s_val[0], c2 = s_sec[0];
+                    int i0 = s_idx[0];
+                    for (int w = 1; w < 4; ++w) top2_merge<double>(bb, i0, c2, s_val[w], s_idx[w], s_sec[w]);
+                    CtaBest& o = g.best[(size_t)p * tiles + mt];
+                    o.val = bb * sc;
+                    o.second = c2 > 0.0 ? c2 * sc : 0.0;
+                    o.idx = i0;
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");         // s_val is reused by the next tile
             }
-            if (u >= 1) ok = umma::mbar_wait(empty + s, (u - 1) & 1) && ok;
-            uint8_t* dst = a_st + s * kAStage + half * 2048 + row * 16;
-            *reinterpret_cast<float4*>(dst) = make_float4(ph[0], ph[1], ph[2], ph[3]);
-            *reinterpret_cast<float4*>(dst + 4096) = make_float4(pl[0], pl[1], pl[2], pl[3]);
-            *reinterpret_cast<float4*>(dst + 8192) = make_float4(qh[0], qh[1], qh[2], qh[3]);
-            *reinterpret_cast<float4*>(dst + 12288) = make_float4(ql[0], ql[1], ql[2], ql[3]);
-            umma::fence_smem_to_async();
+            umma::fence_before_sync();
             __syncwarp();
-            if (lane == 0) umma::mbar_arrive(full + s);
-        }
-        // ---- epilogue: TMEM -> registers
-        ok = umma::mbar_wait(done, 0) && ok;
-        umma::fence_after_sync();
-        const int q = warp & 3, hcol = warp >> 2;
-        const int kbeg = hcol * (NP >> 1), kend = kbeg + (NP >> 1);
-        const uint32_t trow = tb + ((uint32_t)(32 * q) << 16);
-        if (!ok) {
-            if (lane == 0) atomicExch(g.fault, 1);
-        } else if (MODE == 0) {
-            float2* zp = g.Zh + ((size_t)(p * 2 + img) * nb) * Sh + y0 + 32 * q + lane;
-            for (int k0 = kbeg; k0 < kend; k0 += 8) {
-                uint32_t re[8], im[8];
-                umma::tmem_ld8(trow + k0, re);
-                umma::tmem_ld8(trow + NP + k0, im);
-                umma::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (k0 + i < nb) zp[(size_t)(k0 + i) * Sh] = make_float2(__uint_as_float(re[i]), __uint_as_float(im[i]));
-            }
-        }
-        if (MODE == 1) {
-            // |cc| of this thread's row over its half of the folded columns: first maximum (ties -> lowest index in the C
-            // order of the ORIGINAL strip), second-largest value, row maximum
-            const int y = y0 + 32 * q + lane;
-            float bv = -1.f, b2 = -1.f, rm = 0.f;
-            int bi = 0x7fffffff;
-            if (ok) {
-                for (int x0 = kbeg; x0 < kend; x0 += 8) {
-                    uint32_t pr[8], qr[8];
-                    umma::tmem_ld8(trow + x0, pr);
-                    umma::tmem_ld8(trow + NP + x0, qr);
-                    umma::tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int x = x0 + i;
-                        const float P = __uint_as_float(pr[i]), Q = __uint_as_float(qr[i]);
-                        if (x <= nh) {
-                            const float v = fabsf(P + Q);
-                            top2_update<float>(bv, bi, b2, v, g.swap ? x * Sh + y : y * n + x);
-                            rm = fmaxf(rm, v);
-                        }
-                        if (x >= 1 && x <= no) {
-                            const float v = fabsf(P - Q);
-                            const int xm = n - x;
-                            top2_update<float>(bv, bi, b2, v, g.swap ? xm * Sh + y : y * n + xm);
-                            rm = fmaxf(rm, v);
-                        }
-                    }
-                }
-                atomicMax(reinterpret_cast<int*>(&s_row[32 * q + lane]), __float_as_int(rm));   // non-negative floats order as ints
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const float o2 = __shfl_xor_sync(0xffffffffu, b2, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                top2_merge<float>(bv, bi, b2, ov, oi, o2);
-            }
-            if (lane == 0) { s_val[warp] = (double)bv; s_sec[warp] = (double)b2; s_idx[warp] = bi; }
-            asm volatile("bar.sync 1, 256;" ::: "memory");             // warps 0-7 only (warp 8 waits at the final barrier)
-            const double sc = 1.0 / ((double)Sh * (double)n);
-            if (t < 128) g.rowmax[(size_t)p * Sh + y0 + t] = (float)((double)s_row[t] * sc);
-            if (t == 0) {
-                double b = s_val[0], c2 = s_sec[0];
-                int i0 = s_idx[0];
-                for (int w = 1; w < 8; ++w) top2_merge<double>(b, i0, c2, s_val[w], s_idx[w], s_sec[w]);
-                CtaBest& o = g.best[(size_t)p * tiles + mt];
-                o.val = b * sc;
-                o.second = c2 > 0.0 ? c2 * sc : 0.0;
-                o.idx = i0;
-            }
+            if (lane == 0) umma::mbar_arrive(acc_empty + acc);
         }
     }
+    if (!ok && lane == 0) atomicExch(g.fault, 1);
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 8) umma::tmem_dealloc(tb, tmem_cols);
@@ -529,7 +598,9 @@ int sb_tc_plan(sb_ctx* ctx, int Sh, int n, TcPlan* plan) {
     plan->NP = (plan->nb + 15) & ~15;
     plan->nchunks = (plan->nb + 7) / 8;
     plan->pitch_w = ((n + 1) / 2) | 1;
-    const TcSmem L = tc_smem_layout(plan->NP, plan->pitch_w);
+    plan->acc_bufs = 4 * plan->NP <= 512 ? 2 : 1;
+    plan->stg_bufs = tc_smem_layout(plan->NP, plan->pitch_w, 2).total <= 227 * 1024 ? 2 : 1;
+    const TcSmem L = tc_smem_layout(plan->NP, plan->pitch_w, plan->stg_bufs);
     plan->smem_fwd = L.total;
     if (L.total > 227 * 1024) return SB_OK;
     const int nb = plan->nb, NP = plan->NP, nh = n / 2, no = (n - 1) / 2;
@@ -594,7 +665,7 @@ int sb_tc_plan(sb_ctx* ctx, int Sh, int n, TcPlan* plan) {
         iti = ctx->twiddle_cache.emplace(keyi, b).first;
     }
     plan->Binv = reinterpret_cast<const uint8_t*>(iti->second.p);
-    plan->smem_inv = tc_smem_layout(NP, 0).total;
+    plan->smem_inv = tc_smem_layout(NP, 0, 0).total;
     static const bool no_inv = getenv("SB_REG_NO_TC_INV") != nullptr;
     plan->inverse = !no_inv;
     // column-pass twiddles: tw[k2][l] = exp(-2 pi i l k2 / 1024)
@@ -631,7 +702,8 @@ int sb_tc_forward(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, const void* 
     g.Bmat = plan.Bfwd; g.fault = d_fault;
     g.pairs = static_cast<const PairDesc*>(d_pairs); g.mm = d_mm; g.tile_w = tile_w; g.maxval = maxval;
     g.Zh = static_cast<float2*>(Zh); g.nonzero = d_nonzero;
-    const int grid = n_pairs * 2 * (plan.Sh >> 7);
+    g.n_tiles = n_pairs * 2 * (plan.Sh >> 7); g.stg_bufs = plan.stg_bufs; g.acc_bufs = plan.acc_bufs;
+    const int grid = std::min(g.n_tiles, ctx->sm_count);
     xdft_tc_kernel<0><<<grid, kTcThreads, plan.smem_fwd, st>>>(g);
     ctx->launches++;
     SB_CUDA(ctx, cudaGetLastError());
@@ -650,7 +722,8 @@ int sb_tc_inverse(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs,
     g.Bmat = plan.Binv; g.fault = d_fault;
     g.Y = static_cast<const float2*>(Y); g.lines_in = lines_in;
     g.best = static_cast<CtaBest*>(best); g.rowmax = rowmax;
-    const int grid = n_pairs * (plan.Sh >> 7);
+    g.n_tiles = n_pairs * (plan.Sh >> 7); g.stg_bufs = 0; g.acc_bufs = plan.acc_bufs;
+    const int grid = std::min(g.n_tiles, ctx->sm_count);
     xdft_tc_kernel<1><<<grid, kTcThreads, plan.smem_inv, st>>>(g);
     ctx->launches++;
     SB_CUDA(ctx, cudaGetLastError());

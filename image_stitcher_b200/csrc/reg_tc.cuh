@@ -16,6 +16,7 @@ struct TcPlan {
     const uint8_t* Bfwd = nullptr;   // cos / -sin operand images of the forward transform (device)
     const uint8_t* Binv = nullptr;   // ... and of the inverse transform
     int smem_inv = 0;
+    int stg_bufs = 1, acc_bufs = 1;  // staged-tile buffers (forward), TMEM accumulator buffers
     bool inverse = false;            // the inverse short-axis transform + argmax runs on the tensor cores too
     const void* tw1024 = nullptr;    // [k2][l] table of W1024^(l k2) (device, float2)
 };

@@ -64,8 +64,10 @@ def test_tensor_core_stages_match_numpy(ctx, tiles, direction, ov):
     P = A * np.conj(B)
     mag = np.abs(P)
     Rn = P / np.maximum(mag, 1e-300)
-    strong = mag > 1e-4 * np.median(mag)
-    assert np.abs(R[:nb] - Rn)[strong].max() < 5e-4               # float32 phase error grows as |P| shrinks
+    # float32 phase error grows as |P| shrinks (the spectra carry an ABSOLUTE error ~1e-7 of their largest bins): weigh
+    # the error of a bin by its magnitude relative to the median bin
+    weight = np.minimum(mag / np.median(mag), 1.0)
+    assert (np.abs(R[:nb] - Rn) * weight).max() < 1e-4
     assert np.abs(np.abs(R[:nb]) - 1.0).max() < 1e-5
     Yn = sfft.ifft(R[:nb].astype(np.complex128), axis=1) * Sh
     assert np.abs(Y[:nb] - Yn).max() / np.abs(Yn).max() < 2e-6

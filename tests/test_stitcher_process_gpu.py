@@ -340,3 +340,59 @@ def test_process_cli_worker_process_end_to_end(tmp_path):
     bad = subprocess.run([sys.executable, "-m", "image_stitcher_b200.stitcher_process_cli", "-i", str(tmp_path / "missing")],
                          cwd=ROOT, capture_output=True, text=True, timeout=120)
     assert bad.returncode != 0
+
+
+def test_visualize_registration_writes_the_reference_pngs(tmp_path):
+    """a15: with visualize_registration the overlap strips of the registered pairs land in <out>/horizontal.png and
+    vertical.png exactly as the reference's visualize_image builds them (:857-881); off by default."""
+    import cv2
+    from oracle import stitch_ref as sr
+    g, st, tiles, kw = load_golden("reg_2x2_mono")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    s = _make(root, st, visualize_registration=True)
+    try:
+        _prepare(s)
+        s.calculate_shifts(s.timepoints[0], s.regions[0])
+        assert tuple(s.h_shift) == tuple(int(v) for v in g["h_shift"])
+        from image_stitcher_b200 import geometry as geo
+        xs, ys = list(s.x_positions), list(s.y_positions)
+        ovx, ovy = geo.strip_overlaps(s.input_width, s.input_height, xs, ys, s.pixel_size_um, s.pixel_binning)
+        lut = {(t.x_mm, t.y_mm): t.pixels for t in tiles}
+        plan, _ = geo.center_pairs(xs, ys, False)
+        for kind, a_xy, b_xy in plan:
+            na, nb = sr.normalize_image(lut[a_xy]), sr.normalize_image(lut[b_xy])
+            if kind == "h":
+                m = int(na.shape[0] * 0.25)
+                exp = np.hstack((na[m:-m, -ovx:], nb[m:-m, :ovx]))
+                name = "horizontal.png"
+            else:
+                m = int(na.shape[1] * 0.25)
+                exp = np.vstack((na[-ovy:, m:-m], nb[:ovy, m:-m]))
+                name = "vertical.png"
+            got = cv2.imread(os.path.join(s.output_folder, name), cv2.IMREAD_UNCHANGED)
+            assert got is not None and np.array_equal(got, (exp / 65535 * 255).astype(np.uint8))
+    finally:
+        s.cleanup()
+    s2 = _make(root, st)
+    assert s2.visualize_registration is False
+
+
+def test_tiles_of_another_shape_are_refused_before_the_c_abi(tmp_path):
+    """a tile whose shape differs from (input_height, input_width) must not be handed to the library."""
+    from image_stitcher_b200 import _ffi
+    g, st, tiles, kw = load_golden("reg_2x2_mono")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    s = _make(root, st)
+    try:
+        _prepare(s)
+        a = tiles[0].pixels
+        with pytest.raises(ValueError):
+            s.calculate_horizontal_shift(a, a[:-8], 14)
+        with pytest.raises(ValueError):
+            s.ctx.register_pairs([(a, np.ascontiguousarray(a[:, :-8]), 0)], a.shape, 14, 14)
+        with pytest.raises(ValueError):
+            s.ctx.fuse_region([(a[::2], 0, 0, 0, 0, 0, 0, 0, 0)], a.shape, (1, 1, 64, 64), out=np.zeros((1, 1, 1, 64, 64), np.uint16))
+    finally:
+        s.cleanup()
