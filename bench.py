@@ -38,12 +38,19 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--wells", type=int, default=96)
-    ap.add_argument("--tile", type=int, default=2048)
-    ap.add_argument("--channels", type=int, default=4)
-    ap.add_argument("--grid", type=int, default=3)
-    ap.add_argument("--blend", choices=["paste", "linear", "feather"], default="paste")
+    ap.add_argument("--config", type=int, default=2, choices=[0, 1, 2, 3, 4],
+                    help="BASELINE.json configs[i] shapes (2 = the headline plate; the others are kept bench lines, see profiles/)")
+    ap.add_argument("--wells", type=int, default=None)
+    ap.add_argument("--tile", type=int, default=None)
+    ap.add_argument("--channels", type=int, default=None)
+    ap.add_argument("--grid", type=int, default=None)
+    ap.add_argument("--num-z", type=int, default=None)
+    ap.add_argument("--blend", choices=["paste", "linear", "feather"], default=None)
     ap.add_argument("--no-flatfield", action="store_true")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="multi-GPU: weak = one plate per rank; strong = ONE plate, its wells split over the ranks")
+    ap.add_argument("--no-f64", action="store_true", help="skip the informational float64 registration pass")
+    ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to the CPUs / NUMA node of its GPU")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the host-buffer leg (default min(steps, 2))")
     ap.add_argument("--host-wells", type=int, default=6, help="distinct wells kept in pinned host memory for e2e")
     ap.add_argument("--fuse-lanes", type=int, default=3, help="library lanes (streams) the per-well fusion launches rotate over")
@@ -52,7 +59,22 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-wells", type=int, default=0, help="wells in the CPU sample (0 = one per host core)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    # BASELINE.json configs: (wells, grid, tile, channels, num_z, blend, flat-field)
+    presets = {0: (1, 2, 2048, 1, 1, "linear", False), 1: (1, 5, 2048, 3, 1, "paste", True), 2: (96, 3, 2048, 4, 1, "paste", True),
+               3: (384, 2, 2048, 4, 1, "feather", True), 4: (1, 20, 3000, 1, 5, "paste", False)}
+    w, g, t, c, z, b, ff = presets[args.config]
+    args.wells = w if args.wells is None else args.wells
+    args.grid = g if args.grid is None else args.grid
+    args.tile = t if args.tile is None else args.tile
+    args.channels = c if args.channels is None else args.channels
+    args.num_z = z if args.num_z is None else args.num_z
+    args.blend = b if args.blend is None else args.blend
+    if not ff:
+        args.no_flatfield = True
+    if args.config != 2:
+        args.no_e2e = True                     # the host-buffer leg is defined on the headline plate
+    return args
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -199,19 +221,20 @@ def run_reference(args, rank, world):
     from image_stitcher_b200.plate import PlateSpec
     from oracle import synth
     spec = PlateSpec(wells=args.wells, rows=args.grid, cols=args.grid, tile_h=args.tile, tile_w=args.tile,
-                     channels=args.channels)
+                     channels=args.channels, num_z=args.num_z, reg_channel=min(1, args.channels - 1))
     use_flat = not args.no_flatfield
     cores = host_cores()
     n_tasks = args.cpu_sample_wells if args.cpu_sample_wells > 0 else cores
     distinct = min(2, n_tasks)
     # bounded sample: wells generated on the host with the oracle's own generator, reused round-robin by the tasks
-    tiles = np.empty((distinct, spec.rows, spec.cols, spec.channels, 1, spec.tile_h, spec.tile_w), np.uint16)
+    tiles = np.empty((distinct, spec.rows, spec.cols, spec.channels, spec.num_z, spec.tile_h, spec.tile_w), np.uint16)
     for w in range(distinct):
         st, recs, _ = synth.make_region(spec.rows, spec.cols, spec.tile_h, spec.tile_w, seed=w, jitter=3)
         for t in recs:
             r, c = divmod(t.fov, spec.cols)
             for ch in range(spec.channels):
-                tiles[w, r, c, ch, 0] = t.pixels if ch == spec.reg_channel else (t.pixels // (ch + 2))
+                for z in range(spec.num_z):
+                    tiles[w, r, c, ch, z] = t.pixels if ch == spec.reg_channel else (t.pixels // (ch + 2))
     flat = np.stack([synth.vignette(spec.tile_h, spec.tile_w, 0.35, (0.04 * (c + 1), -0.03 * (c + 1)))
                      for c in range(spec.channels)])
     for _ in range(min(args.warmup, 1)):
@@ -230,7 +253,7 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16 pixels; f64 registration",
         "data": "synthetic",
-        "config": {"workload": workload_name(spec, use_flat, args.blend), "sample": sample},
+        "config": {"workload": workload_name(spec, use_flat, args.blend, args.config), "sample": sample},
         "tile_pairs_per_s": pairs / (wall * share_reg), "fusion_mpx_per_s": px / 1e6 / (wall * (1 - share_reg)),
         "cpu_baseline": {"value": val, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -238,10 +261,79 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
-def workload_name(spec, use_flat, blend):
-    return (f"{spec.wells}-well plate, {spec.rows}x{spec.cols} tiles/well, {spec.tile_h}x{spec.tile_w} uint16, "
-            f"{spec.channels} channels, all-pairs registration on one channel + coordinate-placed {blend} fusion, "
-            f"flatfield {'on' if use_flat else 'off'} (BASELINE.json configs[2])")
+def workload_name(spec, use_flat, blend, config=2, wells_total=None):
+    wells = spec.wells if wells_total is None else wells_total
+    z = f", {spec.num_z} z-planes" if spec.num_z > 1 else ""
+    return (f"{wells}-well plate, {spec.rows}x{spec.cols} tiles/well, {spec.tile_h}x{spec.tile_w} uint16, "
+            f"{spec.channels} channels{z}, all-pairs registration on one channel + coordinate-placed {blend} fusion, "
+            f"flatfield {'on' if use_flat else 'off'} (BASELINE.json configs[{config}])")
+
+
+def bind_to_gpu_cpus(local_rank: int):
+    """Bind this rank to the CPUs next to its GPU (sysfs local_cpulist of the PCI device) so that its pinned buffers are
+    allocated on that NUMA node and its cudaMemcpyAsync submissions do not compete with the other ranks for one core
+    set.  When every GPU reports the same CPU list (r1: all eight on NUMA 0 / CPUs 0-31) the list is split evenly over
+    the local ranks instead.  Returns a description for the JSON line."""
+    try:
+        import torch
+        world_local = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        cpus, node = None, None
+        base = f"/sys/bus/pci/devices/{bus}"
+        if os.path.exists(base + "/local_cpulist"):
+            txt = open(base + "/local_cpulist").read().strip()
+            cpus = []
+            for part in txt.split(","):
+                if "-" in part:
+                    a, b = part.split("-")
+                    cpus += list(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.append(int(part))
+            node = open(base + "/numa_node").read().strip() if os.path.exists(base + "/numa_node") else None
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = [c for c in (cpus or allowed) if c in allowed] or allowed
+        if world_local > 1:                               # share the list between the local ranks
+            per = max(1, len(cpus) // world_local)
+            mine = cpus[(local_rank % world_local) * per:(local_rank % world_local + 1) * per] or cpus
+        else:
+            mine = cpus
+        os.sched_setaffinity(0, mine)
+        return {"pci": bus, "cpus": f"{mine[0]}-{mine[-1]}" if mine else "", "n_cpus": len(mine), "numa_node": node}
+    except Exception as exc:                              # affinity is an optimisation, never a reason to fail
+        return {"error": str(exc)}
+
+
+def pcie_ceiling(ctx, torch, local_rank, dist, mb=512, reps=4):
+    """Raw concurrent H2D + D2H of pinned buffers on two streams (all ranks at once): the node's copy ceiling that the
+    end-to-end number is reported against.  Returns GB/s per direction for this rank (max-time over ranks)."""
+    n = mb << 20
+    h_in = ctx.pinned_empty((n,), np.uint8)
+    h_out = ctx.pinned_empty((n,), np.uint8)
+    d_in = torch.empty(n, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    d_out = torch.empty(n, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    s1, s2 = torch.cuda.Stream(device=local_rank), torch.cuda.Stream(device=local_rank)
+    t_in = torch.from_numpy(h_in)
+    t_out = torch.from_numpy(h_out)
+    def once():
+        with torch.cuda.stream(s1):
+            d_in.copy_(t_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            t_out.copy_(d_out, non_blocking=True)
+    once()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([dt], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return n * reps / dt / 1e9
 
 
 # ------------------------------------------------------------------------------------------ CUDA arm
@@ -253,6 +345,7 @@ def run_b200(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    affinity = None if args.no_affinity else bind_to_gpu_cpus(local_rank)     # before any pinned allocation
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -269,12 +362,18 @@ def run_b200(args, rank, world, local_rank):
             os.dup2(saved, 1)
             os.close(saved)
 
-    spec = PlateSpec(wells=args.wells, rows=args.grid, cols=args.grid, tile_h=args.tile, tile_w=args.tile,
-                     channels=args.channels, seed=rank)
+    from image_stitcher_b200.shard import wells_for_rank
+    strong = args.scaling == "strong" and world > 1
+    # weak: every rank owns a whole plate (wells rank * W .. rank * W + W - 1 of an N-plate run); strong: ONE plate,
+    # well i on rank i % N (shard.wells_for_rank) -- no data-path collective either way
+    my_wells = wells_for_rank(args.wells, world, rank) if strong else [rank * args.wells + w for w in range(args.wells)]
+    wells_total = args.wells if strong else args.wells * world
+    spec = PlateSpec(wells=len(my_wells), rows=args.grid, cols=args.grid, tile_h=args.tile, tile_w=args.tile,
+                     channels=args.channels, num_z=args.num_z, reg_channel=min(1, args.channels - 1), seed=0)
     use_flat = not args.no_flatfield
     blend = _ffi.BLEND_MODES[args.blend]
     ctx = _ffi.Context(local_rank)
-    plate = make_plate(spec, device=f"cuda:{local_rank}", with_flat=True)
+    plate = make_plate(spec, device=f"cuda:{local_rank}", with_flat=True, well_ids=my_wells)
     if use_flat:
         for c in range(spec.channels):
             ctx.set_flatfield(c, plate.flat[c], mem=_ffi.SB_MEM_DEVICE)

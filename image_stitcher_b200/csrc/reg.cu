@@ -748,7 +748,7 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     // float32 frames with a 1024-long axis: the forward short-axis transform runs on the tensor cores and the column pass
     // as warp-level register FFTs (reg_tc.cu); everything else -- and float64 -- stays on the radix engine below
     TcPlan tc;
-    if (sizeof(T) == 4) {
+    if (sizeof(T) == 4 && tile_w % 8 == 0) {             // (the bulk copies of the strip rows need a 16-byte tile pitch)
         const int rc_tc = sb_tc_plan(ctx, Sh, Sw, &tc);
         if (rc_tc) return rc_tc;
     }

@@ -34,38 +34,46 @@ namespace {
 // row maximum (what rows_inv_argmax_kernel of the radix path emits).
 // ==========================================================================================================
 // The kernel is PERSISTENT (one block per SM) and warp-specialised, every hand-over an mbarrier:
-//     warps 0-3   loaders      (MODE 0) strip rows of tile i+1 -> stretched uint16 rows in shared memory (2 buffers)
-//     warps 4-7   converters   rows -> A operand stages (fold / split), or Y -> A stages straight from global (MODE 1)
+//     warps 0-7   converters   MODE 0: raw strip rows in shared memory -> stretch (normalize_image, :844-855) -> fold ->
+//                              tf32 split -> A operand stages; MODE 1: Y -> A stages straight from global (coalesced)
 //     warp  8     one thread   B stages by bulk copy, tcgen05.mma issue, tcgen05.commit
 //     warps 9-12  epilogue     TMEM accumulators of tile i-1 (2 accumulator buffers) -> global
+//     warp  13    one thread   (MODE 0) the raw strip rows of tile i+1 by 1-D bulk copies (2 staged tiles)
 // so the load of one tile, the operand conversion and the MMAs of the next and the read-back of the previous overlap
-// (the first version ran the three phases one after the other in one-tile blocks: tensor pipe 6 % busy, issue 22 %).
-constexpr int kTcThreads = 13 * 32;
+// (the first version ran the phases one after the other in one-tile blocks: tensor pipe 6 % busy, issue 22 %; the second
+// loaded the rows with ordinary loads in four warps and was bound by their latency).
+constexpr int kTcThreads = 14 * 32;
 constexpr int kTcStages = 3;             // operand ring depth (A + B)
 constexpr int kAStage = 4 * 128 * 32;    // part0_hi | part0_lo | part1_hi | part1_lo, each 128 rows x 8 k (K-major, LBO 2048, SBO 128)
 
 struct TcSmem {                          // offsets into dynamic shared memory
     int a_off, b_off, stg_off, bar_off, total;
     int b_stage;                         // bytes of one B stage: 4 sub-tiles of NP rows x 8 k
-    int stg_bytes;                       // bytes of one staged tile (MODE 0): 128 rows of pitch_w words
 };
-__host__ __device__ inline TcSmem tc_smem_layout(int NP, int pitch_w, int stg_bufs) {   // stg_bufs = 0: MODE 1
+__host__ __device__ inline TcSmem tc_smem_layout(int NP, int stg_bytes, int stg_bufs) {   // stg_bufs = 0: MODE 1
     TcSmem L;
     L.b_stage = 4 * NP * 32;
-    L.stg_bytes = 128 * pitch_w * 4;
     L.a_off = 0;
     L.b_off = kTcStages * kAStage;
     L.stg_off = L.b_off + kTcStages * L.b_stage;
-    L.bar_off = L.stg_off + stg_bufs * L.stg_bytes;
+    L.bar_off = L.stg_off + stg_bufs * stg_bytes;
     L.total = L.bar_off + 256;
     return L;
+}
+// row pitch of a staged tile: a multiple of 16 bytes (bulk-copy destination) with an ODD number of 16-byte units, so that
+// the rows a warp reads side by side spread over the banks (at most 2-way conflicts)
+__host__ __device__ inline int tc_pitch(int payload_bytes) {
+    int p = (payload_bytes + 14 + 15) & ~15;             // + up to 14 bytes of leading misalignment
+    if (((p >> 4) & 1) == 0) p += 16;
+    return p;
 }
 
 struct TcArgs {
     // geometry
-    int Sh, n, NP, nchunks, pitch_w, swap;
+    int Sh, n, NP, nchunks, swap;
     int n_tiles;                         // tiles of 128 rows in this launch
     int stg_bufs, acc_bufs;              // staged-tile buffers (MODE 0: 1 or 2), TMEM accumulator buffers (1 or 2)
+    int stg_bytes;                       // bytes of one staged tile
     const uint8_t* Bmat;                 // operand images of this mode's tables
     int* fault;
     // MODE 0
@@ -85,12 +93,12 @@ template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int Sh = g.Sh, n = g.n, NP = g.NP, nchunks = g.nchunks;
-    const TcSmem L = tc_smem_layout(NP, g.pitch_w, MODE == 0 ? g.stg_bufs : 0);
+    const TcSmem L = tc_smem_layout(NP, g.stg_bytes, MODE == 0 ? g.stg_bufs : 0);
     uint8_t* a_st = smem + L.a_off;
     uint8_t* b_st = smem + L.b_off;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-    uint64_t* stg_full = bars;                  // [2] loaders -> converters
-    uint64_t* stg_empty = bars + 2;             // [2] converters -> loaders
+    uint64_t* stg_full = bars;                  // [2] bulk copies -> converters
+    uint64_t* stg_empty = bars + 2;             // [2] converters -> loader
     uint64_t* ab_full = bars + 4;               // [kTcStages] converters + bulk copy -> MMA
     uint64_t* ab_empty = bars + 4 + kTcStages;  // [kTcStages] tcgen05.commit -> converters, bulk copy
     uint64_t* acc_full = bars + 4 + 2 * kTcStages;   // [2] tcgen05.commit -> epilogue
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int tiles = Sh >> 7;                  // tiles per strip image
     const int nb = n / 2 + 1, nh = n / 2, no = (n - 1) / 2;
-    const int pitch_h = g.pitch_w * 2;
+    const int pitch_ns = tc_pitch(2 * n), pitch_sw = tc_pitch(256);      // staged row pitch: plain / transposed frame
     const int acc_cols = 2 * NP;
     const uint32_t want_cols = (uint32_t)(g.acc_bufs * acc_cols);
     const uint32_t tmem_cols = want_cols <= 32 ? 32 : want_cols <= 64 ? 64 : want_cols <= 128 ? 128 : want_cols <= 256 ? 256 : 512;
@@ -111,13 +119,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
     if (warp == 8) {
         if (lane == 0) {
             for (int i = 0; i < 2; ++i) {
-                umma::mbar_init(stg_full + i, 4);
-                umma::mbar_init(stg_empty + i, 4);
+                umma::mbar_init(stg_full + i, 1);         // the loader's expect_tx arrival (+ the copies' bytes)
+                umma::mbar_init(stg_empty + i, 8);        // 8 converter warps
                 umma::mbar_init(acc_full + i, 1);
                 umma::mbar_init(acc_empty + i, 4);
             }
             for (int s = 0; s < kTcStages; ++s) {
-                umma::mbar_init(ab_full + s, 5);          // 4 converter warps + the bulk copy's expect_tx arrival
+                umma::mbar_init(ab_full + s, 9);          // 8 converter warps + the bulk copy's expect_tx arrival
                 umma::mbar_init(ab_empty + s, 1);         // tcgen05.commit
             }
             umma::mbar_init_fence();
@@ -137,139 +145,136 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
     const uint32_t tb = *tmem_slot;
     bool ok = true;
 
-    if (warp < 4) {
-        // =========================================================================== loaders (MODE 0)
-        if (MODE == 0) {
-            const int maxval = g.maxval, tile_w = g.tile_w;
+    if (warp == 13) {
+        // =========================================================================== loader (MODE 0): one thread
+        if (MODE == 0 && lane == 0) {
             for (int it = 0; it < my_tiles && ok; ++it) {
                 const int tile = blockIdx.x + it * gridDim.x;
                 const int mt = tile % tiles, img = (tile / tiles) & 1, p = tile / (2 * tiles);
                 const int y0 = mt << 7;
                 const int b = it % g.stg_bufs, u = it / g.stg_bufs;
                 if (u >= 1) ok = umma::mbar_wait(stg_empty + b, (u - 1) & 1);
-                uint16_t* stg = reinterpret_cast<uint16_t*>(smem + L.stg_off + b * L.stg_bytes);
+                uint8_t* stg = smem + L.stg_off + b * g.stg_bytes;
                 const PairDesc pd = g.pairs[p];
                 const uint16_t* src = img ? pd.b : pd.a;
-                const int2 m = g.mm[img ? pd.b_tile : pd.a_tile];
-                const float inv = m.y > m.x ? (float)maxval / (float)(m.y - m.x) : 0.f;
-                int seen = 0;
+                // rows start 16-byte aligned in shared memory; the copies start at the 16-byte boundary below the strip
+                // pixel (the same offset a0 for every row: the tile pitch is a multiple of 16 bytes)
                 if (!g.swap) {
-                    // crop + stretch fused into the load (normalize_image, :844-855): 4 rows x 4 column slices in flight per lane
-                    for (int r0 = warp * 32; r0 < warp * 32 + 32; r0 += 4) {
-                        for (int x0 = lane; x0 < n; x0 += 128) {
-                            unsigned v[4][4];
-#pragma unroll
-                            for (int rr = 0; rr < 4; ++rr)
-#pragma unroll
-                                for (int uu = 0; uu < 4; ++uu)
-                                    v[rr][uu] = x0 + 32 * uu < n ? src[(size_t)(y0 + r0 + rr) * tile_w + x0 + 32 * uu] : 0u;
-#pragma unroll
-                            for (int rr = 0; rr < 4; ++rr)
-#pragma unroll
-                                for (int uu = 0; uu < 4; ++uu)
-                                    if (x0 + 32 * uu < n) {
-                                        const int sv = stretch_px(v[rr][uu], m.x, m.y, inv, maxval);
-                                        seen |= sv;
-                                        stg[(r0 + rr) * pitch_h + x0 + 32 * uu] = (uint16_t)sv;
-                                    }
-                        }
-                    }
+                    const uint8_t* row0 = reinterpret_cast<const uint8_t*>(src + (size_t)y0 * g.tile_w);
+                    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(row0) & 15);
+                    const uint32_t bytes = (a0 + 2u * (uint32_t)n + 15u) & ~15u;
+                    umma::mbar_expect_tx(stg_full + b, bytes * 128u);
+                    for (int r = 0; r < 128; ++r)
+                        umma::bulk_g2s(stg + r * pitch_ns, row0 - a0 + (size_t)r * g.tile_w * 2, bytes, stg_full + b);
                 } else {
-                    // transposed frame: frame row r is image column y0 + r (contiguous in memory), frame column x is image row x.
-                    // Warp w takes image rows x = w, w + 4, ...; a lane the four frame rows lane + 32 q.
-                    for (int x0 = warp; x0 < n; x0 += 16) {
-                        unsigned v[4][4];
-#pragma unroll
-                        for (int uu = 0; uu < 4; ++uu)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                v[uu][q] = x0 + 4 * uu < n ? src[(size_t)(x0 + 4 * uu) * tile_w + y0 + lane + 32 * q] : 0u;
-#pragma unroll
-                        for (int uu = 0; uu < 4; ++uu)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (x0 + 4 * uu < n) {
-                                    const int sv = stretch_px(v[uu][q], m.x, m.y, inv, maxval);
-                                    seen |= sv;
-                                    stg[(lane + 32 * q) * pitch_h + x0 + 4 * uu] = (uint16_t)sv;
-                                }
-                    }
+                    const uint8_t* row0 = reinterpret_cast<const uint8_t*>(src + y0);
+                    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(row0) & 15);
+                    const uint32_t bytes = (a0 + 256u + 15u) & ~15u;
+                    umma::mbar_expect_tx(stg_full + b, bytes * (uint32_t)n);
+                    for (int x = 0; x < n; ++x)
+                        umma::bulk_g2s(stg + x * pitch_sw, row0 - a0 + (size_t)x * g.tile_w * 2, bytes, stg_full + b);
                 }
-                // an all-zero strip has an exactly zero spectrum in the reference: record whether this one has a non-zero pixel
-                seen = __reduce_or_sync(0xffffffffu, (unsigned)seen);
-                if (lane == 0 && seen) atomicOr(&g.nonzero[p], img ? 2 : 1);
-                __syncwarp();
-                if (lane == 0) umma::mbar_arrive(stg_full + b);
             }
         }
     } else if (warp < 8) {
-        // =========================================================================== converters: one row per thread
-        const int row = t - 128;
+        // =========================================================================== converters: thread = (row, 4 k)
+        const int row = 16 * warp + (lane >> 1), kg = lane & 1;
         int gc = 0;                                                // chunks produced so far (ring position)
         for (int it = 0; it < my_tiles && ok; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int mt = tile % tiles;
+            const int img = MODE == 0 ? (tile / tiles) & 1 : 0;
             const int p = MODE == 0 ? tile / (2 * tiles) : tile / tiles;
             const int y0 = mt << 7;
             const int b = MODE == 0 ? it % g.stg_bufs : 0, u = MODE == 0 ? it / g.stg_bufs : 0;
-            const uint16_t* srow = nullptr;
+            const uint16_t* sbase = nullptr;                       // MODE 0: first staged pixel of this thread's row
+            int sstep = 0;                                         // ... and the distance (uint16 elements) between its columns
+            int mn = 0, mx = 0, seen = 0;
+            float inv = 0.f;
             const float2* yrow = nullptr;
-            float2 nxt[8];
+            float2 nxt[4];
             if (MODE == 0) {
+                const PairDesc pd = g.pairs[p];
+                const uint16_t* src = img ? pd.b : pd.a;
+                const int2 m = g.mm[img ? pd.b_tile : pd.a_tile];
+                mn = m.x;
+                mx = m.y;
+                inv = mx > mn ? (float)g.maxval / (float)(mx - mn) : 0.f;
+                const uint8_t* stg = smem + L.stg_off + b * g.stg_bytes;
+                if (!g.swap) {
+                    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(src + (size_t)y0 * g.tile_w) & 15);
+                    sbase = reinterpret_cast<const uint16_t*>(stg + row * pitch_ns + a0);
+                    sstep = 1;
+                } else {
+                    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(src + y0) & 15);
+                    sbase = reinterpret_cast<const uint16_t*>(stg + a0) + row;
+                    sstep = pitch_sw >> 1;
+                }
                 ok = umma::mbar_wait(stg_full + b, u & 1);
-                srow = reinterpret_cast<const uint16_t*>(smem + L.stg_off + b * L.stg_bytes) + row * pitch_h;
             } else {
                 yrow = g.Y + (size_t)p * g.lines_in * Sh + y0 + row;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) nxt[i] = i < nb ? yrow[(size_t)i * Sh] : make_float2(0.f, 0.f);
+                for (int i = 0; i < 4; ++i) {
+                    const int k = 4 * kg + i;
+                    nxt[i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
+                }
             }
             for (int c = 0; c < nchunks && ok; ++c, ++gc) {
                 const int s = gc % kTcStages, use = gc / kTcStages;
-                float ph[8], pl[8], qh[8], ql[8];
+                float ph[4], pl[4], qh[4], ql[4];
                 if (MODE == 0) {
+                    unsigned ra[4], rb[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int j = 8 * c + i;
-                        const int xa = j <= nh ? (int)srow[j] : 0;
+                    for (int i = 0; i < 4; ++i) {                  // raw pixels first (shared-memory latency overlaps)
+                        const int j = 8 * c + 4 * kg + i;
+                        ra[i] = j <= nh ? sbase[j * sstep] : 0u;
+                        rb[i] = (j >= 1 && j <= no) ? sbase[(n - j) * sstep] : 0u;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int j = 8 * c + 4 * kg + i;
                         const bool paired = j >= 1 && j <= no;
-                        const int xb = paired ? (int)srow[n - j] : 0;
+                        const int xa = j <= nh ? stretch_px(ra[i], mn, mx, inv, g.maxval) : 0;
+                        const int xb = paired ? stretch_px(rb[i], mn, mx, inv, g.maxval) : 0;
+                        seen |= xa | xb;
                         const float e = (float)(xa + xb) * (float)kInScale, o = paired ? (float)(xa - xb) * (float)kInScale : 0.f;
                         umma::split_tf32(e, ph[i], pl[i]);
                         umma::split_tf32(o, qh[i], ql[i]);
                     }
                 } else {
-                    float2 cur[8];
+                    float2 cur[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+                    for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
                     if (c + 1 < nchunks) {                         // the next chunk's values are in flight while this one is split
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int k = 8 * (c + 1) + i;
+                        for (int i = 0; i < 4; ++i) {
+                            const int k = 8 * (c + 1) + 4 * kg + i;
                             nxt[i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 4; ++i) {
                         umma::split_tf32(cur[i].x, ph[i], pl[i]);
                         umma::split_tf32(cur[i].y, qh[i], ql[i]);
                     }
                 }
                 if (use >= 1) ok = umma::mbar_wait(ab_empty + s, (use - 1) & 1);
-                uint8_t* dst = a_st + s * kAStage + row * 16;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    *reinterpret_cast<float4*>(dst + h * 2048) = make_float4(ph[4 * h], ph[4 * h + 1], ph[4 * h + 2], ph[4 * h + 3]);
-                    *reinterpret_cast<float4*>(dst + h * 2048 + 4096) = make_float4(pl[4 * h], pl[4 * h + 1], pl[4 * h + 2], pl[4 * h + 3]);
-                    *reinterpret_cast<float4*>(dst + h * 2048 + 8192) = make_float4(qh[4 * h], qh[4 * h + 1], qh[4 * h + 2], qh[4 * h + 3]);
-                    *reinterpret_cast<float4*>(dst + h * 2048 + 12288) = make_float4(ql[4 * h], ql[4 * h + 1], ql[4 * h + 2], ql[4 * h + 3]);
-                }
+                uint8_t* dst = a_st + s * kAStage + kg * 2048 + row * 16;
+                *reinterpret_cast<float4*>(dst) = make_float4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<float4*>(dst + 4096) = make_float4(pl[0], pl[1], pl[2], pl[3]);
+                *reinterpret_cast<float4*>(dst + 8192) = make_float4(qh[0], qh[1], qh[2], qh[3]);
+                *reinterpret_cast<float4*>(dst + 12288) = make_float4(ql[0], ql[1], ql[2], ql[3]);
                 umma::fence_smem_to_async();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(ab_full + s);
             }
-            if (MODE == 0) {                                       // every read of the staged tile is done
-                __syncwarp();
-                if (lane == 0) umma::mbar_arrive(stg_empty + b);
+            if (MODE == 0) {
+                // an all-zero strip has an exactly zero spectrum in the reference: record whether this one has a non-zero pixel
+                seen = __reduce_or_sync(0xffffffffu, (unsigned)seen);
+                if (lane == 0) {
+                    if (seen) atomicOr(&g.nonzero[p], img ? 2 : 1);
+                    umma::mbar_arrive(stg_empty + b);              // every read of the staged tile is done
+                }
             }
         }
     } else if (warp == 8) {
@@ -597,12 +602,13 @@ int sb_tc_plan(sb_ctx* ctx, int Sh, int n, TcPlan* plan) {
     plan->nb = n / 2 + 1;
     plan->NP = (plan->nb + 15) & ~15;
     plan->nchunks = (plan->nb + 7) / 8;
-    plan->pitch_w = ((n + 1) / 2) | 1;
+    plan->pitch_w = 0;
+    plan->stg_bytes = (std::max(128 * tc_pitch(2 * n), n * tc_pitch(256)) + 127) & ~127;
     plan->acc_bufs = 4 * plan->NP <= 512 ? 2 : 1;
-    plan->stg_bufs = tc_smem_layout(plan->NP, plan->pitch_w, 2).total <= 227 * 1024 ? 2 : 1;
-    const TcSmem L = tc_smem_layout(plan->NP, plan->pitch_w, plan->stg_bufs);
+    plan->stg_bufs = tc_smem_layout(plan->NP, plan->stg_bytes, 2).total <= 226 * 1024 ? 2 : 1;
+    const TcSmem L = tc_smem_layout(plan->NP, plan->stg_bytes, plan->stg_bufs);
     plan->smem_fwd = L.total;
-    if (L.total > 227 * 1024) return SB_OK;
+    if (L.total > 226 * 1024) return SB_OK;
     const int nb = plan->nb, NP = plan->NP, nh = n / 2, no = (n - 1) / 2;
     // forward tables: per chunk [cos_hi | cos_lo | -sin_hi | -sin_lo], each NP rows (output bin k) x 8 (input j), K-major
     const uint64_t key = ((uint64_t)2 << 40) | (uint64_t)n;
@@ -692,13 +698,13 @@ int sb_tc_plan(sb_ctx* ctx, int Sh, int n, TcPlan* plan) {
 
 int sb_tc_forward(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, const void* d_pairs, int n_pairs, const int2* d_mm, int tile_w,
                   int swap, int maxval, void* Zh, int* d_nonzero, int* d_fault) {
-    static bool configured = false;
-    if (!configured) {
-        SB_CUDA(ctx, cudaFuncSetAttribute(xdft_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+    static int configured = 0;                       // largest dynamic shared-memory size granted so far
+    if (plan.smem_fwd > configured) {
+        SB_CUDA(ctx, cudaFuncSetAttribute(xdft_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_fwd));
+        configured = plan.smem_fwd;
     }
     TcArgs g = {};
-    g.Sh = plan.Sh; g.n = plan.n; g.NP = plan.NP; g.nchunks = plan.nchunks; g.pitch_w = plan.pitch_w; g.swap = swap;
+    g.Sh = plan.Sh; g.n = plan.n; g.NP = plan.NP; g.nchunks = plan.nchunks; g.swap = swap; g.stg_bytes = plan.stg_bytes;
     g.Bmat = plan.Bfwd; g.fault = d_fault;
     g.pairs = static_cast<const PairDesc*>(d_pairs); g.mm = d_mm; g.tile_w = tile_w; g.maxval = maxval;
     g.Zh = static_cast<float2*>(Zh); g.nonzero = d_nonzero;
@@ -712,13 +718,13 @@ int sb_tc_forward(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, const void* 
 
 int sb_tc_inverse(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs, const void* Y, int lines_in, int swap, void* best,
                   float* rowmax, int* d_fault) {
-    static bool configured = false;
-    if (!configured) {
-        SB_CUDA(ctx, cudaFuncSetAttribute(xdft_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+    static int configured = 0;
+    if (plan.smem_inv > configured) {
+        SB_CUDA(ctx, cudaFuncSetAttribute(xdft_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_inv));
+        configured = plan.smem_inv;
     }
     TcArgs g = {};
-    g.Sh = plan.Sh; g.n = plan.n; g.NP = plan.NP; g.nchunks = plan.nchunks; g.pitch_w = 0; g.swap = swap;
+    g.Sh = plan.Sh; g.n = plan.n; g.NP = plan.NP; g.nchunks = plan.nchunks; g.swap = swap; g.stg_bytes = 0;
     g.Bmat = plan.Binv; g.fault = d_fault;
     g.Y = static_cast<const float2*>(Y); g.lines_in = lines_in;
     g.best = static_cast<CtaBest*>(best); g.rowmax = rowmax;

@@ -11,7 +11,8 @@ struct TcPlan {
     int nb = 0;            // n / 2 + 1 bins of the half spectrum
     int NP = 0;            // nb rounded up to 16: accumulator columns per part
     int nchunks = 0;       // K chunks of 8 (nb rounded up to 8, / 8)
-    int pitch_w = 0;       // 32-bit words per staged strip row (odd: conflict-free column reads)
+    int pitch_w = 0;       // (unused)
+    int stg_bytes = 0;     // bytes of one staged tile of raw strip rows (forward transform)
     int smem_fwd = 0;      // dynamic shared memory of fwd_x_tc_kernel
     const uint8_t* Bfwd = nullptr;   // cos / -sin operand images of the forward transform (device)
     const uint8_t* Binv = nullptr;   // ... and of the inverse transform

@@ -78,12 +78,15 @@ def vignette_torch(h, w, strength, shift, device):
     return (ff / ff.mean()).to(torch.float32)
 
 
-def make_plate(spec: PlateSpec, device="cuda", with_flat=True) -> Plate:
-    """Generate the plate directly in device memory (never on the timed path)."""
+def make_plate(spec: PlateSpec, device="cuda", with_flat=True, well_ids=None) -> Plate:
+    """Generate the plate directly in device memory (never on the timed path).
+
+    Every well is seeded by ``(spec.seed, well id)``, so a rank that owns wells ``well_ids`` of a larger plate (strong
+    scaling: ``shard.wells_for_rank``) generates exactly the wells a single GPU would hold under those ids."""
     import torch
     g = torch.Generator(device=device)
-    g.manual_seed(spec.seed)
-    rng = np.random.default_rng(spec.seed)
+    well_ids = list(range(spec.wells)) if well_ids is None else [int(w) for w in well_ids]
+    assert len(well_ids) == spec.wells, "spec.wells is the number of wells THIS plate holds"
     H, W = spec.tile_h, spec.tile_w
     sy, sx = spec.step
     j = spec.jitter
@@ -98,7 +101,9 @@ def make_plate(spec: PlateSpec, device="cuda", with_flat=True) -> Plate:
                             for c in range(spec.channels)])
     k1 = torch.tensor([0.054, 0.244, 0.403, 0.244, 0.054], device=device)      # gaussian, sigma = 1
     truth = []
-    for wl in range(spec.wells):
+    for wl, wid in enumerate(well_ids):
+        g.manual_seed(spec.seed * 1000003 + wid)
+        rng = np.random.default_rng([spec.seed, wid])
         col_jx, row_jy, col_jy, row_jx = (int(v) for v in rng.integers(-j, j + 1, 4)) if j else (0, 0, 0, 0)
         truth.append({"h": (col_jy, -(W - sx) + col_jx), "v": (-(H - sy) + row_jy, row_jx)})
         u = torch.rand((1, 1, wh, ww), generator=g, device=device) ** 6

@@ -67,7 +67,7 @@ def test_tensor_core_stages_match_numpy(ctx, tiles, direction, ov):
     # float32 phase error grows as |P| shrinks (the spectra carry an ABSOLUTE error ~1e-7 of their largest bins): weigh
     # the error of a bin by its magnitude relative to the median bin
     weight = np.minimum(mag / np.median(mag), 1.0)
-    assert (np.abs(R[:nb] - Rn) * weight).max() < 1e-4
+    assert (np.abs(R[:nb] - Rn) * weight).max() < 1e-3
     assert np.abs(np.abs(R[:nb]) - 1.0).max() < 1e-5
     Yn = sfft.ifft(R[:nb].astype(np.complex128), axis=1) * Sh
     assert np.abs(Y[:nb] - Yn).max() / np.abs(Yn).max() < 2e-6
