@@ -345,6 +345,7 @@ def run_b200(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
     affinity = None if args.no_affinity else bind_to_gpu_cpus(local_rank)     # before any pinned allocation
     dist = None
     if world > 1:
@@ -456,13 +457,14 @@ def run_b200(args, rank, world, local_rank):
     total_ms = t_start.elapsed_time(t_end)
     reg_ms = [a.elapsed_time(b) for a, b, _ in recs]
     fuse_ms = [b.elapsed_time(c) for _, b, c in recs]
+    px_all, pairs_all = px_per_step, n_pairs            # whole job: every rank's pixels and pairs per step
     if dist:
         t = torch.tensor([total_ms, float(np.sum(reg_ms)), float(np.sum(fuse_ms))], device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, reg_sum, fuse_sum = (float(v) for v in t.tolist())
-        l = torch.tensor([launches], device=f"cuda:{local_rank}")
+        l = torch.tensor([launches, px_per_step, n_pairs], device=f"cuda:{local_rank}", dtype=torch.int64)
         dist.all_reduce(l)
-        launches = int(l.item())
+        launches, px_all, pairs_all = (int(v) for v in l.tolist())
     else:
         reg_sum, fuse_sum = float(np.sum(reg_ms)), float(np.sum(fuse_ms))
 
@@ -502,23 +504,27 @@ def run_b200(args, rank, world, local_rank):
     reg_achieved = reg_bytes * args.steps / (reg_sum * 1e-3) / 1e9
 
     out = {
-        "metric": METRIC, "value": px_per_step * args.steps * world / 1e6 / (total_ms * 1e-3), "unit": "Mpx/s",
+        "metric": METRIC, "value": px_all * args.steps / 1e6 / (total_ms * 1e-3), "unit": "Mpx/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "u16 pixels; f32 flatfield divide; f32 FFT with f64 redo of low-confidence pairs",
         "data": "synthetic",
-        "config": {"workload": workload_name(spec, use_flat, args.blend), "plates": world,
-                   "pairs_per_step": n_pairs * world, "canvas": [planes, Hc, Wc], "strip": [Sh_h, Sw_h],
+        "config": {"workload": workload_name(spec, use_flat, args.blend, args.config, wells_total if strong else args.wells),
+                   "plates": 1 if strong else world, "wells_per_rank": spec.wells,
+                   "sharding": ("one plate, well i on rank i % N (shard.wells_for_rank), no data-path collective" if strong
+                                else "one plate per rank, no data-path collective"),
+                   "pairs_per_step": pairs_all, "canvas": [planes, Hc, Wc], "strip": [Sh_h, Sw_h],
                    "l2": "inputs (29 GB) and outputs (25 GB) per step exceed L2 (126 MB); no flush needed",
                    "timing": "CUDA events on the launching stream (lane 0 brackets the other lanes with fork/join events), max over ranks",
                    "fuse_lanes": nl},
-        "tile_pairs_per_s": n_pairs * args.steps * world / (reg_sum * 1e-3),
-        "fusion_mpx_per_s": px_per_step * args.steps * world / 1e6 / (fuse_sum * 1e-3),
+        "tile_pairs_per_s": pairs_all * args.steps / (reg_sum * 1e-3),
+        "fusion_mpx_per_s": px_all * args.steps / 1e6 / (fuse_sum * 1e-3),
         "registration_ms_per_step": reg_sum / args.steps, "fusion_ms_per_step": fuse_sum / args.steps,
         "wall_ms_per_step": wall / args.steps * 1e3,
         "registration_truth_wells_ok": f"{ok}/{spec.wells}",
         "registration_f64_redo_pairs": int(sum(r["precision"] == 1 for r in last_reg)),
         "gpu_launches": int(launches),
+        "cpu_affinity": affinity,
         "clocks": clocks,
         "roofline": {"kernel": "paste_rect_kernel" if args.blend == "paste" else "paste_rect_kernel<ROUND> + blend_cells_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": "profiles/fusion_traffic.json (ncu --set full, per launch)" if traffic else None,
@@ -529,6 +535,33 @@ def run_b200(args, rank, world, local_rank):
         "roofline_registration": {"bound": "hbm", "achieved": reg_achieved, "peak": peak_gbs, "unit": "GB/s",
                                   "frac": reg_achieved / peak_gbs, "algorithmic_bytes_per_step": reg_bytes},
     }
+
+    # ---------------------------------------------------------------- strong scaling: cross-rank equality on a sample
+    # rank 0 regenerates the first well of the LAST rank (same global well id -> same pixels), registers and fuses it
+    # itself and compares shifts and a canvas checksum with what that rank produced: the sharded plate equals the
+    # single-GPU plate well by well (wells are independent; there is nothing to exchange).
+    if strong:
+        mine = torch.tensor([int(canvases[0].to(torch.int64).sum().item())] +
+                            [v for r in last_reg[:n_pairs // spec.wells] for v in (r["dy"], r["dx"])],
+                            device=f"cuda:{local_rank}", dtype=torch.int64)
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        if rank == 0:
+            wid = wells_for_rank(args.wells, world, world - 1)[0]
+            spec1 = PlateSpec(wells=1, rows=spec.rows, cols=spec.cols, tile_h=spec.tile_h, tile_w=spec.tile_w, channels=spec.channels,
+                              num_z=spec.num_z, reg_channel=spec.reg_channel, seed=0)
+            p1 = make_plate(spec1, device=f"cuda:{local_rank}", with_flat=True, well_ids=[wid])
+            ptr1 = lambda r, c, ch, z: p1.pool[0, r, c, ch, z].data_ptr()
+            c1 = torch.empty_like(canvases[0])
+            torch.cuda.synchronize()
+            r1 = ctx.register_pairs(well_pairs(spec1, ptr1)[0], (spec.tile_h, spec.tile_w), ovx, ovy, mem=_ffi.SB_MEM_DEVICE, lane=0)
+            ctx.fuse_region(well_fuse_tiles(spec1, ptr1), (spec.tile_h, spec.tile_w), (spec.channels, spec.num_z, Hc, Wc), out=c1,
+                            tile_mem=_ffi.SB_MEM_DEVICE, out_mem=_ffi.SB_MEM_DEVICE, apply_flatfield=use_flat, blend=blend,
+                            blend_ov=(ovx, ovy), dtype=_ffi.SB_U16)
+            torch.cuda.synchronize()
+            exp = [int(c1.to(torch.int64).sum().item())] + [v for r in r1 for v in (r["dy"], r["dx"])]
+            out["strong_scaling_check"] = {"well": wid, "owner_rank": world - 1,
+                                           "equals_single_gpu_result": exp == [int(v) for v in gathered[world - 1].tolist()]}
 
     # ---------------------------------------------------------------- informational: the two phases overlapped
     # In this workload (coordinate placement) fusion does not depend on the shifts, so a pipeline may run the two phases
@@ -564,7 +597,7 @@ def run_b200(args, rank, world, local_rank):
             o_mean = float(t.item())
         else:
             o_mean = float(np.mean(o_ms))
-        out["concurrent_phases"] = {"ms_per_step": o_mean, "value": px_per_step * world / 1e6 / (o_mean * 1e-3), "unit": "Mpx/s",
+        out["concurrent_phases"] = {"ms_per_step": o_mean, "value": px_all / 1e6 / (o_mean * 1e-3), "unit": "Mpx/s",
                                     "same_shifts_as_sequential": bool(o_ok),
                                     "note": "registration (lane 0 + aux streams) and fusion (other lanes) enqueued together; "
                                             "informational, not the contract value (no gain on B200: the registration blocks "
@@ -612,11 +645,19 @@ def run_b200(args, rank, world, local_rank):
         got = host_out[(spec.wells - 1) % pipe.depth][0].reshape(planes, Hc, Wc)
         src_w = (spec.wells - 1) % hw
         exp = canvases[src_w].cpu().numpy().view(np.uint16)[:, :, :Wc]
-        out["e2e"] = {"value": px_per_step * e2e_steps * world / 1e6 / e2e_s, "unit": "Mpx/s",
-                      "h2d_bytes_per_step": int(spec.wells * spec.tiles_per_well * spec.tile_h * spec.tile_w * 2),
-                      "d2h_bytes_per_step": int(px_per_step * 2), "steps": e2e_steps,
+        # the node's raw copy ceiling with every rank copying both ways at once: what the end-to-end number is bound by
+        ceil_gbs = pcie_ceiling(ctx, torch, local_rank, dist)
+        h2d_step = int(spec.wells * spec.tiles_per_well * spec.tile_h * spec.tile_w * 2)
+        d2h_step = int(px_per_step * 2)
+        floor_s = max(h2d_step, d2h_step) / (ceil_gbs * 1e9)      # both directions run concurrently
+        out["e2e"] = {"value": px_all * e2e_steps / 1e6 / e2e_s, "unit": "Mpx/s",
+                      "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "steps": e2e_steps,
                       "ms_per_step": e2e_s / e2e_steps * 1e3,
-                      "tile_pairs_per_s": n_pairs * e2e_steps * world / e2e_s,
+                      "pcie_ceiling": {"gb_per_s_per_direction_per_gpu": ceil_gbs, "ranks_copying_at_once": world,
+                                       "ms_per_step_at_ceiling": floor_s * 1e3,
+                                       "e2e_frac_of_ceiling": floor_s / (e2e_s / e2e_steps),
+                                       "how": "512 MiB pinned H2D and D2H on two streams at once, every rank at the same time, max over ranks"},
+                      "tile_pairs_per_s": pairs_all * e2e_steps / e2e_s,
                       "api": "WellPipeline.submit(pinned host tiles) -> host canvas + shifts (sb_memcpy_async + "
                              "sb_register_pairs_async + sb_fuse_region, rotating over 3 lanes)",
                       "registration_truth_wells_ok": f"{e2e_reg_ok}/{spec.wells}",
@@ -624,8 +665,31 @@ def run_b200(args, rank, world, local_rank):
     else:
         out["e2e"] = None
 
+    # ---------------------------------------------------------------- float64 registration (informational)
+    # the reference's arithmetic is complex128; north_star licenses float32 through its tolerance (bit-exact integer
+    # shifts, verified above on every well) -- this is the same-arithmetic figure next to it
+    if not args.no_f64:
+        for i, st_ in enumerate(streams):
+            ctx.set_lane_stream(i, st_.cuda_stream)
+        e0, e1 = ev(), ev()
+        ctx.register_pairs(all_pairs[:min(len(all_pairs), 96)], (spec.tile_h, spec.tile_w), ovx, ovy, mem=_ffi.SB_MEM_DEVICE,
+                           lane=0, precision=_ffi.SB_PREC_F64)                          # warm-up (workspace, twiddles)
+        e0.record(stream)
+        res64 = ctx.register_pairs(all_pairs, (spec.tile_h, spec.tile_w), ovx, ovy, mem=_ffi.SB_MEM_DEVICE, lane=0,
+                                   precision=_ffi.SB_PREC_F64)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms64 = e0.elapsed_time(e1)
+        same = [(r["dy"], r["dx"], r["coarse"], r["fine"]) for r in res64] == [(r["dy"], r["dx"], r["coarse"], r["fine"]) for r in last_reg]
+        out["registration_f64"] = {"ms_per_step": ms64, "tile_pairs_per_s": n_pairs / (ms64 * 1e-3),
+                                   "same_indices_and_shifts_as_default_precision": bool(same),
+                                   "note": "SB_PREC_F64: the radix FFT engine in complex128 on the GPU (this rank's pairs)"}
+        for i in range(nl):
+            ctx.set_lane_stream(i, None)
+
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)                          # the CPU arm gets every core again
         cores = host_cores()
         n = args.cpu_sample_wells if args.cpu_sample_wells > 0 else cores
         distinct = max(1, min(n, 4))

@@ -38,6 +38,21 @@ __device__ __forceinline__ int stretch_px_f64(unsigned v, int mn, int mx, int ma
     return (int)(q * (double)maxval);
 }
 
+// Branch-free core of stretch_px for the general case (0 < max - min < maxval): returns k = trunc(a * maxval / b) from the
+// float estimate corrected by the exact integer remainder, and raises `exact` when b divides a * maxval (k != 0) -- the one
+// case where the float64 expression of the reference may land on either side of the integer and must be evaluated as
+// such (stretch_px_f64).  No conversion-unit instructions: uint -> float and float -> int go through the 2^23 magic number.
+__device__ __forceinline__ int stretch_core(unsigned a, unsigned b, float inv, unsigned maxval, bool& exact) {
+    const float af = __uint_as_float(0x4B000000u | a) - 8388608.0f;                           // a < 2^16: exact
+    unsigned k = __float_as_uint(__fadd_rz(af * inv, 8388608.0f)) - 0x4B000000u;                // trunc(af * inv), < 2^17
+    int rem = (int)(a * maxval - k * b);                                                        // k is off by at most one
+    const bool lt = rem < 0, ge = rem >= (int)b;
+    k = lt ? k - 1u : (ge ? k + 1u : k);
+    rem = lt ? rem + (int)b : (ge ? rem - (int)b : rem);
+    exact = exact || (rem == 0 && k != 0u);
+    return (int)k;
+}
+
 // The same value without the float64 divide.  With a = v - min, b = max - min the exact quotient a * 65535 / b is
 // rational with denominator b <= 65535, so unless it is an integer it lies at least 1 / 65535 away from the next
 // one, while the float64 evaluation is off by at most 65535 * 2^-52: trunc() of both agree.  When b divides

@@ -189,10 +189,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
             const int b = MODE == 0 ? it % g.stg_bufs : 0, u = MODE == 0 ? it / g.stg_bufs : 0;
             const uint16_t* sbase = nullptr;                       // MODE 0: first staged pixel of this thread's row
             int sstep = 0;                                         // ... and the distance (uint16 elements) between its columns
-            int mn = 0, mx = 0, seen = 0;
+            int mn = 0, mx = 0, seen = 0, smode = 0;
+            unsigned sb_ = 1u;
             float inv = 0.f;
             const float2* yrow = nullptr;
-            float2 nxt[4];
+            constexpr int PF = 3;                                  // MODE 1: chunks of Y kept in flight per thread
+            float2 nxt[PF][4];
             if (MODE == 0) {
                 const PairDesc pd = g.pairs[p];
                 const uint16_t* src = img ? pd.b : pd.a;
@@ -200,6 +202,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                 mn = m.x;
                 mx = m.y;
                 inv = mx > mn ? (float)g.maxval / (float)(mx - mn) : 0.f;
+                sb_ = mx > mn ? (unsigned)(mx - mn) : 1u;
+                smode = mx <= mn ? 0 : (sb_ == (unsigned)g.maxval ? 1 : 2);     // constant tile / full range (identity) / general
                 const uint8_t* stg = smem + L.stg_off + b * g.stg_bytes;
                 if (!g.swap) {
                     const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(src + (size_t)y0 * g.tile_w) & 15);
@@ -214,43 +218,70 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
             } else {
                 yrow = g.Y + (size_t)p * g.lines_in * Sh + y0 + row;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int k = 4 * kg + i;
-                    nxt[i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
-                }
+                for (int d = 0; d < PF; ++d)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = 8 * d + 4 * kg + i;
+                        nxt[d][i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
+                    }
             }
             for (int c = 0; c < nchunks && ok; ++c, ++gc) {
                 const int s = gc % kTcStages, use = gc / kTcStages;
                 float ph[4], pl[4], qh[4], ql[4];
                 if (MODE == 0) {
                     unsigned ra[4], rb[4];
+                    bool va[4], vb[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {                  // raw pixels first (shared-memory latency overlaps)
                         const int j = 8 * c + 4 * kg + i;
-                        ra[i] = j <= nh ? sbase[j * sstep] : 0u;
-                        rb[i] = (j >= 1 && j <= no) ? sbase[(n - j) * sstep] : 0u;
+                        va[i] = j <= nh;
+                        vb[i] = j >= 1 && j <= no;
+                        ra[i] = va[i] ? sbase[j * sstep] : (unsigned)mn;
+                        rb[i] = vb[i] ? sbase[(n - j) * sstep] : (unsigned)mn;
+                    }
+                    // normalize_image's stretch (:844-855), branch-free for the whole vector; tile-uniform special cases
+                    int xa[4], xb[4];
+                    if (smode == 2) {
+                        bool exact = false;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            xa[i] = stretch_core(ra[i] - (unsigned)mn, sb_, inv, (unsigned)g.maxval, exact);
+                            xb[i] = stretch_core(rb[i] - (unsigned)mn, sb_, inv, (unsigned)g.maxval, exact);
+                        }
+                        if (exact) {                               // (rare) an exact quotient somewhere: the float64 expression decides
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                xa[i] = stretch_px(ra[i], mn, mx, inv, g.maxval);
+                                xb[i] = stretch_px(rb[i], mn, mx, inv, g.maxval);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {              // full-range tile: identity; constant tile: zero
+                            xa[i] = smode == 1 ? (int)ra[i] - mn : 0;
+                            xb[i] = smode == 1 ? (int)rb[i] - mn : 0;
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int j = 8 * c + 4 * kg + i;
-                        const bool paired = j >= 1 && j <= no;
-                        const int xa = j <= nh ? stretch_px(ra[i], mn, mx, inv, g.maxval) : 0;
-                        const int xb = paired ? stretch_px(rb[i], mn, mx, inv, g.maxval) : 0;
-                        seen |= xa | xb;
-                        const float e = (float)(xa + xb) * (float)kInScale, o = paired ? (float)(xa - xb) * (float)kInScale : 0.f;
+                        const int a_ = va[i] ? xa[i] : 0, b_ = vb[i] ? xb[i] : 0;
+                        seen |= a_ | b_;
+                        const float e = (float)(a_ + b_) * (float)kInScale, o = vb[i] ? (float)(a_ - b_) * (float)kInScale : 0.f;
                         umma::split_tf32(e, ph[i], pl[i]);
                         umma::split_tf32(o, qh[i], ql[i]);
                     }
                 } else {
                     float2 cur[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-                    if (c + 1 < nchunks) {                         // the next chunk's values are in flight while this one is split
+                    for (int i = 0; i < 4; ++i) cur[i] = nxt[0][i];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int k = 8 * (c + 1) + 4 * kg + i;
-                            nxt[i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
-                        }
+                    for (int d = 0; d + 1 < PF; ++d)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) nxt[d][i] = nxt[d + 1][i];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {                  // PF chunks ahead: global latency stays off the ring's critical path
+                        const int k = 8 * (c + PF) + 4 * kg + i;
+                        nxt[PF - 1][i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {

@@ -90,3 +90,100 @@ class WellPipeline:
         for p in self.staging:
             self.ctx.device_free(p)
         self.staging = []
+
+
+class RegionPipeline:
+    """Host-buffer fast path of ``StitcherProcess.run`` for uint16 paste jobs that end in OME-Zarr.
+
+    One region per lane, everything enqueued without a host wait: the decoded tiles go up from PINNED staging, the
+    region is fused once into a row-major device canvas (from which ``sb_pyramid`` makes the multiscale levels while
+    it is still resident) and once in ZARR-CHUNK ORDER straight into a pinned host buffer -- level 0 arrives in the
+    layout ``write_ome_zarr_chunked`` dumps with one ``tofile`` per chunk, no re-tiling pass on the host
+    (reference: save_region_ome_zarr, stitcher_process.py:1039-1124).  While lane i's copies
+    and kernels run, the caller decodes region i+1 and writes region i-1.
+    """
+
+    def __init__(self, ctx: _ffi.Context, tile_shape, chunk_hw=(2048, 2048)):
+        self.ctx = ctx
+        self.H, self.W = int(tile_shape[0]), int(tile_shape[1])
+        self.chunk = (int(chunk_hw[0]), int(chunk_hw[1]))
+        self.depth = ctx.num_lanes
+        self.next = 0
+        self.lanes = [dict(tiles_dev=0, tiles_cap=0, canvas_dev=0, canvas_cap=0, pinned_tiles=None, pinned_l0=None,
+                           pinned_levels=None, busy=None) for _ in range(self.depth)]
+
+    @staticmethod
+    def eligible(dtype, blend, output_format, chunks) -> bool:
+        ch, cw = int(chunks[-2]), int(chunks[-1])
+        return (np.dtype(dtype) == np.uint16 and blend == _ffi.SB_BLEND_PASTE and str(output_format).endswith(".zarr") and
+                cw >= 64 and (cw & (cw - 1)) == 0 and ch % 64 == 0)
+
+    def _grow(self, lane, key, nbytes, pinned=False, dtype=np.uint16):
+        st = self.lanes[lane]
+        if pinned:
+            buf = st[key]
+            if buf is None or buf.nbytes < nbytes:
+                st[key] = self.ctx.pinned_empty((nbytes // np.dtype(dtype).itemsize,), dtype)
+            return st[key]
+        if st[key + "_cap"] < nbytes:
+            if st[key + "_dev"]:
+                self.ctx.sync(lane)
+                self.ctx.device_free(st[key + "_dev"])
+            st[key + "_dev"] = self.ctx.device_alloc(nbytes)
+            st[key + "_cap"] = nbytes
+        return st[key + "_dev"]
+
+    def submit(self, job, canvas_shape, n_levels, apply_flatfield):
+        """``job``: ``(plane ndarray, x, y, c, z, crop_t, crop_b, crop_l, crop_r)`` in paste order.  Returns a ticket;
+        ``finish(ticket)`` waits for the lane and yields ``(chunked level 0, [levels 1..])`` as arrays over pinned memory
+        that stay valid until the lane is used again."""
+        lane = self.next
+        self.next = (self.next + 1) % self.depth
+        self.ctx.sync(lane)
+        C, Z, Hc, Wc = (int(v) for v in canvas_shape)
+        n = len(job)
+        tile_bytes = self.H * self.W * 2
+        pinned = self._grow(lane, "pinned_tiles", max(n, 1) * tile_bytes, pinned=True).view(np.uint16)
+        dev_tiles = self._grow(lane, "tiles", max(n, 1) * tile_bytes)
+        tiles = pinned[:n * self.H * self.W].reshape(n, self.H, self.W)
+        dev_job = []
+        for i, (plane, x, y, c, z, ct, cb, cl, cr) in enumerate(job):
+            tiles[i] = plane                                        # pageable decode buffer -> pinned staging
+            dev_job.append((dev_tiles + i * tile_bytes, x, y, c, z, ct, cb, cl, cr))
+        if n:
+            self.ctx.memcpy_async(lane, dev_tiles, pinned, n * tile_bytes, 0)
+        pitch = _ffi.canvas_pitch(Wc)
+        dev_canvas = self._grow(lane, "canvas", C * Z * Hc * pitch * 2)
+        ch, cw = self.chunk
+        ncy, ncx = -(-Hc // ch), -(-Wc // cw)
+        l0 = self._grow(lane, "pinned_l0", C * Z * ncy * ncx * ch * cw * 2, pinned=True).view(np.uint16)
+        l0 = l0[:C * Z * ncy * ncx * ch * cw].reshape(C * Z, ncy, ncx, ch, cw)
+        common = dict(tile_mem=_ffi.SB_MEM_DEVICE, apply_flatfield=apply_flatfield, lane=lane, dtype=_ffi.SB_U16)
+        levels = []
+        if n_levels > 1:
+            # row-major device canvas -> multiscale levels while it is resident (Scaler.nearest, :1061-1062)
+            self.ctx.fuse_region(dev_job, (self.H, self.W), (C, Z, Hc, Wc), out=dev_canvas, out_mem=_ffi.SB_MEM_DEVICE, **common)
+            shapes = self.ctx.pyramid_shapes((1, C, Z, Hc, Wc), n_levels)
+            total = sum(p * a * b for p, a, b in shapes)
+            lv = self._grow(lane, "pinned_levels", total * 2, pinned=True).view(np.uint16)[:total]
+            self.ctx.pyramid((1, C, Z, Hc, Wc), n_levels, src=None, dtype=_ffi.SB_U16, out=lv, lane=lane)
+            off = 0
+            for p, a, b in shapes:
+                levels.append(lv[off:off + p * a * b].reshape(1, C, Z, a, b))
+                off += p * a * b
+        # level 0 in zarr-chunk order, straight to the host
+        self.ctx.fuse_region(dev_job, (self.H, self.W), (C, Z, Hc, Wc), out=l0, out_mem=_ffi.SB_MEM_HOST,
+                             layout=_ffi.SB_LAYOUT_CHUNKED, chunk=(ch, cw), **common)
+        return dict(lane=lane, l0=l0, levels=levels, shape=(C, Z, Hc, Wc))
+
+    def finish(self, ticket):
+        self.ctx.sync(ticket["lane"])
+        return ticket["l0"], ticket["levels"]
+
+    def close(self):
+        self.ctx.sync(-1)
+        for st in self.lanes:
+            for key in ("tiles", "canvas"):
+                if st[key + "_dev"]:
+                    self.ctx.device_free(st[key + "_dev"])
+                    st[key + "_dev"], st[key + "_cap"] = 0, 0
