@@ -30,7 +30,7 @@ EXPORTS = [
     "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_memcpy_async", "sb_set_flatfield", "sb_set_darkfield", "sb_clear_fields",
     "sb_flatfield_apply", "sb_fuse_region", "sb_fuse_regions", "sb_sync", "sb_lane_mark", "sb_lane_wait_mark", "sb_set_lane_stream", "sb_canvas_pitch",
     "sb_chunked_plane_elems", "sb_register_pairs", "sb_register_pairs_async", "sb_normalize",
-    "sb_pyramid_elems", "sb_pyramid", "sb_estimate_flatfield", "sb_selftest", "sb_debug_read",
+    "sb_pyramid_elems", "sb_pyramid", "sb_estimate_flatfield", "sb_selftest", "sb_debug_read", "sb_debug_tc_profile",
 ]
 
 
@@ -125,6 +125,7 @@ def load_library(path: Optional[str] = None):
     lib.sb_selftest.argtypes = [vp, i32, i64, C.POINTER(C.c_uint64)]
     lib.sb_debug_read.argtypes = [vp, i32, i32, vp, i64]
     lib.sb_debug_read.restype = i64
+    lib.sb_debug_tc_profile.argtypes = [vp, C.POINTER(C.c_longlong)]
     if path == LIB_PATH:
         _lib = lib
     return lib

@@ -1,6 +1,7 @@
 // C-ABI entry points of libstitchb200 (include/stitchb200.h): context lifecycle, memory helpers,
 // flat/dark-field storage.  The compute entry points forward to fuse.cu / reg.cu.
 #include "sb_common.cuh"
+#include "reg_tc.cuh"
 
 #include <algorithm>
 #include <mutex>
@@ -373,12 +374,19 @@ int64_t sb_debug_read(sb_ctx* ctx, int lane, int which, void* out, int64_t max_b
     if (!ctx) return SB_ERR_INVALID;
     SB_ENTER(ctx);
     Lane* l = sb_lane(ctx, lane);
-    if (!l || which < 0 || which > 2 || !out) return sb_fail(ctx, SB_ERR_INVALID, "sb_debug_read: bad arguments");
+    if (!l || which < 0 || which > 3 || !out) return sb_fail(ctx, SB_ERR_INVALID, "sb_debug_read: bad arguments");
     cudaDeviceSynchronize();
     const size_t nbytes = std::min<size_t>(l->dbg_bytes[which], max_bytes < 0 ? 0 : (size_t)max_bytes);
     if (nbytes && cudaMemcpy(out, l->dbg_ptr[which], nbytes, cudaMemcpyDeviceToHost) != cudaSuccess)
         return sb_fail(ctx, SB_ERR_CUDA, "sb_debug_read: copy failed");
     return (int64_t)nbytes;
+}
+
+int sb_debug_tc_profile(sb_ctx* ctx, long long* out48) {
+    if (!ctx || !out48) return SB_ERR_INVALID;
+    SB_ENTER(ctx);
+    cudaDeviceSynchronize();
+    return sb_tc_profile_read(out48);
 }
 
 int sb_sync(sb_ctx* ctx, int lane) {

@@ -834,6 +834,9 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     const size_t o_mag = carve((size_t)B * rs * rs * sizeof(double));
     const size_t o_rmax = carve((size_t)B * Sh * sizeof(float));
     const size_t o_Zh = carve(tc.ok ? sb_tc_zh_bytes(tc, B) : 0);
+    static const bool no_tc_updft = getenv("SB_REG_NO_TC_UPDFT") != nullptr;
+    const bool tc_updft = tc.ok && uf > 1 && rs <= 16 && !no_tc_updft;      // upsampled-DFT rows stage on the tensor cores
+    const size_t o_Bup = carve(tc_updft ? sb_tc_updft_table_bytes(tc, B) : 0);
     const size_t way_bytes = off;                           // everything above exists once per concurrent sub-batch
     off = way_bytes * ways;
     const size_t o_peaks = carve((size_t)n * sizeof(PeakOut));
@@ -860,6 +863,7 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     lane->dbg_ptr[0] = tc.ok ? w + o_Zh : nullptr;  lane->dbg_bytes[0] = tc.ok ? sb_tc_zh_bytes(tc, std::min(B, n)) : 0;
     lane->dbg_ptr[1] = w + o_Z;                     lane->dbg_bytes[1] = (size_t)std::min(B, n) * strip * sizeof(T2);
     lane->dbg_ptr[2] = w + o_R;                     lane->dbg_bytes[2] = (size_t)std::min(B, n) * strip * sizeof(T2);
+    lane->dbg_ptr[3] = w + o_T;                     lane->dbg_bytes[3] = (size_t)std::min(B, n) * rs * Sh * sizeof(T2);
     // Descriptors go up from PINNED memory when the caller provides it: a copy from pageable memory synchronises the
     // stream first, i.e. the host would wait for everything already enqueued on this lane (uploads, earlier groups).
     const PairDesc* h_pairs = pairs.data();
@@ -925,15 +929,21 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
         }
         peak_final_kernel<<<nb, 32, 0, ws>>>(bestw, (tc.ok && tc.inverse) ? (Sh >> 7) : nrb_inv, Sh, Sw, swap, rmaxw, d_nz + p0, d_fault, tc.ok ? nullptr : d_sums + 2 * p0, peaks + p0);
         ctx->launches += 4;
-        if (uf > 1) {
+        if (uf > 1 && tc_updft) {
+            rc = sb_tc_updft_rows(ctx, ws, tc, nb, peaks + p0, uf, rs, dftshift, Rw, w + o_Bup + wo, Eyw, Tw, d_fault);
+            if (rc) return rc;
+        } else if (uf > 1) {
             updft_twiddle_kernel<T><<<dim3(8, nb), 256, 0, ws>>>(peaks + p0, Sh, Sw, uf, rs, dftshift, Exw, Eyw);
+            ctx->launches++;
             for (int u0 = 0; u0 < rs; u0 += 16) {            // rs = 15 for the reference's upsample_factor 10: one launch
                 updft_rows_kernel<T, 16><<<nb * nrb_up, 256, 0, ws>>>(Sh, Sw, rs, u0, nrb_up, Rw, Exw, Tw);
                 ctx->launches++;
             }
+        }
+        if (uf > 1) {
             updft_cols_kernel<T><<<nb * rs, 256, 0, ws>>>(Sh, rs, Tw, Eyw, magw);
             updft_final_kernel<<<nb, 32, 0, ws>>>(rs, swap, magw, inv_n, d_nz + p0, peaks + p0);
-            ctx->launches += 3;
+            ctx->launches += 2;
         }
         SB_CUDA(ctx, cudaGetLastError());
     }

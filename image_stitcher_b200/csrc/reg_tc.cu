@@ -23,6 +23,11 @@ namespace {
 //         P[x] = sum_k Re Y[k] c_k cos(2 pi k x / n)         Q[x] = -sum_k Im Y[k] c_k sin(2 pi k x / n)
 //         cc[x] = P[x] + Q[x],   cc[n - x] = P[x] - Q[x]     (x = 0 .. n/2)
 //
+// MODE 2 (first stage of the upsampled-DFT refinement, T4).  skimage's _upsampled_dft contracts the cross-power with a
+// 15 x n twiddle matrix per pair: T[u][y] = sum_x conj(R[y][x]) Ex[u][x].  As one real product per 128 rows: A = (Re R,
+// Im R) over ALL n columns, B = the pair's twiddles arranged as [Ex_re | Ex_im] for the real part and [Ex_im | -Ex_re]
+// for the imaginary part (N = 32 accumulator columns: 16 real + 16 imaginary outputs), both parts into ONE accumulator.
+//
 // A block owns 128 rows (M) of one strip image / one pair; K runs in chunks of 8 through a kTcStages-deep ring of
 // shared-memory operand stages: the A sub-tiles (part 0 / part 1, tf32 hi / lo) are produced by 8 warps -- MODE 0 from
 // the stretched strip rows staged in shared memory (crop + normalize_image's stretch fused into the coalesced load, as
@@ -87,7 +92,19 @@ struct TcArgs {
     int lines_in;                        // lines per pair in Y
     CtaBest* best;                       // [pair][Sh / 128]
     float* rowmax;                       // [pair][Sh]
+    // MODE 2 (upsampled-DFT rows): Y = the full cross-power R [pair][x][y], Bmat = per-pair twiddle images
+    float2* Tm;                          // [pair][u][y], u < rs
+    int rs;
 };
+
+#ifdef SB_TC_PROFILE
+__device__ long long g_tc_prof[3][16];      // per mode: cycles block 0 spent per role / wait (see scratch/tc_profile.py)
+#define TC_T0() const long long t0__ = clock64()
+#define TC_ACC(slot) atomicAdd((unsigned long long*)&g_tc_prof[MODE][slot], (unsigned long long)(clock64() - t0__))
+#else
+#define TC_T0()
+#define TC_ACC(slot)
+#endif
 
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) {
@@ -110,7 +127,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
     const int tiles = Sh >> 7;                  // tiles per strip image
     const int nb = n / 2 + 1, nh = n / 2, no = (n - 1) / 2;
     const int pitch_ns = tc_pitch(2 * n), pitch_sw = tc_pitch(256);      // staged row pitch: plain / transposed frame
-    const int acc_cols = 2 * NP;
+    const int acc_cols = MODE == 2 ? NP : 2 * NP;
+    const int kdim = MODE == 2 ? n : nb;                       // valid K indices of the converters' source (MODE 1 / 2)
     const uint32_t want_cols = (uint32_t)(g.acc_bufs * acc_cols);
     const uint32_t tmem_cols = want_cols <= 32 ? 32 : want_cols <= 64 ? 64 : want_cols <= 128 ? 128 : want_cols <= 256 ? 256 : 512;
     const int my_tiles = blockIdx.x < g.n_tiles ? (g.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -135,8 +153,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
         umma::tmem_relinquish();
         if (lane == 0)
             for (int c = 0; c < kTcStages && c < my_chunks; ++c) {           // the first B stages need no free slot
+                const int t2 = blockIdx.x + (c / nchunks) * gridDim.x;       // MODE 2: the tables belong to the tile's pair
+                const size_t img = (MODE == 2 ? (size_t)(t2 / tiles) * nchunks : 0) + (size_t)(c % nchunks);
                 umma::mbar_expect_tx(ab_full + c, (uint32_t)L.b_stage);
-                umma::bulk_g2s(b_st + c * L.b_stage, g.Bmat + (size_t)(c % nchunks) * L.b_stage, (uint32_t)L.b_stage, ab_full + c);
+                umma::bulk_g2s(b_st + c * L.b_stage, g.Bmat + img * L.b_stage, (uint32_t)L.b_stage, ab_full + c);
             }
     }
     umma::fence_before_sync();
@@ -144,6 +164,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
     umma::fence_after_sync();
     const uint32_t tb = *tmem_slot;
     bool ok = true;
+#ifdef SB_TC_PROFILE
+    const long long t_kernel0 = clock64();
+#endif
 
     if (warp == 13) {
         // =========================================================================== loader (MODE 0): one thread
@@ -153,7 +176,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                 const int mt = tile % tiles, img = (tile / tiles) & 1, p = tile / (2 * tiles);
                 const int y0 = mt << 7;
                 const int b = it % g.stg_bufs, u = it / g.stg_bufs;
-                if (u >= 1) ok = umma::mbar_wait(stg_empty + b, (u - 1) & 1);
+                { TC_T0(); if (u >= 1) ok = umma::mbar_wait(stg_empty + b, (u - 1) & 1); if (blockIdx.x == 0) TC_ACC(0); }
                 uint8_t* stg = smem + L.stg_off + b * g.stg_bytes;
                 const PairDesc pd = g.pairs[p];
                 const uint16_t* src = img ? pd.b : pd.a;
@@ -214,7 +237,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                     sbase = reinterpret_cast<const uint16_t*>(stg + a0) + row;
                     sstep = pitch_sw >> 1;
                 }
-                ok = umma::mbar_wait(stg_full + b, u & 1);
+                { TC_T0(); ok = umma::mbar_wait(stg_full + b, u & 1); if (blockIdx.x == 0 && t == 0) TC_ACC(1); }
             } else {
                 yrow = g.Y + (size_t)p * g.lines_in * Sh + y0 + row;
 #pragma unroll
@@ -222,12 +245,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int k = 8 * d + 4 * kg + i;
-                        nxt[d][i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
+                        nxt[d][i] = k < kdim ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
                     }
             }
             for (int c = 0; c < nchunks && ok; ++c, ++gc) {
                 const int s = gc % kTcStages, use = gc / kTcStages;
                 float ph[4], pl[4], qh[4], ql[4];
+#ifdef SB_TC_PROFILE
+                const long long t_conv0 = clock64();
+#endif
                 if (MODE == 0) {
                     unsigned ra[4], rb[4];
                     bool va[4], vb[4];
@@ -281,7 +307,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {                  // PF chunks ahead: global latency stays off the ring's critical path
                         const int k = 8 * (c + PF) + 4 * kg + i;
-                        nxt[PF - 1][i] = k < nb ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
+                        nxt[PF - 1][i] = k < kdim ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -289,15 +315,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                         umma::split_tf32(cur[i].y, qh[i], ql[i]);
                     }
                 }
-                if (use >= 1) ok = umma::mbar_wait(ab_empty + s, (use - 1) & 1);
+#ifdef SB_TC_PROFILE
+                if (blockIdx.x == 0 && t == 0) atomicAdd((unsigned long long*)&g_tc_prof[MODE][10], (unsigned long long)(clock64() - t_conv0));
+#endif
+                { TC_T0(); if (use >= 1) ok = umma::mbar_wait(ab_empty + s, (use - 1) & 1); if (blockIdx.x == 0 && t == 0) TC_ACC(2); }
                 uint8_t* dst = a_st + s * kAStage + kg * 2048 + row * 16;
                 *reinterpret_cast<float4*>(dst) = make_float4(ph[0], ph[1], ph[2], ph[3]);
                 *reinterpret_cast<float4*>(dst + 4096) = make_float4(pl[0], pl[1], pl[2], pl[3]);
                 *reinterpret_cast<float4*>(dst + 8192) = make_float4(qh[0], qh[1], qh[2], qh[3]);
                 *reinterpret_cast<float4*>(dst + 12288) = make_float4(ql[0], ql[1], ql[2], ql[3]);
+#ifdef SB_TC_PROFILE
+                const long long t_f0 = clock64();
+#endif
                 umma::fence_smem_to_async();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(ab_full + s);
+#ifdef SB_TC_PROFILE
+                if (blockIdx.x == 0 && t == 0) atomicAdd((unsigned long long*)&g_tc_prof[MODE][11], (unsigned long long)(clock64() - t_f0));
+#endif
             }
             if (MODE == 0) {
                 // an all-zero strip has an exactly zero spectrum in the reference: record whether this one has a non-zero pixel
@@ -318,13 +353,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
             for (int it = 0; it < my_tiles && ok; ++it) {
                 const int acc = it % g.acc_bufs, ua = it / g.acc_bufs;
                 if (ua >= 1) {
-                    ok = umma::mbar_wait(acc_empty + acc, (ua - 1) & 1);
+                    { TC_T0(); ok = umma::mbar_wait(acc_empty + acc, (ua - 1) & 1); if (blockIdx.x == 0) TC_ACC(3); }
                     umma::fence_after_sync();
                 }
                 const uint32_t d0 = tb + (uint32_t)(acc * acc_cols);
                 for (int c = 0; c < nchunks && ok; ++c, ++gc) {
                     const int s = gc % kTcStages, use = gc / kTcStages;
-                    ok = umma::mbar_wait(ab_full + s, use & 1);
+                    { TC_T0(); ok = umma::mbar_wait(ab_full + s, use & 1); if (blockIdx.x == 0) TC_ACC(4); }
                     umma::fence_after_sync();
                     const uint32_t as = a0 + s * kAStage, bs = b0 + s * L.b_stage;
                     const uint64_t eh = umma::desc_kmajor(as, 2048, 128), el = umma::desc_kmajor(as + 4096, 2048, 128);
@@ -335,17 +370,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                     umma::mma_tf32(d0, eh, ch, idesc, accum);
                     umma::mma_tf32(d0, el, ch, idesc, 1);
                     umma::mma_tf32(d0, eh, cl, idesc, 1);
-                    umma::mma_tf32(d0 + NP, oh, sh, idesc, accum);
-                    umma::mma_tf32(d0 + NP, ol, sh, idesc, 1);
-                    umma::mma_tf32(d0 + NP, oh, sl, idesc, 1);
+                    const uint32_t d1 = MODE == 2 ? d0 : d0 + NP;              // MODE 2: both parts feed one accumulator
+                    umma::mma_tf32(d1, oh, sh, idesc, MODE == 2 ? 1u : accum);
+                    umma::mma_tf32(d1, ol, sh, idesc, 1);
+                    umma::mma_tf32(d1, oh, sl, idesc, 1);
                     umma::mma_commit(ab_empty + s);
                     // refill the B stage used ONE chunk ago (its MMAs have had a whole chunk to finish)
                     const int g2 = gc - 1 + kTcStages;
                     if (gc >= 1 && g2 < my_chunks) {
                         const int sp = (gc - 1) % kTcStages, up = (gc - 1) / kTcStages;
-                        ok = ok && umma::mbar_wait(ab_empty + sp, up & 1);
+                        { TC_T0(); ok = ok && umma::mbar_wait(ab_empty + sp, up & 1); if (blockIdx.x == 0) TC_ACC(5); }
+                        const int t2 = blockIdx.x + (g2 / nchunks) * gridDim.x;
+                        const size_t img = (MODE == 2 ? (size_t)(t2 / tiles) * nchunks : 0) + (size_t)(g2 % nchunks);
                         umma::mbar_expect_tx(ab_full + sp, (uint32_t)L.b_stage);
-                        umma::bulk_g2s(b_st + sp * L.b_stage, g.Bmat + (size_t)(g2 % nchunks) * L.b_stage, (uint32_t)L.b_stage, ab_full + sp);
+                        umma::bulk_g2s(b_st + sp * L.b_stage, g.Bmat + img * L.b_stage, (uint32_t)L.b_stage, ab_full + sp);
                     }
                 }
                 umma::mma_commit(acc_full + acc);
@@ -362,7 +400,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
             const int p = MODE == 0 ? tile / (2 * tiles) : tile / tiles;
             const int y0 = mt << 7;
             const int acc = it % g.acc_bufs, ua = it / g.acc_bufs;
-            ok = umma::mbar_wait(acc_full + acc, ua & 1);
+            { TC_T0(); ok = umma::mbar_wait(acc_full + acc, ua & 1); if (blockIdx.x == 0 && warp == 9 && lane == 0) TC_ACC(6); }
             umma::fence_after_sync();
             const uint32_t trow = tb + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * acc_cols);
             const int y = y0 + 32 * q + lane;
@@ -378,6 +416,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                         for (int i = 0; i < 8; ++i)
                             if (k0 + i < nb) zp[(size_t)(k0 + i) * Sh] = make_float2(__uint_as_float(re[i]), __uint_as_float(im[i]));
                     }
+                }
+            } else if (MODE == 2) {
+                if (ok) {
+                    float2* tp = g.Tm + (size_t)p * g.rs * Sh + y;
+                    uint32_t re[16], im[16];
+                    umma::tmem_ld8(trow, *reinterpret_cast<uint32_t(*)[8]>(re));
+                    umma::tmem_ld8(trow + 8, *reinterpret_cast<uint32_t(*)[8]>(re + 8));
+                    umma::tmem_ld8(trow + 16, *reinterpret_cast<uint32_t(*)[8]>(im));
+                    umma::tmem_ld8(trow + 24, *reinterpret_cast<uint32_t(*)[8]>(im + 8));
+                    umma::tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+                        if (u < g.rs) tp[(size_t)u * Sh] = make_float2(__uint_as_float(re[u]), __uint_as_float(im[u]));
                 }
             } else {
                 // |cc| of this thread's row: first maximum (ties -> lowest index in the C order of the ORIGINAL strip),
@@ -438,7 +489,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
     if (!ok && lane == 0) atomicExch(g.fault, 1);
     umma::fence_before_sync();
     __syncthreads();
+#ifdef SB_TC_PROFILE
+    if (blockIdx.x == 0 && t == 0) {
+        atomicAdd((unsigned long long*)&g_tc_prof[MODE][7], (unsigned long long)(clock64() - t_kernel0));
+        atomicAdd((unsigned long long*)&g_tc_prof[MODE][8], (unsigned long long)my_tiles);
+        atomicAdd((unsigned long long*)&g_tc_prof[MODE][9], 1ull);
+    }
+#endif
     if (warp == 8) umma::tmem_dealloc(tb, tmem_cols);
+}
+
+// Twiddles of skimage's _upsampled_dft for the tensor-core rows stage (MODE 2) and the column stage:
+//   Ex[u][x] = exp(-2 pi i (u - off_x) fftfreq(n, uf)[x]),  off = dftshift - shift * uf   (shift = wrapped coarse peak)
+// (u - off) and n * uf * fftfreq are integers, so the phase is reduced exactly in integer arithmetic before sincospi.
+// Ex goes straight into the per-pair B operand image of xdft_tc_kernel<2> -- per chunk of 8 x: [B0_hi | B0_lo | B1_hi |
+// B1_lo], 32 rows (output columns: u = real part, 16 + u = imaginary part) x 8, K-major; B0 = [Ex_re | Ex_im] multiplies
+// Re R, B1 = [Ex_im | -Ex_re] multiplies Im R.  Ey[v][y] is written as plain complex rows for updft_cols_kernel.
+__global__ void __launch_bounds__(256) updft_tables_tc_kernel(const PeakOut* __restrict__ peaks, int Sh, int n, int uf, int rs,
+                                                              int dftshift, int nchunks, float* __restrict__ Bimg,
+                                                              float2* __restrict__ Ey) {
+    const int p = blockIdx.y;
+    const PeakOut pk = peaks[p];
+    const int cy = pk.coarse_y > Sh / 2 ? pk.coarse_y - Sh : pk.coarse_y;     // shift[shift > fix(n/2)] -= n
+    const int cx = pk.coarse_x > n / 2 ? pk.coarse_x - n : pk.coarse_x;
+    const int npad = nchunks * 8;
+    const int total = 16 * npad + rs * Sh;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const bool isx = i < 16 * npad;
+        const int ii = isx ? i : i - 16 * npad;
+        const int len = isx ? npad : Sh, nn = isx ? n : Sh;
+        const int u = ii / len, k = ii - u * len;
+        double s = 0.0, c = 0.0;
+        if (u < rs && k < nn) {
+            const long long m = (long long)u - dftshift + (long long)(isx ? cx : cy) * uf;
+            const int sk = (k < (nn + 1) / 2) ? k : k - nn;                  // n * fftfreq(n)[k]
+            const long long den = (long long)nn * uf;
+            long long num = (m * sk) % den;
+            if (num < 0) num += den;
+            sincospi(-2.0 * (double)num / (double)den, &s, &c);
+        }
+        if (!isx) {
+            Ey[((size_t)p * rs + u) * Sh + k] = make_float2((float)c, (float)s);
+            continue;
+        }
+        float rh, rl, ih, il, nh_, nl_;
+        umma::split_tf32((float)c, rh, rl);
+        umma::split_tf32((float)s, ih, il);
+        umma::split_tf32(-(float)c, nh_, nl_);
+        float* img = Bimg + ((size_t)p * nchunks + (k >> 3)) * (4 * 32 * 8);      // 4 sub-tiles of 32 rows x 8 k
+        const int e_re = ((k & 7) >> 2) * (32 * 4) + u * 4 + (k & 3), e_im = e_re + 16 * 4;
+        img[e_re] = rh;               img[32 * 8 + e_re] = rl;                    // B0: column u      <- Ex_re
+        img[e_im] = ih;               img[32 * 8 + e_im] = il;                    //     column 16 + u <- Ex_im
+        img[2 * 32 * 8 + e_re] = ih;  img[3 * 32 * 8 + e_re] = il;                // B1: column u      <- Ex_im
+        img[2 * 32 * 8 + e_im] = nh_; img[3 * 32 * 8 + e_im] = nl_;               //     column 16 + u <- -Ex_re
+    }
 }
 
 // ==========================================================================================================
@@ -622,6 +726,20 @@ static void split_tf32_host(float v, float& hi, float& lo) {
     lo = v - hi;
 }
 
+int sb_tc_profile_read(long long* out48) {          // test / tuning hook: the cycle counters of a -DSB_TC_PROFILE build
+#ifdef SB_TC_PROFILE
+    long long h[3][16];
+    if (cudaMemcpyFromSymbol(h, g_tc_prof, sizeof(h)) != cudaSuccess) return -1;
+    memcpy(out48, h, sizeof(h));
+    long long z[3][16] = {};
+    cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+    return 48;
+#else
+    (void)out48;
+    return 0;
+#endif
+}
+
 size_t sb_tc_zh_bytes(const TcPlan& plan, int n_pairs) { return (size_t)n_pairs * 2 * plan.nb * plan.Sh * sizeof(float2); }
 
 int sb_tc_plan(sb_ctx* ctx, int Sh, int n, TcPlan* plan) {
@@ -763,6 +881,36 @@ int sb_tc_inverse(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs,
     const int grid = std::min(g.n_tiles, ctx->sm_count);
     xdft_tc_kernel<1><<<grid, kTcThreads, plan.smem_inv, st>>>(g);
     ctx->launches++;
+    SB_CUDA(ctx, cudaGetLastError());
+    return SB_OK;
+}
+
+size_t sb_tc_updft_table_bytes(const TcPlan& plan, int n_pairs) {
+    return (size_t)n_pairs * ((plan.n + 7) / 8) * (4 * 32 * 8) * sizeof(float);
+}
+
+// First stage of the upsampled-DFT refinement on the tensor cores: tables (B operand images + Ey) from the coarse
+// peaks, then T[pair][u][y] = sum_x conj(R[y][x]) Ex[u][x].  rs <= 16 (upsample factors up to 10).
+int sb_tc_updft_rows(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs, const void* d_peaks, int uf, int rs,
+                     int dftshift, const void* R, void* Bimg, void* Ey, void* Tm, int* d_fault) {
+    const int nch = (plan.n + 7) / 8;
+    updft_tables_tc_kernel<<<dim3(8, n_pairs), 256, 0, st>>>(static_cast<const PeakOut*>(d_peaks), plan.Sh, plan.n, uf, rs, dftshift, nch,
+                                                             static_cast<float*>(Bimg), static_cast<float2*>(Ey));
+    const int smem = tc_smem_layout(32, 0, 0).total;
+    static int configured = 0;
+    if (smem > configured) {
+        SB_CUDA(ctx, cudaFuncSetAttribute(xdft_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    TcArgs g = {};
+    g.Sh = plan.Sh; g.n = plan.n; g.NP = 32; g.nchunks = nch; g.swap = 0; g.stg_bytes = 0;
+    g.Bmat = static_cast<const uint8_t*>(Bimg); g.fault = d_fault;
+    g.Y = static_cast<const float2*>(R); g.lines_in = plan.n;
+    g.Tm = static_cast<float2*>(Tm); g.rs = rs;
+    g.n_tiles = n_pairs * (plan.Sh >> 7); g.stg_bufs = 0; g.acc_bufs = 2;
+    const int grid = std::min(g.n_tiles, ctx->sm_count);
+    xdft_tc_kernel<2><<<grid, kTcThreads, smem, st>>>(g);
+    ctx->launches += 2;
     SB_CUDA(ctx, cudaGetLastError());
     return SB_OK;
 }

@@ -37,3 +37,10 @@ int sb_tc_columns(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs,
 int sb_tc_inverse(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs, const void* Y, int lines_in, int swap, void* best,
                   float* rowmax, int* d_fault);
 size_t sb_tc_zh_bytes(const TcPlan& plan, int n_pairs);
+// Upsampled-DFT refinement, first stage, on the tensor cores (rs <= 16): twiddle tables from the coarse peaks (B operand
+// images into `Bimg`, sb_tc_updft_table_bytes() bytes; Ey[pair][v][y]) and T[pair][u][y] = sum_x conj(R[y][x]) Ex[u][x].
+size_t sb_tc_updft_table_bytes(const TcPlan& plan, int n_pairs);
+int sb_tc_updft_rows(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs, const void* d_peaks, int uf, int rs,
+                     int dftshift, const void* R, void* Bimg, void* Ey, void* Tm, int* d_fault);
+
+int sb_tc_profile_read(long long* out48);   // cycle counters of a -DSB_TC_PROFILE build (0 = not such a build)

@@ -54,8 +54,8 @@ struct Lane {
     void* reg_host = nullptr;       // pinned block the registration results are copied into
     size_t reg_host_cap = 0;
     void* reg_pending = nullptr;    // parked asynchronous registration job (RegPending in reg.cu)
-    void* dbg_ptr[3] = {nullptr, nullptr, nullptr};   // last registration group's Zh / Y / R of sub-batch 0 (sb_debug_read, tests)
-    size_t dbg_bytes[3] = {0, 0, 0};
+    void* dbg_ptr[4] = {nullptr, nullptr, nullptr, nullptr};   // last registration group's Zh / Y / R / T of sub-batch 0 (sb_debug_read, tests)
+    size_t dbg_bytes[4] = {0, 0, 0, 0};
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // extra streams of the lane: registration sub-batches rotate over them
     cudaEvent_t aux_fork = nullptr, aux_join[3] = {nullptr, nullptr, nullptr};
     std::vector<int32_t> rect_pieces;   // cached rectangle decomposition of the rectangle-streaming paste kernel ...

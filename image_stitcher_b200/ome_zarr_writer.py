@@ -140,10 +140,12 @@ def write_ome_zarr(path: str, data: np.ndarray, *, pixel_size_um: float, dz_um: 
 
 
 def write_ome_zarr_chunked(path: str, chunked: np.ndarray, shape, chunk_hw, *, pixel_size_um: float, dz_um: float = 1.0,
-                           channel_names: Sequence[str], channel_colors: Sequence[int], name: Optional[str] = None) -> str:
-    """Level 0 only, from the library's SB_LAYOUT_CHUNKED buffer: ``chunked`` is
-    ``(C * Z, ncy, ncx, chunk_h, chunk_w)`` -- each chunk contiguous, edge chunks already zero-padded --
-    and ``shape`` the logical ``(C, Z, Hc, Wc)``.  No re-tiling pass on the host: one write per chunk."""
+                           channel_names: Sequence[str], channel_colors: Sequence[int], name: Optional[str] = None,
+                           levels: Optional[Sequence[np.ndarray]] = None) -> str:
+    """Level 0 from the library's SB_LAYOUT_CHUNKED buffer: ``chunked`` is ``(C * Z, ncy, ncx, chunk_h, chunk_w)`` -- each
+    chunk contiguous, edge chunks already zero-padded -- and ``shape`` the logical ``(C, Z, Hc, Wc)``.  No re-tiling pass
+    on the host: one write per chunk.  ``levels`` = the multiscale levels 1.. as ``(1, C, Z, h, w)`` arrays
+    (``sb_pyramid``); they are small and go through the ordinary per-level writer."""
     C, Z, H, W = (int(v) for v in shape)
     ch_y, ch_x = int(chunk_hw[0]), int(chunk_hw[1])
     ncy, ncx = -(-H // ch_y), -(-W // ch_x)
@@ -156,8 +158,12 @@ def write_ome_zarr_chunked(path: str, chunked: np.ndarray, shape, chunk_hw, *, p
             for iy in range(ncy):
                 for ix in range(ncx):
                     _write_chunk(os.path.join(path, "0"), (0, c, z, iy, ix), buf[c * Z + z, iy, ix], None)
+    n_written = 1
+    for l, level in enumerate(levels or [], start=1):
+        _write_level(os.path.join(path, str(l)), np.asarray(level), (1, 1, 1, ch_y, ch_x), None)
+        n_written += 1
     _dump(os.path.join(path, ".zattrs"),
-          _group_attrs(name or os.path.basename(path).replace(".ome.zarr", ""), 1, pixel_size_um, dz_um,
+          _group_attrs(name or os.path.basename(path).replace(".ome.zarr", ""), n_written, pixel_size_um, dz_um,
                        channel_names, channel_colors, buf.dtype))
     return path
 

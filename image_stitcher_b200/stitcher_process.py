@@ -523,43 +523,48 @@ class StitcherProcess(Process):
         with ThreadPoolExecutor(max_workers=self.decode_threads) as pool:
             return list(pool.map(_load, data.items()))
 
+    def _region_job(self, timepoint, region, loaded=None):
+        """Geometry of one region: the paste-ordered ``sb_tile`` tuples and the canvas shape (:883-942)."""
+        data = self.get_region_data(int(timepoint), region)
+        width, height = self.calculate_output_dimensions(timepoint, region)
+        lattice = self._lattice()
+        xs, ys = list(self.x_positions), list(self.y_positions)
+        solved = None
+        if self.use_registration and self.placement == "global":
+            solved = self.tile_positions.get((int(timepoint), region)) or self.register_region_global(timepoint, region)
+            width = max(p[0] for p in solved.values()) + self.input_width
+            height = max(p[1] for p in solved.values()) + self.input_height
+        self.emit_status(f"Stitching... (Timepoint:{timepoint} Region:{region})")
+        self.check_stop()
+        job = []
+        if loaded is None:
+            loaded = self._decode_region(timepoint, region)
+        for key, info, tile, exc in loaded:
+            if tile is None:
+                self.emit_status(f"Error Loading Image {info['filepath']}: {exc}")
+                continue
+            if solved is not None:
+                p = geo.Placement(*solved[(info["x"], info["y"])])
+            else:
+                p = geo.place_tile(info["x"], info["y"], self.input_width, self.input_height, xs, ys,
+                                   self.pixel_size_um, lattice)
+            for c, plane in self._tile_planes(tile, key[4]):
+                if plane.shape != (self.input_height, self.input_width):
+                    # the C ABI reads input_height x input_width pixels per tile: skip what does not have them
+                    self.emit_status(f"Error Loading Image {info['filepath']}: shape {plane.shape} != "
+                                     f"{(self.input_height, self.input_width)}")
+                    continue
+                plane = np.ascontiguousarray(plane, dtype=self._pixel_np())
+                job.append((plane, p.x, p.y, c, key[3], p.crop_t, p.crop_b, p.crop_l, p.crop_r))
+        return job, (self.num_c, self.num_z, height, width), len(data)
+
     def stitch_region(self, timepoint, region, loaded=None):
         """One region -> ``(1, C, Z, Hc, Wc)`` NumPy canvas, ONE ``sb_fuse_region`` call (:883-956).  ``loaded`` takes the
         result of an earlier ``_decode_region`` (``run`` decodes the next region while this one is fused and saved)."""
         start = time.time()
         try:
-            data = self.get_region_data(int(timepoint), region)
-            width, height = self.calculate_output_dimensions(timepoint, region)
-            lattice = self._lattice()
+            job, (_, _, height, width), n_data = self._region_job(timepoint, region, loaded)
             xs, ys = list(self.x_positions), list(self.y_positions)
-            solved = None
-            if self.use_registration and self.placement == "global":
-                solved = self.tile_positions.get((int(timepoint), region)) or self.register_region_global(timepoint, region)
-                width = max(p[0] for p in solved.values()) + self.input_width
-                height = max(p[1] for p in solved.values()) + self.input_height
-            self.emit_status(f"Stitching... (Timepoint:{timepoint} Region:{region})")
-            self.check_stop()
-            job, keep = [], []
-            if loaded is None:
-                loaded = self._decode_region(timepoint, region)
-            for key, info, tile, exc in loaded:
-                if tile is None:
-                    self.emit_status(f"Error Loading Image {info['filepath']}: {exc}")
-                    continue
-                if solved is not None:
-                    p = geo.Placement(*solved[(info["x"], info["y"])])
-                else:
-                    p = geo.place_tile(info["x"], info["y"], self.input_width, self.input_height, xs, ys,
-                                       self.pixel_size_um, lattice)
-                for c, plane in self._tile_planes(tile, key[4]):
-                    if plane.shape != (self.input_height, self.input_width):
-                        # the C ABI reads input_height x input_width pixels per tile: skip what does not have them
-                        self.emit_status(f"Error Loading Image {info['filepath']}: shape {plane.shape} != "
-                                         f"{(self.input_height, self.input_width)}")
-                        continue
-                    plane = np.ascontiguousarray(plane, dtype=self._pixel_np())
-                    keep.append(plane)
-                    job.append((plane, p.x, p.y, c, key[3], p.crop_t, p.crop_b, p.crop_l, p.crop_r))
             out = np.empty((1, self.num_c, self.num_z, height, width), dtype=self._pixel_np())
             if self.apply_flatfield:
                 self._sync_fields()
@@ -576,7 +581,7 @@ class StitcherProcess(Process):
                     out.shape, self.num_pyramid_levels, dtype=_ffi._pixel_dtype(out)))
                 while len(self._pyramids) > 4:             # callers that never save: do not hoard levels (dicts keep insertion order)
                     self._pyramids.pop(next(iter(self._pyramids)))
-            self.emit_progress(len(data), len(data))
+            self.emit_progress(n_data, n_data)
             print(f"(Timepoint:{timepoint}, Region:{region}) Complete Stitching in {time.time() - start:.1f}s\n")
             return out
         except Exception as exc:
@@ -620,7 +625,18 @@ class StitcherProcess(Process):
             levels = None                                  # not the canvas stitch_region produced: slice on the host
         write_ome_zarr(path, stitched_region, pixel_size_um=self.pixel_size_um, dz_um=dz,
                        channel_names=self.monochrome_channels, channel_colors=self.monochrome_colors,
-                       num_levels=n_levels, chunks=self.chunks, levels=levels)
+                       num_levels=n_levels, chunks=self.chunks, levels=levels, name=f"{region}_t{timepoint}")
+        return path
+
+    def _save_ticket(self, timepoint, region, pipe, ticket):
+        """Writer-thread half of the fast path: wait for the lane, dump level 0 chunk by chunk, levels 1.. as made on the GPU."""
+        from .ome_zarr_writer import write_ome_zarr_chunked
+        l0, levels = pipe.finish(ticket)
+        path = self.per_timepoint_region_output_template.format(timepoint=timepoint, region=region)
+        dz = self.acquisition_params.get("dz(um)", 1.0) if self.acquisition_params else 1.0
+        write_ome_zarr_chunked(path, l0, ticket["shape"], self.chunks[-2:], pixel_size_um=self.pixel_size_um, dz_um=dz,
+                               channel_names=self.monochrome_channels, channel_colors=self.monochrome_colors,
+                               name=f"{region}_t{timepoint}", levels=levels)
         return path
 
     def run(self):
@@ -653,21 +669,48 @@ class StitcherProcess(Process):
                 os.makedirs(os.path.join(self.output_folder, f"{timepoint}_stitched"), exist_ok=True)
             # three stages in flight: decode of region i+1 (thread pool), GPU fusion of region i (this thread),
             # OME-Zarr write of region i-1 (writer thread)
+            from .pipeline import RegionPipeline
+            fast = (os.environ.get("SB_NO_FAST_IO") is None and self.placement != "global" and
+                    RegionPipeline.eligible(self.dtype, _ffi.BLEND_MODES[self.blend_mode], self.output_format, self.chunks))
+            pipe = RegionPipeline(self.ctx, (self.input_height, self.input_width), self.chunks[-2:]) if fast and work else None
+            self.fast_io_used = pipe is not None
             with ThreadPoolExecutor(max_workers=1) as prefetch, ThreadPoolExecutor(max_workers=1) as writer:
                 nxt = prefetch.submit(self._decode_region, *work[0]) if work else None
                 pending_write = None
+                lane_writes = {}                                   # lane -> write still reading that lane's pinned buffers
                 for i, (timepoint, region) in enumerate(work):
                     self.check_stop()
                     loaded = nxt.result()
                     nxt = prefetch.submit(self._decode_region, *work[i + 1]) if i + 1 < len(work) else None
-                    stitched = self.stitch_region(timepoint, region, loaded=loaded)
-                    if pending_write is not None:
-                        last_path = pending_write.result()
+                    if pipe is None:
+                        stitched = self.stitch_region(timepoint, region, loaded=loaded)
+                        if pending_write is not None:
+                            last_path = pending_write.result()
+                        self.emit_status(f"Saving... (Timepoint:{timepoint} Region:{region})", is_saving=True)
+                        pending_write = writer.submit(self.save_region_ome_zarr, timepoint, region, stitched,
+                                                      self.num_pyramid_levels)  # per-region value, fixed before the next region
+                        continue
+                    # fast path: pinned staging in, level 0 back in zarr-chunk order + device-side pyramid, nothing re-tiled
+                    start = time.time()
+                    job, cshape, n_data = self._region_job(timepoint, region, loaded)
+                    if self.apply_flatfield:
+                        self._sync_fields()
+                    busy = lane_writes.pop(pipe.next, None)
+                    if busy is not None:
+                        last_path = busy.result()              # the lane's pinned buffers are free again
+                    n_levels = self.num_pyramid_levels
+                    ticket = pipe.submit(job, cshape, n_levels, self.apply_flatfield)
+                    self.emit_progress(n_data, n_data)
+                    print(f"(Timepoint:{timepoint}, Region:{region}) Stitching enqueued in {time.time() - start:.1f}s\n")
                     self.emit_status(f"Saving... (Timepoint:{timepoint} Region:{region})", is_saving=True)
-                    pending_write = writer.submit(self.save_region_ome_zarr, timepoint, region, stitched,
-                                                  self.num_pyramid_levels)      # per-region value, fixed before the next region
-                if pending_write is not None:
+                    lane_writes[ticket["lane"]] = writer.submit(self._save_ticket, timepoint, region, pipe, ticket)
+                    pending_write = lane_writes[ticket["lane"]]
+                for fut in lane_writes.values():
+                    last_path = fut.result()
+                if pipe is None and pending_write is not None:
                     last_path = pending_write.result()
+            if pipe is not None:
+                pipe.close()
             self.check_stop()
             self.emit_complete(last_path, self.dtype)
             print(f"Processing complete. Total time: {time.time() - stime:.1f}s")

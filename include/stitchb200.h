@@ -254,9 +254,12 @@ enum { SB_SELFTEST_STRETCH = 0, SB_SELFTEST_DIVIDE = 1, SB_SELFTEST_UMMA = 2 };
 int sb_selftest(sb_ctx* ctx, int which, int64_t arg, uint64_t* out);
 /* Test hook: intermediates of the lane's last float32 registration group (first sub-batch), as left in its workspace:
  * which = 0: half spectra along the short strip axis Zh[pair][image][k][y] (tensor-core path only), 1: the inverse
- * column transform Y[pair][x][y], 2: the normalised cross-power R[pair][x][y]; complex64, y (the strip's long axis)
- * fastest.  Returns the bytes copied (<= max_bytes) or a negative status. */
+ * column transform Y[pair][x][y], 2: the normalised cross-power R[pair][x][y], 3: the first stage of the upsampled
+ * DFT T[pair][u][y]; complex64, y (the strip's long axis) fastest.  Returns the bytes copied (<= max_bytes) or a negative status. */
 int64_t sb_debug_read(sb_ctx* ctx, int lane, int which, void* out, int64_t max_bytes);
+/* Tuning hook: per-role wait / work cycle counters of the tensor-core kernels, filled only by a -DSB_TC_PROFILE build
+ * (3 modes x 16 counters of block 0; read-and-clear).  Returns the number of values written (0 in a normal build). */
+int sb_debug_tc_profile(sb_ctx* ctx, long long* out48);
 
 #ifdef __cplusplus
 }

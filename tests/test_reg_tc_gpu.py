@@ -75,6 +75,17 @@ def test_tensor_core_stages_match_numpy(ctx, tiles, direction, ov):
     for kx in range(1, (n - 1) // 2 + 1):
         assert np.array_equal(R[n - kx], np.conj(R[kx][(-np.arange(Sh)) % Sh]))
         assert np.array_equal(Y[n - kx], np.conj(Y[kx]))
+    # ---- T4: first stage of the upsampled DFT around the coarse peak, T[u][y] = sum_x conj(R[y][x]) Ex[u][x]
+    uf, rs = 10, 15
+    T = ctx.debug_read(0, 3, rs * Sh).reshape(rs, Sh)
+    cy, cx = res["coarse"]
+    if direction == V_DIR:                                       # the kernels work in the transposed frame
+        cy, cx = cx, cy
+    cxw = cx - n if cx > n // 2 else cx
+    off = rs // 2 - cxw * uf
+    Ex = np.exp(-2j * np.pi * (np.arange(rs) - off)[:, None] * sfft.fftfreq(n, uf)[None, :])
+    Tn = Ex @ np.conj(R.astype(np.complex128))                   # R is stored [x][y]
+    assert np.abs(T - Tn).max() / np.abs(Tn).max() < 5e-6
     # ---- and the chain built on them lands where the complex128 oracle does (the narrower strips do not reach the
     # 205-pixel overlap of these tiles: their correlation is noise, an argmax float32 need not reproduce)
     if ov == 214:
