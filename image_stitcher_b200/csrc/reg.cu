@@ -766,10 +766,12 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     // workspace slice) -- the chain is a sequence of short dependent kernels, and the neighbours' blocks fill the tails
     // and launch gaps.  Measured on B200 (1152 pairs): 64 MB of spectra in flight (L2 resident) 18.6 ms, 128 MB 17.1,
     // 256 MB 16.7, 384 MB over 3 streams 16.1 (15.3 with 3 blocks per SM), 768 MB over 4 streams 14.9: fewer, larger launches beat
-    // strict L2 residency, so the budget is 768 MB (54 pairs of 1024 x 214 per sub-batch).
-    static const int kWays = getenv("SB_REG_WAYS") ? std::max(1, std::min(4, atoi(getenv("SB_REG_WAYS")))) : 4;
+    // strict L2 residency.  The persistent tensor-core kernels (r2) want MANY tiles per block -- at 54 pairs a block sees
+    // 3-6 tiles and the pipeline fill / drain is a third of the launch -- so the budget is 4 GB over 2 streams: the 576
+    // pairs of one direction of a 96-well plate in one sub-batch (7.8 -> 7.35 ms per 1152 pairs at 4.5 GB / 1 stream).
+    static const int kWays = getenv("SB_REG_WAYS") ? std::max(1, std::min(4, atoi(getenv("SB_REG_WAYS")))) : 2;
     const size_t per_pair = 2 * strip * sizeof(T2);
-    static const size_t kL2Budget = (size_t)(getenv("SB_REG_L2_MB") ? std::max(8, atoi(getenv("SB_REG_L2_MB"))) : 768) << 20;
+    static const size_t kL2Budget = (size_t)(getenv("SB_REG_L2_MB") ? std::max(8, atoi(getenv("SB_REG_L2_MB"))) : 4096) << 20;
     int B = (int)std::max<size_t>(1, kL2Budget / per_pair);
     int ways = 1;
     while (ways < kWays && B / (ways + 1) >= 2 && n > B / (ways + 1)) ++ways;
@@ -837,6 +839,8 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     static const bool no_tc_updft = getenv("SB_REG_NO_TC_UPDFT") != nullptr;
     const bool tc_updft = tc.ok && uf > 1 && rs <= 16 && !no_tc_updft;      // upsampled-DFT rows stage on the tensor cores
     const size_t o_Bup = carve(tc_updft ? sb_tc_updft_table_bytes(tc, B) : 0);
+    const bool half_lines = tc.ok && tc.inverse && (uf == 1 || tc_updft);   // no radix kernel reads R / Y: half arrays
+    const int tc_lines = half_lines ? Sw / 2 + 1 : Sw;
     const size_t way_bytes = off;                           // everything above exists once per concurrent sub-batch
     off = way_bytes * ways;
     const size_t o_peaks = carve((size_t)n * sizeof(PeakOut));
@@ -861,8 +865,9 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     unsigned long long* d_sums = (unsigned long long*)(w + o_sums);
     SB_CUDA(ctx, cudaMemsetAsync(d_nz, 0, (o_sums - o_nz) + (size_t)2 * n * sizeof(unsigned long long), st));
     lane->dbg_ptr[0] = tc.ok ? w + o_Zh : nullptr;  lane->dbg_bytes[0] = tc.ok ? sb_tc_zh_bytes(tc, std::min(B, n)) : 0;
-    lane->dbg_ptr[1] = w + o_Z;                     lane->dbg_bytes[1] = (size_t)std::min(B, n) * strip * sizeof(T2);
-    lane->dbg_ptr[2] = w + o_R;                     lane->dbg_bytes[2] = (size_t)std::min(B, n) * strip * sizeof(T2);
+    const size_t dbg_strip = tc.ok ? (size_t)tc_lines * Sh : strip;          // (half arrays: n/2 + 1 lines per pair)
+    lane->dbg_ptr[1] = w + o_Z;                     lane->dbg_bytes[1] = (size_t)std::min(B, n) * dbg_strip * sizeof(T2);
+    lane->dbg_ptr[2] = w + o_R;                     lane->dbg_bytes[2] = (size_t)std::min(B, n) * dbg_strip * sizeof(T2);
     lane->dbg_ptr[3] = w + o_T;                     lane->dbg_bytes[3] = (size_t)std::min(B, n) * rs * Sh * sizeof(T2);
     // Descriptors go up from PINNED memory when the caller provides it: a copy from pageable memory synchronises the
     // stream first, i.e. the host would wait for everything already enqueued on this lane (uploads, earlier groups).
@@ -913,7 +918,9 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
             void* Zhw = w + o_Zh + wo;
             rc = sb_tc_forward(ctx, ws, tc, d_pairs + p0, nb, d_mm, tile_w, swap, maxval, Zhw, d_nz + p0, d_fault);
             if (rc) return rc;
-            rc = sb_tc_columns(ctx, ws, tc, nb, Zhw, Rw, Zw, Sw, 1);
+            // full arrays with the mirrored (conjugate) lines only for the radix kernels downstream: R for updft_rows_kernel,
+            // Y for rows_inv_argmax_kernel; the tensor-core stages read the half arrays
+            rc = sb_tc_columns(ctx, ws, tc, nb, Zhw, Rw, Zw, tc_lines, half_lines ? 0 : (1 | (tc.inverse ? 0 : 2)));
             if (rc) return rc;
             ctx->launches -= 2;                          // (counted below with the other two)
         } else {
@@ -921,7 +928,7 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
             k2<<<nb * ncg, 256, smem_y, ws>>>(Sh, Sw, ncg, tw_y, py_plan, cy, cyn, Zw, Rw);
         }
         if (tc.ok && tc.inverse) {
-            rc = sb_tc_inverse(ctx, ws, tc, nb, Zw, Sw, swap, bestw, rmaxw, d_fault);
+            rc = sb_tc_inverse(ctx, ws, tc, nb, Zw, tc_lines, swap, bestw, rmaxw, d_fault);
             if (rc) return rc;
             ctx->launches--;
         } else {
@@ -930,7 +937,7 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
         peak_final_kernel<<<nb, 32, 0, ws>>>(bestw, (tc.ok && tc.inverse) ? (Sh >> 7) : nrb_inv, Sh, Sw, swap, rmaxw, d_nz + p0, d_fault, tc.ok ? nullptr : d_sums + 2 * p0, peaks + p0);
         ctx->launches += 4;
         if (uf > 1 && tc_updft) {
-            rc = sb_tc_updft_rows(ctx, ws, tc, nb, peaks + p0, uf, rs, dftshift, Rw, w + o_Bup + wo, Eyw, Tw, d_fault);
+            rc = sb_tc_updft_rows(ctx, ws, tc, nb, peaks + p0, uf, rs, dftshift, Rw, tc_lines, w + o_Bup + wo, Eyw, Tw, d_fault);
             if (rc) return rc;
         } else if (uf > 1) {
             updft_twiddle_kernel<T><<<dim3(8, nb), 256, 0, ws>>>(peaks + p0, Sh, Sw, uf, rs, dftshift, Exw, Eyw);
@@ -1286,17 +1293,27 @@ int sb_normalize_impl(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, in
 }
 
 // ------------------------------------------------------------------------------------------ self-test (test hook)
-// Exhaustive proof that the integer stretch fused into the strip load (stretch_px) equals the float64 expression of
+// Exhaustive proof that the integer stretches fused into the strip loads (stretch_px of the radix kernels; stretch_bits and
+// stretch_core of the tensor-core converters, with their hand-over to stretch_px) equal the float64 expression of
 // normalize_image (stretch_px_f64, stitcher_process.py:844-855) for EVERY pixel value and tile range: all pairs
 // a = v - min, b = max - min with 0 <= a <= b, 1 <= b <= maxval (2^31 pairs for uint16).
 namespace {
 __global__ void __launch_bounds__(256) selftest_stretch_kernel(int maxval, unsigned long long* __restrict__ res) {
     const int b = blockIdx.x + 1;
     const float inv = (float)maxval / (float)b;                         // as rows_fwd_kernel forms it
-    unsigned long long bad = 0, first = ~0ull;
+    const float inv_lo = stretch_inv_lo((unsigned)b, (unsigned)maxval);   // as the tensor-core converters form it
+    const unsigned magic_b = kStretchMagic * (unsigned)b;
+    unsigned long long bad = 0, first = ~0ull, fallbacks = 0;
     for (int a = threadIdx.x; a <= b; a += blockDim.x) {
         const int fast = stretch_px((unsigned)a, 0, b, inv, maxval), ref = stretch_px_f64((unsigned)a, 0, b, maxval);
-        if (fast != ref) {
+        // the converters' form: magic-number bits, one-sided repair; `exact` hands the value to stretch_px
+        bool ex = false, ex2 = false;
+        const unsigned bits = stretch_bits((unsigned)a, (unsigned)b, inv_lo, (unsigned)maxval, magic_b, ex);
+        const int fast_tc = ex ? fast : (int)(bits - kStretchMagic);
+        const int core = stretch_core((unsigned)a, (unsigned)b, inv, (unsigned)maxval, ex2);      // (edge chunks, b < maxval)
+        const int fast_core = (ex2 || b == maxval) ? fast : core;
+        fallbacks += ex ? 1 : 0;
+        if (fast != ref || fast_tc != ref || fast_core != ref) {
             ++bad;
             const unsigned long long key = ((unsigned long long)b << 32) | (unsigned)a;
             first = key < first ? key : first;
@@ -1306,6 +1323,7 @@ __global__ void __launch_bounds__(256) selftest_stretch_kernel(int maxval, unsig
         atomicAdd(res + 1, bad);
         atomicMin(res + 2, first);
     }
+    if (fallbacks) atomicAdd(res + 3, fallbacks);
 }
 }  // namespace
 
@@ -1314,12 +1332,12 @@ int sb_selftest_stretch_impl(sb_ctx* ctx, int maxval, uint64_t* out) {
     Lane* lane = sb_lane(ctx, 0);
     int rc = sb_reserve(ctx, lane->work, 64);
     if (rc) return rc;
-    unsigned long long init[3] = {0ull, 0ull, ~0ull};
+    unsigned long long init[4] = {0ull, 0ull, ~0ull, 0ull};
     SB_CUDA(ctx, cudaMemcpyAsync(lane->work.p, init, sizeof(init), cudaMemcpyHostToDevice, lane->stream));
     selftest_stretch_kernel<<<maxval, 256, 0, lane->stream>>>(maxval, (unsigned long long*)lane->work.p);
     ctx->launches++;
     SB_CUDA(ctx, cudaGetLastError());
-    SB_CUDA(ctx, cudaMemcpyAsync(out, lane->work.p, 24, cudaMemcpyDeviceToHost, lane->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(out, lane->work.p, 32, cudaMemcpyDeviceToHost, lane->stream));   // out[3]: exact-quotient fallbacks
     SB_CUDA(ctx, cudaStreamSynchronize(lane->stream));
     out[0] = (uint64_t)maxval * ((uint64_t)maxval + 3) / 2;            // sum over b of (b + 1)
     return SB_OK;

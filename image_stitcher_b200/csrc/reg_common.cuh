@@ -53,6 +53,27 @@ __device__ __forceinline__ int stretch_core(unsigned a, unsigned b, float inv, u
     return (int)k;
 }
 
+// The form the tensor-core converters run (reg_tc.cu, 8 warps x 14 chunks per tile: instruction count is what bounds them).
+// The float estimate is biased DOWNWARD -- inv_lo = maxval / b * (1 - 1.5e-6), all rounding errors together stay below
+// 2e-7 relative -- so that trunc(a * inv_lo) is k or k - 1 (never above: q * 1.7e-6 < 0.12 for q <= 65535) and ONE compare
+// of the exact integer remainder repairs it.  Returns kStretchMagic + k (the float 2^23 bit pattern carrying k in its
+// mantissa: sums and differences of two of them cancel the constant) and raises `exact` as stretch_core does.
+// magic_b = kStretchMagic * b (mod 2^32), inv_lo = stretch_inv_lo(b, maxval): once per tile.
+constexpr unsigned kStretchMagic = 0x4B000000u;
+__device__ __forceinline__ float stretch_inv_lo(unsigned b, unsigned maxval) {
+    return __fmul_rn(__fdiv_rn((float)maxval, (float)b), 0.9999985f);
+}
+__device__ __forceinline__ unsigned stretch_bits(unsigned a, unsigned b, float inv_lo, unsigned maxval, unsigned magic_b, bool& exact) {
+    const float af = __uint_as_float(kStretchMagic | a) - 8388608.0f;                          // a < 2^16: exact
+    unsigned bits = __float_as_uint(__fadd_rz(__fmul_rn(af, inv_lo), 8388608.0f));             // kStretchMagic + k - {0, 1}
+    unsigned rem = a * maxval + magic_b - bits * b;                                            // in [0, 2 b)
+    const bool ge = rem >= b;
+    bits += ge ? 1u : 0u;
+    rem -= ge ? b : 0u;
+    exact = exact || (rem == 0u && a != 0u);
+    return bits;
+}
+
 // The same value without the float64 divide.  With a = v - min, b = max - min the exact quotient a * 65535 / b is
 // rational with denominator b <= 65535, so unless it is an integer it lies at least 1 / 65535 away from the next
 // one, while the float64 evaluation is off by at most 65535 * 2^-52: trunc() of both agree.  When b divides

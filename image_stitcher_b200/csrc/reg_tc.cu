@@ -39,15 +39,23 @@ namespace {
 // row maximum (what rows_inv_argmax_kernel of the radix path emits).
 // ==========================================================================================================
 // The kernel is PERSISTENT (one block per SM) and warp-specialised, every hand-over an mbarrier:
-//     warps 0-7   converters   MODE 0: raw strip rows in shared memory -> stretch (normalize_image, :844-855) -> fold ->
-//                              tf32 split -> A operand stages; MODE 1: Y -> A stages straight from global (coalesced)
-//     warp  8     one thread   B stages by bulk copy, tcgen05.mma issue, tcgen05.commit
-//     warps 9-12  epilogue     TMEM accumulators of tile i-1 (2 accumulator buffers) -> global
-//     warp  13    one thread   (MODE 0) the raw strip rows of tile i+1 by 1-D bulk copies (2 staged tiles)
+//     warps 0-15  converters   MODE 0: raw strip rows in shared memory -> stretch (normalize_image, :844-855) -> fold ->
+//                              tf32 split -> A operand stages; MODE 1 / 2: Y or R -> A stages straight from global
+//                              (coalesced).  Two groups of 8 warps take alternate chunks: the conversion is the
+//                              longest stage (r2 cycle counters: 12 k of 18 k cycles per tile with one group)
+//     warp  16    one thread   tcgen05.mma issue, tcgen05.commit
+//     warps 17-20 epilogue     TMEM accumulators of tile i-1 (2 accumulator buffers) -> global
+//     warp  21                 (MODE 0) the raw strip rows of tile i+1 by 1-D bulk copies (2 staged tiles), 4 rows per lane
+//     warp  22    one thread   B stages (table slices) by bulk copy -- off the MMA thread, whose loop bounds modes 1 / 2
 // so the load of one tile, the operand conversion and the MMAs of the next and the read-back of the previous overlap
 // (the first version ran the phases one after the other in one-tile blocks: tensor pipe 6 % busy, issue 22 %; the second
 // loaded the rows with ordinary loads in four warps and was bound by their latency).
-constexpr int kTcThreads = 14 * 32;
+constexpr int kCvWarps = 16;             // converter warps: two groups of 8, group g converts the chunks c = g (mod 2)
+constexpr int kMmaWarp = kCvWarps;       // warp 16
+constexpr int kEpiWarp0 = kCvWarps + 1;  // warps 17-20 (warp % 4 = 1, 2, 3, 0: one TMEM lane quadrant each)
+constexpr int kLoadWarp = kCvWarps + 5;  // warp 21
+constexpr int kBWarp = kCvWarps + 6;     // warp 22
+constexpr int kTcThreads = (kCvWarps + 7) * 32;
 constexpr int kTcStages = 3;             // operand ring depth (A + B)
 constexpr int kAStage = 4 * 128 * 32;    // part0_hi | part0_lo | part1_hi | part1_lo, each 128 rows x 8 k (K-major, LBO 2048, SBO 128)
 
@@ -95,6 +103,7 @@ struct TcArgs {
     // MODE 2 (upsampled-DFT rows): Y = the full cross-power R [pair][x][y], Bmat = per-pair twiddle images
     float2* Tm;                          // [pair][u][y], u < rs
     int rs;
+    int half;                            // R holds the lines 0 .. n/2 only (lines_in = n/2 + 1)
 };
 
 #ifdef SB_TC_PROFILE
@@ -121,6 +130,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
     uint64_t* acc_full = bars + 4 + 2 * kTcStages;   // [2] tcgen05.commit -> epilogue
     uint64_t* acc_empty = acc_full + 2;         // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    int4* tile_info = reinterpret_cast<int4*>(smem + L.bar_off + 128);     // [2] MODE 0: (min, max, row misalignment) of a staged tile
     __shared__ double s_val[4], s_sec[4];       // MODE 1: block reduction of the epilogue warps
     __shared__ int s_idx[4];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -134,16 +144,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
     const int my_tiles = blockIdx.x < g.n_tiles ? (g.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int my_chunks = my_tiles * nchunks;
 
-    if (warp == 8) {
+    if (warp == kMmaWarp) {
         if (lane == 0) {
             for (int i = 0; i < 2; ++i) {
-                umma::mbar_init(stg_full + i, 1);         // the loader's expect_tx arrival (+ the copies' bytes)
-                umma::mbar_init(stg_empty + i, 8);        // 8 converter warps
+                umma::mbar_init(stg_full + i, 2);         // the loader's expect_tx arrival (+ the copies' bytes) and the tile record
+                umma::mbar_init(stg_empty + i, kCvWarps); // every converter warp
                 umma::mbar_init(acc_full + i, 1);
                 umma::mbar_init(acc_empty + i, 4);
             }
             for (int s = 0; s < kTcStages; ++s) {
-                umma::mbar_init(ab_full + s, 9);          // 8 converter warps + the bulk copy's expect_tx arrival
+                umma::mbar_init(ab_full + s, 9);          // the 8 warps of one converter group + the bulk copy's expect_tx arrival
                 umma::mbar_init(ab_empty + s, 1);         // tcgen05.commit
             }
             umma::mbar_init_fence();
@@ -151,13 +161,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
         __syncwarp();
         umma::tmem_alloc(tmem_slot, tmem_cols);
         umma::tmem_relinquish();
-        if (lane == 0)
-            for (int c = 0; c < kTcStages && c < my_chunks; ++c) {           // the first B stages need no free slot
-                const int t2 = blockIdx.x + (c / nchunks) * gridDim.x;       // MODE 2: the tables belong to the tile's pair
-                const size_t img = (MODE == 2 ? (size_t)(t2 / tiles) * nchunks : 0) + (size_t)(c % nchunks);
-                umma::mbar_expect_tx(ab_full + c, (uint32_t)L.b_stage);
-                umma::bulk_g2s(b_st + c * L.b_stage, g.Bmat + img * L.b_stage, (uint32_t)L.b_stage, ab_full + c);
-            }
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -168,41 +171,65 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
     const long long t_kernel0 = clock64();
 #endif
 
-    if (warp == 13) {
-        // =========================================================================== loader (MODE 0): one thread
-        if (MODE == 0 && lane == 0) {
+    if (warp == kLoadWarp) {
+        // =========================================================================== loader (MODE 0): one warp
+        // (issuing a bulk copy costs the issuing thread ~130 cycles: one thread issuing the 128 rows of a tile bounded the
+        // whole kernel at 17 k cycles per tile -- r2 cycle counters -- so the rows are spread over the 32 lanes)
+        if (MODE == 0) {
             for (int it = 0; it < my_tiles && ok; ++it) {
                 const int tile = blockIdx.x + it * gridDim.x;
                 const int mt = tile % tiles, img = (tile / tiles) & 1, p = tile / (2 * tiles);
                 const int y0 = mt << 7;
                 const int b = it % g.stg_bufs, u = it / g.stg_bufs;
-                { TC_T0(); if (u >= 1) ok = umma::mbar_wait(stg_empty + b, (u - 1) & 1); if (blockIdx.x == 0) TC_ACC(0); }
+                { TC_T0(); if (u >= 1) ok = umma::mbar_wait(stg_empty + b, (u - 1) & 1); if (blockIdx.x == 0 && lane == 0) TC_ACC(0); }
                 uint8_t* stg = smem + L.stg_off + b * g.stg_bytes;
                 const PairDesc pd = g.pairs[p];
                 const uint16_t* src = img ? pd.b : pd.a;
                 // rows start 16-byte aligned in shared memory; the copies start at the 16-byte boundary below the strip
                 // pixel (the same offset a0 for every row: the tile pitch is a multiple of 16 bytes)
+                const uint8_t* row0 = reinterpret_cast<const uint8_t*>(g.swap ? src + y0 : src + (size_t)y0 * g.tile_w);
+                const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(row0) & 15);
                 if (!g.swap) {
-                    const uint8_t* row0 = reinterpret_cast<const uint8_t*>(src + (size_t)y0 * g.tile_w);
-                    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(row0) & 15);
                     const uint32_t bytes = (a0 + 2u * (uint32_t)n + 15u) & ~15u;
-                    umma::mbar_expect_tx(stg_full + b, bytes * 128u);
-                    for (int r = 0; r < 128; ++r)
+                    if (lane == 0) umma::mbar_expect_tx(stg_full + b, bytes * 128u);
+                    for (int r = lane; r < 128; r += 32)
                         umma::bulk_g2s(stg + r * pitch_ns, row0 - a0 + (size_t)r * g.tile_w * 2, bytes, stg_full + b);
                 } else {
-                    const uint8_t* row0 = reinterpret_cast<const uint8_t*>(src + y0);
-                    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(row0) & 15);
                     const uint32_t bytes = (a0 + 256u + 15u) & ~15u;
-                    umma::mbar_expect_tx(stg_full + b, bytes * (uint32_t)n);
-                    for (int x = 0; x < n; ++x)
+                    if (lane == 0) umma::mbar_expect_tx(stg_full + b, bytes * (uint32_t)n);
+                    for (int x = lane; x < n; x += 32)
                         umma::bulk_g2s(stg + x * pitch_sw, row0 - a0 + (size_t)x * g.tile_w * 2, bytes, stg_full + b);
+                }
+                // the tile's record for the converters -- two DEPENDENT global loads (descriptor -> min/max table) that used
+                // to open every tile of every converter thread; here they ride on the loader, a tile ahead
+                if (lane == 1) {
+                    const int2 m = g.mm[img ? pd.b_tile : pd.a_tile];
+                    tile_info[b] = make_int4(m.x, m.y, (int)a0, 0);
+                    umma::mbar_arrive(stg_full + b);               // (release: the record is visible to whoever sees the phase)
                 }
             }
         }
-    } else if (warp < 8) {
+    } else if (warp == kBWarp) {
+        // =========================================================================== B stages (whole warp, one elected lane issues)
+        int s = 0;
+        uint32_t ph = 1;                                           // parity of the PREVIOUS use of the stage
+        int c = 0, it = 0;
+        for (int gc = 0; gc < my_chunks && ok; ++gc) {
+            { TC_T0(); if (gc >= kTcStages) ok = umma::mbar_wait(ab_empty + s, ph); if (blockIdx.x == 0 && lane == 0) TC_ACC(5); }
+            if (umma::elect_one()) {
+                const int t2 = blockIdx.x + it * gridDim.x;                      // MODE 2: the tables belong to the tile's pair
+                const size_t img = (MODE == 2 ? (size_t)(t2 / tiles) * nchunks : 0) + (size_t)c;
+                umma::mbar_expect_tx(ab_full + s, (uint32_t)L.b_stage);
+                umma::bulk_g2s(b_st + s * L.b_stage, g.Bmat + img * L.b_stage, (uint32_t)L.b_stage, ab_full + s);
+            }
+            __syncwarp();
+            if (++s == kTcStages) { s = 0; ph ^= 1u; }
+            if (++c == nchunks) { c = 0; ++it; }
+        }
+    } else if (warp < kCvWarps) {
         // =========================================================================== converters: thread = (row, 4 k)
-        const int row = 16 * warp + (lane >> 1), kg = lane & 1;
-        int gc = 0;                                                // chunks produced so far (ring position)
+        const int grp = warp >> 3;                                 // this group converts the chunks c = grp (mod 2)
+        const int row = 16 * (warp & 7) + (lane >> 1), kg = lane & 1;
         for (int it = 0; it < my_tiles && ok; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int mt = tile % tiles;
@@ -214,47 +241,96 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
             int sstep = 0;                                         // ... and the distance (uint16 elements) between its columns
             int mn = 0, mx = 0, seen = 0, smode = 0;
             unsigned sb_ = 1u;
-            float inv = 0.f;
+            float inv = 0.f, inv_lo = 0.f;
+            unsigned magic_b = 0u;
             const float2* yrow = nullptr;
-            constexpr int PF = 3;                                  // MODE 1: chunks of Y kept in flight per thread
+            const float2* yrow_m = nullptr;                        // MODE 2, half arrays: row -y of the same pair
+            // MODE 1 / 2 source element k of this thread's row.  MODE 2 on a HALF cross-power array (lines 0 .. n/2): the
+            // columns beyond n/2 are the conjugates of the mirrored column at row -y, R[y][n-kx] = conj(R[-y][kx])
+            auto ld_src = [&](int k) -> float2 {
+                if (k >= kdim) return make_float2(0.f, 0.f);
+                if (MODE == 2 && g.half && k >= nb) {
+                    const float2 v = yrow_m[(size_t)(n - k) * Sh];
+                    return make_float2(v.x, -v.y);
+                }
+                return yrow[(size_t)k * Sh];
+            };
+            constexpr int PF = 2;                                  // MODE 1 / 2: chunks (of this group) kept in flight per thread
             float2 nxt[PF][4];
             if (MODE == 0) {
-                const PairDesc pd = g.pairs[p];
-                const uint16_t* src = img ? pd.b : pd.a;
-                const int2 m = g.mm[img ? pd.b_tile : pd.a_tile];
-                mn = m.x;
-                mx = m.y;
+                { TC_T0(); ok = umma::mbar_wait(stg_full + b, u & 1); if (blockIdx.x == 0 && t == 0) TC_ACC(1); }
+                const int4 ti = tile_info[b];
+                mn = ti.x;
+                mx = ti.y;
                 inv = mx > mn ? (float)g.maxval / (float)(mx - mn) : 0.f;
                 sb_ = mx > mn ? (unsigned)(mx - mn) : 1u;
+                inv_lo = stretch_inv_lo(sb_, (unsigned)g.maxval);
+                magic_b = kStretchMagic * sb_;
                 smode = mx <= mn ? 0 : (sb_ == (unsigned)g.maxval ? 1 : 2);     // constant tile / full range (identity) / general
                 const uint8_t* stg = smem + L.stg_off + b * g.stg_bytes;
+                const uint32_t a0 = (uint32_t)ti.z;
                 if (!g.swap) {
-                    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(src + (size_t)y0 * g.tile_w) & 15);
                     sbase = reinterpret_cast<const uint16_t*>(stg + row * pitch_ns + a0);
                     sstep = 1;
                 } else {
-                    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(src + y0) & 15);
                     sbase = reinterpret_cast<const uint16_t*>(stg + a0) + row;
                     sstep = pitch_sw >> 1;
                 }
-                { TC_T0(); ok = umma::mbar_wait(stg_full + b, u & 1); if (blockIdx.x == 0 && t == 0) TC_ACC(1); }
             } else {
                 yrow = g.Y + (size_t)p * g.lines_in * Sh + y0 + row;
+                yrow_m = g.Y + (size_t)p * g.lines_in * Sh + ((Sh - (y0 + row)) & (Sh - 1));
 #pragma unroll
                 for (int d = 0; d < PF; ++d)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int k = 8 * d + 4 * kg + i;
-                        nxt[d][i] = k < kdim ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
-                    }
+                    for (int i = 0; i < 4; ++i) nxt[d][i] = ld_src(8 * (grp + 2 * d) + 4 * kg + i);
             }
-            for (int c = 0; c < nchunks && ok; ++c, ++gc) {
+            for (int c = grp; c < nchunks && ok; c += 2) {
+                const int gc = it * nchunks + c;                   // position of this chunk in the operand ring
                 const int s = gc % kTcStages, use = gc / kTcStages;
                 float ph[4], pl[4], qh[4], ql[4];
 #ifdef SB_TC_PROFILE
                 const long long t_conv0 = clock64();
 #endif
-                if (MODE == 0) {
+#ifdef SB_TC_EXP_NOCV                                                          // (timing experiment: no operand conversion)
+                if (true) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ph[i] = pl[i] = qh[i] = ql[i] = 0.f;
+                } else
+#endif
+                if (MODE == 0 && smode == 2 && c >= 1 && 8 * c + 7 <= no) {
+                    // interior chunk of a general tile (12 of the 14 chunks of a 214-wide strip): every j has both fold
+                    // partners, no guards; stretch on the 2^23 magic-number bit patterns (stretch_bits)
+                    unsigned ra[4], rb[4], ba[4], bb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int j = 8 * c + 4 * kg + i;
+                        ra[i] = sbase[j * sstep];
+                        rb[i] = sbase[(n - j) * sstep];
+                    }
+                    bool exact = false;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        ba[i] = stretch_bits(ra[i] - (unsigned)mn, sb_, inv_lo, (unsigned)g.maxval, magic_b, exact);
+                        bb[i] = stretch_bits(rb[i] - (unsigned)mn, sb_, inv_lo, (unsigned)g.maxval, magic_b, exact);
+                    }
+                    if (exact) {                                   // (rare) an exact quotient somewhere: the float64 expression decides
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            ba[i] = kStretchMagic + (unsigned)stretch_px(ra[i], mn, mx, inv, g.maxval);
+                            bb[i] = kStretchMagic + (unsigned)stretch_px(rb[i], mn, mx, inv, g.maxval);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const unsigned es = ba[i] + bb[i] - 2u * kStretchMagic;          // a + b       in [0, 2^17)
+                        const unsigned os = ba[i] - bb[i] + 0x400000u;                   // a - b + 2^22 in (0, 2^23)
+                        seen |= (int)es;
+                        const float e = __uint_as_float(kStretchMagic | es) - 8388608.0f;
+                        const float o = __uint_as_float(kStretchMagic | os) - 12582912.0f;
+                        umma::split_tf32(e, ph[i], pl[i]);
+                        umma::split_tf32(o, qh[i], ql[i]);
+                    }
+                } else if (MODE == 0) {
                     unsigned ra[4], rb[4];
                     bool va[4], vb[4];
 #pragma unroll
@@ -292,7 +368,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                     for (int i = 0; i < 4; ++i) {
                         const int a_ = va[i] ? xa[i] : 0, b_ = vb[i] ? xb[i] : 0;
                         seen |= a_ | b_;
-                        const float e = (float)(a_ + b_) * (float)kInScale, o = vb[i] ? (float)(a_ - b_) * (float)kInScale : 0.f;
+                        const float e = (float)(a_ + b_), o = vb[i] ? (float)(a_ - b_) : 0.f;      // (the 2^-16 input scaling is in the tables)
                         umma::split_tf32(e, ph[i], pl[i]);
                         umma::split_tf32(o, qh[i], ql[i]);
                     }
@@ -305,10 +381,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
 #pragma unroll
                         for (int i = 0; i < 4; ++i) nxt[d][i] = nxt[d + 1][i];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {                  // PF chunks ahead: global latency stays off the ring's critical path
-                        const int k = 8 * (c + PF) + 4 * kg + i;
-                        nxt[PF - 1][i] = k < kdim ? yrow[(size_t)k * Sh] : make_float2(0.f, 0.f);
-                    }
+                    for (int i = 0; i < 4; ++i)                    // PF chunks ahead: global latency stays off the ring's critical path
+                        nxt[PF - 1][i] = ld_src(8 * (c + 2 * PF) + 4 * kg + i);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         umma::split_tf32(cur[i].x, ph[i], pl[i]);
@@ -343,56 +417,57 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                 }
             }
         }
-    } else if (warp == 8) {
-        // =========================================================================== MMA issue + B stages (one thread)
-        if (lane == 0) {
-            const uint32_t idesc = umma::idesc_tf32(128, NP);
-            const uint32_t a0 = umma::smem_addr(a_st), b0 = umma::smem_addr(b_st);
-            const uint32_t bsub = (uint32_t)NP * 32, blbo = (uint32_t)NP * 16;
-            int gc = 0;
-            for (int it = 0; it < my_tiles && ok; ++it) {
-                const int acc = it % g.acc_bufs, ua = it / g.acc_bufs;
-                if (ua >= 1) {
-                    { TC_T0(); ok = umma::mbar_wait(acc_empty + acc, (ua - 1) & 1); if (blockIdx.x == 0) TC_ACC(3); }
-                    umma::fence_after_sync();
-                }
-                const uint32_t d0 = tb + (uint32_t)(acc * acc_cols);
-                for (int c = 0; c < nchunks && ok; ++c, ++gc) {
-                    const int s = gc % kTcStages, use = gc / kTcStages;
-                    { TC_T0(); ok = umma::mbar_wait(ab_full + s, use & 1); if (blockIdx.x == 0) TC_ACC(4); }
-                    umma::fence_after_sync();
-                    const uint32_t as = a0 + s * kAStage, bs = b0 + s * L.b_stage;
-                    const uint64_t eh = umma::desc_kmajor(as, 2048, 128), el = umma::desc_kmajor(as + 4096, 2048, 128);
-                    const uint64_t oh = umma::desc_kmajor(as + 8192, 2048, 128), ol = umma::desc_kmajor(as + 12288, 2048, 128);
-                    const uint64_t ch = umma::desc_kmajor(bs, blbo, 128), cl = umma::desc_kmajor(bs + bsub, blbo, 128);
-                    const uint64_t sh = umma::desc_kmajor(bs + 2 * bsub, blbo, 128), sl = umma::desc_kmajor(bs + 3 * bsub, blbo, 128);
+    } else if (warp == kMmaWarp) {
+        // =========================================================================== MMA issue
+        // The WHOLE warp runs the loop (uniform control flow, descriptors in uniform registers) and one elected lane
+        // issues: with the loop inside `if (lane == 0)` the compiler wrapped every tcgen05 instruction in an election
+        // loop and moved each descriptor through R2UR -- ~100 dependent instructions, ~900 cycles per K chunk, the floor
+        // of all three modes (r2 cycle counters; the MMAs themselves take 6 x 60 cycles).
+        const uint32_t idesc = umma::idesc_tf32(128, NP);
+        const uint32_t bsub16 = ((uint32_t)NP * 32) >> 4, blbo = (uint32_t)NP * 16;
+        // descriptors of stage 0; the 14-bit address field (16-byte units) advances by the stage size
+        const uint64_t dA0 = umma::desc_kmajor(umma::smem_addr(a_st), 2048, 128);
+        const uint64_t dB0 = umma::desc_kmajor(umma::smem_addr(b_st), blbo, 128);
+        const uint32_t a_step = kAStage >> 4, b_step = (uint32_t)L.b_stage >> 4;
+        int s = 0;
+        uint32_t ph = 0;                                           // stage and its phase parity in the operand ring
+        for (int it = 0; it < my_tiles && ok; ++it) {
+            const int acc = it % g.acc_bufs, ua = it / g.acc_bufs;
+            if (ua >= 1) {
+                { TC_T0(); ok = umma::mbar_wait(acc_empty + acc, (ua - 1) & 1); if (blockIdx.x == 0 && lane == 0) TC_ACC(3); }
+                umma::fence_after_sync();
+            }
+            const uint32_t d0 = tb + (uint32_t)(acc * acc_cols);
+            const uint32_t d1 = MODE == 2 ? d0 : d0 + NP;          // MODE 2: both parts feed one accumulator
+            for (int c = 0; c < nchunks && ok; ++c) {
+                { TC_T0(); ok = umma::mbar_wait(ab_full + s, ph); if (blockIdx.x == 0 && lane == 0) TC_ACC(4); }
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+                    const uint64_t eh = dA0 + (uint64_t)(s * a_step), ch = dB0 + (uint64_t)(s * b_step);
+                    const uint64_t el = eh + (4096 >> 4), oh = eh + (8192 >> 4), ol = eh + (12288 >> 4);
+                    const uint64_t cl = ch + bsub16, sh = ch + 2 * bsub16, sl = ch + 3 * bsub16;
                     const uint32_t accum = c > 0 ? 1u : 0u;
                     umma::mma_tf32(d0, eh, ch, idesc, accum);
+#ifndef SB_TC_EXP_MMA1                                                         // (timing experiment: one product per part)
                     umma::mma_tf32(d0, el, ch, idesc, 1);
                     umma::mma_tf32(d0, eh, cl, idesc, 1);
-                    const uint32_t d1 = MODE == 2 ? d0 : d0 + NP;              // MODE 2: both parts feed one accumulator
+#endif
                     umma::mma_tf32(d1, oh, sh, idesc, MODE == 2 ? 1u : accum);
+#ifndef SB_TC_EXP_MMA1
                     umma::mma_tf32(d1, ol, sh, idesc, 1);
                     umma::mma_tf32(d1, oh, sl, idesc, 1);
+#endif
                     umma::mma_commit(ab_empty + s);
-                    // refill the B stage used ONE chunk ago (its MMAs have had a whole chunk to finish)
-                    const int g2 = gc - 1 + kTcStages;
-                    if (gc >= 1 && g2 < my_chunks) {
-                        const int sp = (gc - 1) % kTcStages, up = (gc - 1) / kTcStages;
-                        { TC_T0(); ok = ok && umma::mbar_wait(ab_empty + sp, up & 1); if (blockIdx.x == 0) TC_ACC(5); }
-                        const int t2 = blockIdx.x + (g2 / nchunks) * gridDim.x;
-                        const size_t img = (MODE == 2 ? (size_t)(t2 / tiles) * nchunks : 0) + (size_t)(g2 % nchunks);
-                        umma::mbar_expect_tx(ab_full + sp, (uint32_t)L.b_stage);
-                        umma::bulk_g2s(b_st + sp * L.b_stage, g.Bmat + img * L.b_stage, (uint32_t)L.b_stage, ab_full + sp);
-                    }
+                    if (c == nchunks - 1) umma::mma_commit(acc_full + acc);
                 }
-                umma::mma_commit(acc_full + acc);
+                __syncwarp();
+                if (++s == kTcStages) { s = 0; ph ^= 1u; }
             }
         }
     } else {
         // =========================================================================== epilogue: one row per thread
         const int q = warp & 3;                                    // TMEM lane quadrant this warp may read
-        const int ew = warp - 9;
+        const int ew = warp - kEpiWarp0;
         for (int it = 0; it < my_tiles && ok; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int mt = tile % tiles;
@@ -400,23 +475,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
             const int p = MODE == 0 ? tile / (2 * tiles) : tile / tiles;
             const int y0 = mt << 7;
             const int acc = it % g.acc_bufs, ua = it / g.acc_bufs;
-            { TC_T0(); ok = umma::mbar_wait(acc_full + acc, ua & 1); if (blockIdx.x == 0 && warp == 9 && lane == 0) TC_ACC(6); }
+            { TC_T0(); ok = umma::mbar_wait(acc_full + acc, ua & 1); if (blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0) TC_ACC(6); }
             umma::fence_after_sync();
             const uint32_t trow = tb + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * acc_cols);
             const int y = y0 + 32 * q + lane;
+#ifdef SB_TC_EXP_NOEPI                                                         // (timing experiment: no read-back)
+            if (false) {
+#else
             if (MODE == 0) {
+#endif
                 if (ok) {
                     float2* zp = g.Zh + ((size_t)(p * 2 + img) * nb) * Sh + y;
-                    for (int k0 = 0; k0 < NP; k0 += 8) {
-                        uint32_t re[8], im[8];
-                        umma::tmem_ld8(trow + k0, re);
-                        umma::tmem_ld8(trow + NP + k0, im);
+                    for (int k0 = 0; k0 < NP; k0 += 16) {            // (NP is a multiple of 16)
+                        uint32_t re[16], im[16];
+                        umma::tmem_ld16(trow + k0, re);
+                        umma::tmem_ld16(trow + NP + k0, im);
                         umma::tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
+                        for (int i = 0; i < 16; ++i)
                             if (k0 + i < nb) zp[(size_t)(k0 + i) * Sh] = make_float2(__uint_as_float(re[i]), __uint_as_float(im[i]));
                     }
                 }
+#ifdef SB_TC_EXP_NOEPI
+            } else if (true) {
+#endif
             } else if (MODE == 2) {
                 if (ok) {
                     float2* tp = g.Tm + (size_t)p * g.rs * Sh + y;
@@ -433,32 +515,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
             } else {
                 // |cc| of this thread's row: first maximum (ties -> lowest index in the C order of the ORIGINAL strip),
                 // second-largest value, row maximum -- what rows_inv_argmax_kernel of the radix path emits
-                float bv = -1.f, b2 = -1.f, rm = 0.f;
-                int bi = 0x7fffffff;
+                // Branch-free, two independent chains (the data-dependent branches of a running top-2 cost ~30 k cycles per
+                // tile and made this epilogue the bound of the whole kernel -- r2 cycle counters): the pixels x = 0 .. n/2 come
+                // from P + Q in ascending order (a strict > keeps the first of equal maxima), the pixels n - x from P - Q in
+                // DESCENDING order (>= keeps the lowest); every pixel of the first chain precedes every pixel of the second.
+                // s = max(s, min(m, v)) before m = max(m, v) keeps the second-largest value of the multiset.
+                float mA = -1.f, sA = -1.f, mB = -1.f, sB = -1.f;
+                int xA = 0, xB = 0;
                 if (ok) {
-                    for (int x0 = 0; x0 < NP; x0 += 8) {
-                        uint32_t pr[8], qr[8];
-                        umma::tmem_ld8(trow + x0, pr);
-                        umma::tmem_ld8(trow + NP + x0, qr);
+                    for (int x0 = 0; x0 < NP; x0 += 16) {
+                        uint32_t pr[16], qr[16];
+                        umma::tmem_ld16(trow + x0, pr);
+                        umma::tmem_ld16(trow + NP + x0, qr);
                         umma::tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
+                        for (int i = 0; i < 16; ++i) {
                             const int x = x0 + i;
                             const float P = __uint_as_float(pr[i]), Q = __uint_as_float(qr[i]);
-                            if (x <= nh) {
-                                const float v = fabsf(P + Q);
-                                top2_update<float>(bv, bi, b2, v, g.swap ? x * Sh + y : y * n + x);
-                                rm = fmaxf(rm, v);
-                            }
-                            if (x >= 1 && x <= no) {
-                                const float v = fabsf(P - Q);
-                                const int xm = n - x;
-                                top2_update<float>(bv, bi, b2, v, g.swap ? xm * Sh + y : y * n + xm);
-                                rm = fmaxf(rm, v);
-                            }
+                            const float va = x <= nh ? fabsf(P + Q) : -2.f;
+                            const float vb = (x >= 1 && x <= no) ? fabsf(P - Q) : -2.f;
+                            sA = fmaxf(sA, fminf(mA, va));
+                            xA = va > mA ? x : xA;
+                            mA = fmaxf(mA, va);
+                            sB = fmaxf(sB, fminf(mB, vb));
+                            xB = vb >= mB ? x : xB;
+                            mB = fmaxf(mB, vb);
                         }
                     }
                 }
+                const bool takeB = mB > mA;                            // equal maxima: the first chain holds the lower pixel
+                float bv = takeB ? mB : mA;
+                float b2 = fmaxf(fmaxf(sA, sB), fminf(mA, mB));
+                const int xw = takeB ? n - xB : xA;
+                int bi = ok ? (g.swap ? xw * Sh + y : y * n + xw) : 0x7fffffff;
+                const float rm = fmaxf(bv, 0.f);
                 const double sc = 1.0 / ((double)Sh * (double)n);
                 g.rowmax[(size_t)p * Sh + y] = (float)((double)rm * sc);
 #pragma unroll
@@ -496,7 +586,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
         atomicAdd((unsigned long long*)&g_tc_prof[MODE][9], 1ull);
     }
 #endif
-    if (warp == 8) umma::tmem_dealloc(tb, tmem_cols);
+    if (warp == kMmaWarp) umma::tmem_dealloc(tb, tmem_cols);
 }
 
 // Twiddles of skimage's _upsampled_dft for the tensor-core rows stage (MODE 2) and the column stage:
@@ -589,7 +679,9 @@ __global__ void __launch_bounds__(128) cols_warp_kernel(int n_cols, int nb, int 
         wfft::fft1024<false>(x, sm.buf, tw, lane);
         // R = A conj(B) / max(|A conj(B)|, 100 eps): slot s holds ky = lane + 32 brev5(s) in both transforms
         float2* rl = Rout + ((size_t)p * lines_out + kx) * N;
-        const bool mir = mirror && kx >= 1 && kx <= (n - 1) / 2;
+        const bool inner = kx >= 1 && kx <= (n - 1) / 2;
+        const bool mir = (mirror & 1) && inner;                                      // R: read by the upsampled-DFT stage
+        const bool mir_y = (mirror & 2) && inner;                                    // Y: only the radix inverse reads the mirrored lines
         float2* rm = Rout + ((size_t)p * lines_out + (n - kx)) * N;
 #pragma unroll
         for (int s = 0; s < 32; ++s) {
@@ -615,7 +707,7 @@ __global__ void __launch_bounds__(128) cols_warp_kernel(int n_cols, int nb, int 
         for (int s = 0; s < 32; ++s) {
             const int yy = lane + 32 * wfft::brev5(s);
             yl[yy] = y[s];
-            if (mir) ym[yy] = make_float2(y[s].x, -y[s].y);
+            if (mir_y) ym[yy] = make_float2(y[s].x, -y[s].y);
         }
     }
 }
@@ -715,6 +807,72 @@ __global__ void __launch_bounds__(128) selftest_umma_check_kernel(const float* _
     if (!(err <= tol)) atomicAdd(res + 1, 1ull);
 }
 
+// Issue-rate probe (tuning hook, timing only -- the operands are zeros): `rounds` x 6 tcgen05.mma in the product's pattern
+// (two accumulators, A / B sub-tiles of a K chunk of 8) from one thread, one commit at the end; cycles from the first issue
+// to the arrival.  layout 0 = the product's K-major no-swizzle form (LBO = rows * 16, SBO = 128), 1 = the same with the
+// 128-byte-swizzle bit set in the descriptors (row pitch 128 B, SBO = 1024).
+__global__ void __launch_bounds__(128) umma_rate_kernel(int N, int layout, int rounds, int per_round, int commit_mode,
+                                                        unsigned long long* __restrict__ res) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar, dummy;
+    __shared__ uint32_t tmem_base;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int i = t; i < (64 + 64) * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (t == 0) {
+        umma::mbar_init(&bar, 1);
+        umma::mbar_init(&dummy, 1u << 20);                 // commit_mode 1: a commit per round lands here (never completes)
+        umma::mbar_init_fence();
+    }
+    if (warp == 0) {
+        umma::tmem_alloc(&tmem_base, 512);
+        umma::tmem_relinquish();
+    }
+    umma::fence_smem_to_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tb = tmem_base;
+    if (t == 0) {
+        const uint32_t idesc = umma::idesc_tf32(128, N);
+        const uint32_t a0 = umma::smem_addr(smem), b0 = a0 + 64 * 1024;
+        uint64_t ad[4], bd[4];
+        for (int i = 0; i < 4; ++i) {
+            if (layout == 0) {
+                ad[i] = umma::desc_kmajor(a0 + i * 4096, 2048, 128);
+                bd[i] = umma::desc_kmajor(b0 + i * N * 32, N * 16, 128);
+            } else {
+                ad[i] = umma::desc_kmajor(a0 + i * 16384, 16, 1024) | (2ull << 61);
+                bd[i] = umma::desc_kmajor(b0 + i * 16384, 16, 1024) | (2ull << 61);
+            }
+        }
+        const long long t0 = clock64();
+        for (int r = 0; r < rounds; ++r) {
+            umma::mma_tf32(tb, ad[0], bd[0], idesc, 1);
+            if (per_round >= 6) {
+                umma::mma_tf32(tb, ad[1], bd[0], idesc, 1);
+                umma::mma_tf32(tb, ad[0], bd[1], idesc, 1);
+            }
+            umma::mma_tf32(tb + N, ad[2], bd[2], idesc, 1);
+            if (per_round >= 6) {
+                umma::mma_tf32(tb + N, ad[3], bd[2], idesc, 1);
+                umma::mma_tf32(tb + N, ad[2], bd[3], idesc, 1);
+            }
+            if (commit_mode == 1) umma::mma_commit(&dummy);
+        }
+        const long long t1 = clock64();
+        umma::mma_commit(&bar);
+        const bool ok = umma::mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        res[0] = (unsigned long long)rounds * (per_round >= 6 ? 6 : 2);
+        res[1] = (unsigned long long)(t2 - t0);
+        res[2] = (unsigned long long)(t1 - t0);
+        res[3] = ok ? 0ull : 0xDEADull;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tb, 512);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ host side
@@ -760,7 +918,7 @@ int sb_tc_plan(sb_ctx* ctx, int Sh, int n, TcPlan* plan) {
     if (L.total > 226 * 1024) return SB_OK;
     const int nb = plan->nb, NP = plan->NP, nh = n / 2, no = (n - 1) / 2;
     // forward tables: per chunk [cos_hi | cos_lo | -sin_hi | -sin_lo], each NP rows (output bin k) x 8 (input j), K-major
-    const uint64_t key = ((uint64_t)2 << 40) | (uint64_t)n;
+    const uint64_t key = ((uint64_t)2 << 40) | (uint64_t)n;                 // (forward tables, scaled by 2^-16)
     auto it = ctx->twiddle_cache.find(key);
     if (it == ctx->twiddle_cache.end()) {
         std::vector<float> img((size_t)plan->nchunks * 4 * NP * 8, 0.0f);
@@ -770,8 +928,10 @@ int sb_tc_plan(sb_ctx* ctx, int Sh, int n, TcPlan* plan) {
                 for (int jj = 0; jj < 8; ++jj) {
                     const int j = 8 * c + jj;
                     const long double ang = tau * (long double)(((long long)j * k) % n) / (long double)n;
-                    const float cv = j <= nh ? (float)cosl(ang) : 0.0f;
-                    const float sv = (j >= 1 && j <= no) ? (float)(-sinl(ang)) : 0.0f;
+                    // x 2^-16 (exact): the input scaling of the chain (kInScale), folded into the table so that the converters
+                    // feed the stretched integers as they are
+                    const float cv = j <= nh ? (float)cosl(ang) * (float)kInScale : 0.0f;
+                    const float sv = (j >= 1 && j <= no) ? (float)(-sinl(ang)) * (float)kInScale : 0.0f;
                     float ch, cl, sh, sl;
                     split_tf32_host(cv, ch, cl);
                     split_tf32_host(sv, sh, sl);
@@ -892,7 +1052,7 @@ size_t sb_tc_updft_table_bytes(const TcPlan& plan, int n_pairs) {
 // First stage of the upsampled-DFT refinement on the tensor cores: tables (B operand images + Ey) from the coarse
 // peaks, then T[pair][u][y] = sum_x conj(R[y][x]) Ex[u][x].  rs <= 16 (upsample factors up to 10).
 int sb_tc_updft_rows(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs, const void* d_peaks, int uf, int rs,
-                     int dftshift, const void* R, void* Bimg, void* Ey, void* Tm, int* d_fault) {
+                     int dftshift, const void* R, int lines_in, void* Bimg, void* Ey, void* Tm, int* d_fault) {
     const int nch = (plan.n + 7) / 8;
     updft_tables_tc_kernel<<<dim3(8, n_pairs), 256, 0, st>>>(static_cast<const PeakOut*>(d_peaks), plan.Sh, plan.n, uf, rs, dftshift, nch,
                                                              static_cast<float*>(Bimg), static_cast<float2*>(Ey));
@@ -905,7 +1065,7 @@ int sb_tc_updft_rows(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pai
     TcArgs g = {};
     g.Sh = plan.Sh; g.n = plan.n; g.NP = 32; g.nchunks = nch; g.swap = 0; g.stg_bytes = 0;
     g.Bmat = static_cast<const uint8_t*>(Bimg); g.fault = d_fault;
-    g.Y = static_cast<const float2*>(R); g.lines_in = plan.n;
+    g.Y = static_cast<const float2*>(R); g.lines_in = lines_in; g.half = lines_in < plan.n ? 1 : 0;
     g.Tm = static_cast<float2*>(Tm); g.rs = rs;
     g.n_tiles = n_pairs * (plan.Sh >> 7); g.stg_bufs = 0; g.acc_bufs = 2;
     const int grid = std::min(g.n_tiles, ctx->sm_count);
@@ -936,8 +1096,21 @@ int sb_tc_columns(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs,
 // out[3] = 0xDEAD if the MMA pipeline never signalled completion (bounded wait).
 int sb_selftest_umma_impl(sb_ctx* ctx, int variant, uint64_t* out) {
     constexpr int N = 112, K = 56;
-    SB_CHECK(ctx, variant >= 0 && variant <= 2, "selftest: unknown tensor-core variant %d", variant);
     Lane* lane = sb_lane(ctx, 0);
+    if (variant >= 1000) {          // issue-rate probe: 1000 + N + 1000 * layout + 10000 * (1 = two MMAs per round instead of six)
+        const int v = variant - 1000, n_ = v % 1000, layout = (v / 1000) % 10, two = (v / 10000) % 10, cm = (v / 100000) % 10;
+        SB_CHECK(ctx, n_ >= 8 && n_ <= 248 && n_ % 8 == 0 && layout <= 1, "selftest: bad rate-probe request %d", variant);
+        int rc = sb_reserve(ctx, lane->work, 64);
+        if (rc) return rc;
+        SB_CUDA(ctx, cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        umma_rate_kernel<<<1, 128, 128 * 1024, lane->stream>>>(n_, layout, 256, two ? 2 : 6, cm, (unsigned long long*)lane->work.p);
+        ctx->launches++;
+        SB_CUDA(ctx, cudaGetLastError());
+        SB_CUDA(ctx, cudaMemcpyAsync(out, lane->work.p, 32, cudaMemcpyDeviceToHost, lane->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(lane->stream));
+        return SB_OK;
+    }
+    SB_CHECK(ctx, variant >= 0 && variant <= 2, "selftest: unknown tensor-core variant %d", variant);
     int rc = sb_reserve(ctx, lane->work, 64 + (size_t)128 * N * 4);
     if (rc) return rc;
     unsigned long long* res = (unsigned long long*)lane->work.p;

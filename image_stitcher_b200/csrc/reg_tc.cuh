@@ -39,8 +39,9 @@ int sb_tc_inverse(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs,
 size_t sb_tc_zh_bytes(const TcPlan& plan, int n_pairs);
 // Upsampled-DFT refinement, first stage, on the tensor cores (rs <= 16): twiddle tables from the coarse peaks (B operand
 // images into `Bimg`, sb_tc_updft_table_bytes() bytes; Ey[pair][v][y]) and T[pair][u][y] = sum_x conj(R[y][x]) Ex[u][x].
+// R holds `lines_in` lines per pair: all n, or the half array of n/2 + 1 (the rest follows from R[y][n-kx] = conj(R[-y][kx])).
 size_t sb_tc_updft_table_bytes(const TcPlan& plan, int n_pairs);
 int sb_tc_updft_rows(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs, const void* d_peaks, int uf, int rs,
-                     int dftshift, const void* R, void* Bimg, void* Ey, void* Tm, int* d_fault);
+                     int dftshift, const void* R, int lines_in, void* Bimg, void* Ey, void* Tm, int* d_fault);
 
 int sb_tc_profile_read(long long* out48);   // cycle counters of a -DSB_TC_PROFILE build (0 = not such a build)

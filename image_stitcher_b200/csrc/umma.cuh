@@ -51,6 +51,19 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // generic-proxy shared-memory writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of a CONVERGED warp (elect.sync): the single-thread tcgen05 / bulk-copy issue without leaving uniform control flow
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- MMA issue (ONE thread): D[tmem] (+)= A[smem desc] . B[smem desc]
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -108,13 +121,31 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// returns false after ~2^31 cycles (about a second) without completion
+// try_wait with a suspend-time hint: the thread may sleep up to `ns` and wakes when the phase completes
+__device__ __forceinline__ bool mbar_try_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+// returns false after ~2^31 cycles (about a second) without completion.  The waiting threads SLEEP in try_wait (time hint)
+// instead of polling: with plain try_wait + a clock read per iteration the spin loops of the loader / MMA / epilogue /
+// converter warps issued 27 % of all instructions of the forward kernel (r2 ncu source counters) -- issue slots taken
+// from the converter warps that bound it.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return true;
     const long long t0 = clock64();
-    while (!mbar_try(bar, parity))
-        if (clock64() - t0 > (1ll << 31)) return false;
-    return true;
+    for (uint32_t i = 1;; ++i) {
+        if (mbar_try_hint(bar, parity, 100000u)) return true;
+        if ((i & 15u) == 0u && clock64() - t0 > (1ll << 31)) return false;
+    }
 }
 // 1-D bulk copy global -> shared with completion on an mbarrier (both addresses and the size multiples of 16 bytes)
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

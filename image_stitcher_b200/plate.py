@@ -166,6 +166,34 @@ class FuseBatchPlan:
             self.ctx._check(rc, "sb_fuse_regions")
 
 
+class RegisterPlan:
+    """A prebuilt ``sb_register_job`` (ctypes) for a fixed pair list, reusable every step: ``run()`` is the bare
+    ``sb_register_pairs`` call (building 1152 ``sb_pair`` structs and as many result dicts in Python costs milliseconds
+    per call -- more than some of the kernels); ``results()`` converts the last run's records on demand."""
+
+    def __init__(self, ctx: _ffi.Context, pairs, tile_shape, max_overlap_x, max_overlap_y, *, mem, upsample_factor=10,
+                 precision=_ffi.SB_PREC_AUTO, lane=0, dtype=None):
+        self.ctx, self.lane = ctx, int(lane)
+        self.arr, self.res, self.job = ctx._register_job(list(pairs), tile_shape, max_overlap_x, max_overlap_y, mem,
+                                                         upsample_factor, precision, lane, dtype)
+
+    def run(self):
+        rc = self.ctx.lib.sb_register_pairs(self.ctx.handle, C.byref(self.job), self.res)
+        if rc != 0:
+            self.ctx._check(rc, "sb_register_pairs")
+        return self
+
+    def run_async(self):
+        """``sb_register_pairs_async``: the records are valid after ``ctx.sync(lane)``."""
+        rc = self.ctx.lib.sb_register_pairs_async(self.ctx.handle, C.byref(self.job), self.res)
+        if rc != 0:
+            self.ctx._check(rc, "sb_register_pairs_async")
+        return self
+
+    def results(self):
+        return _ffi.Context._pair_dicts(self.res)
+
+
 def well_fuse_tiles(spec: PlateSpec, tile_ptr, lattice: Optional[geo.Lattice] = None):
     """sb_tile tuples of one well in the reference's paste order.
 

@@ -242,13 +242,16 @@ int sb_pyramid(sb_ctx* ctx, const void* src, int src_mem, int32_t n_planes, int3
 
 /* ------------------------------------------------------------------ test hook
  * Exhaustive on-device proofs of the two primitives whose exactness the parity claims rest on (tests/test_exhaustive_gpu.py):
- *   SB_SELFTEST_STRETCH, arg = 255 | 65535: the integer form of normalize_image (:844-855) fused into the strip load
- *       equals the float64 expression for every (v - min, max - min) pair of that pixel range;
+ *   SB_SELFTEST_STRETCH, arg = 255 | 65535: the integer forms of normalize_image (:844-855) fused into the strip loads
+ *       (radix kernels and tensor-core converters, each with its hand-over of exact quotients to the float64 sequence)
+ *       equal the float64 expression for every (v - min, max - min) pair of that pixel range; out[3] = how many pairs
+ *       took the exact-quotient hand-over;
  *   SB_SELFTEST_DIVIDE, arg = e in [-5, 19]: the packed float32 divide + truncation / rounding of the paste kernels
  *       equals IEEE a / b and trunc(clip(.)) (:838-841) for every uint16 a and every float32 b in [2^e, 2^(e+1)).
  *   SB_SELFTEST_UMMA, arg = 0: a 128 x 112 x 56 product through the tcgen05 building blocks of the registration
  *       kernels (shared-memory descriptors, 3-term tf32 split, TMEM read-back) against a float64 product on the device;
  *       out[2] = largest |error| * 1e12, out[3] = 0xDEAD if the tensor pipeline never signalled completion.
+ *       (arg >= 1000: tcgen05.mma issue-rate probe, a tuning hook -- scratch/umma_rate.py.)
  * out[0] = cases checked, out[1] = mismatches, out[2] = smallest mismatching case key (or ~0).  out holds 4 values. */
 enum { SB_SELFTEST_STRETCH = 0, SB_SELFTEST_DIVIDE = 1, SB_SELFTEST_UMMA = 2 };
 int sb_selftest(sb_ctx* ctx, int which, int64_t arg, uint64_t* out);

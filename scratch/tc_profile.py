@@ -14,7 +14,7 @@ import torch
 from image_stitcher_b200 import _ffi
 from image_stitcher_b200.plate import PlateSpec, make_plate, well_pairs
 
-spec = PlateSpec(wells=18, rows=3, cols=3, tile_h=2048, tile_w=2048, channels=1, reg_channel=0, jitter=3, seed=1)
+spec = PlateSpec(wells=int(os.environ.get('TCP_WELLS', '18')), rows=3, cols=3, tile_h=2048, tile_w=2048, channels=1, reg_channel=0, jitter=3, seed=1)
 plate = make_plate(spec, device="cuda:0", with_flat=False)
 ctx = _ffi.Context(0)
 pairs = []
@@ -24,7 +24,7 @@ ovx, ovy = spec.strip_overlaps()
 torch.cuda.synchronize()
 names = ["ld_wait_stg_empty", "cv_wait_stg_full", "cv_wait_ab_empty", "mma_wait_acc_empty", "mma_wait_ab_full", "mma_wait_ab_empty_prev",
          "ep_wait_acc_full", "kernel", "tiles", "launches", "cv_compute", "cv_fence_arrive"]
-for rep in range(3):
+for rep in range(2):
     ctx.register_pairs(pairs, (2048, 2048), ovx, ovy, mem=_ffi.SB_MEM_DEVICE, precision=0)
     buf = (C.c_longlong * 48)()
     n = ctx.lib.sb_debug_tc_profile(ctx.handle, buf)

@@ -20,9 +20,12 @@ def ctx():
 
 @pytest.mark.parametrize("maxval", [255, 65535])
 def test_integer_stretch_equals_float64_for_every_pixel_and_range(ctx, maxval):
-    checked, bad, first, _ = ctx.selftest(0, maxval)
+    """Every form the kernels run: ``stretch_px`` (radix path), ``stretch_bits`` and ``stretch_core`` (tensor-core converters,
+    interior / edge chunks) -- each with its hand-over of exact quotients to the float64 sequence."""
+    checked, bad, first, fallbacks = ctx.selftest(0, maxval)
     assert checked == maxval * (maxval + 3) // 2              # 2 147 581 950 pairs for uint16
     assert bad == 0, f"{bad} mismatches, first at b={first >> 32}, a={first & 0xffffffff}"
+    assert 0 < fallbacks < checked // 10                      # exact quotients exist and are rare (4.5 % of the 8-bit pairs, far fewer of the 16-bit ones)"
 
 
 @pytest.mark.parametrize("expo", [-5, -1, 0, 19])

@@ -96,8 +96,11 @@ def test_errors(ctx):
 
 
 def test_stitcher_process_writes_gpu_made_levels(tmp_path, monkeypatch):
-    """``run()`` hands the GPU-made levels to the OME-Zarr writer; every stored level equals the slicing of level 0."""
+    """``run()`` on the plain path (row-major canvas; SB_NO_FAST_IO=1 -- the chunk-ordered fast path is covered by
+    test_run_fast_path_equals_the_plain_path_level_by_level) hands the GPU-made levels to the OME-Zarr writer; every
+    stored level equals the slicing of level 0."""
     from image_stitcher_b200 import geometry as geo
+    monkeypatch.setenv("SB_NO_FAST_IO", "1")
     from image_stitcher_b200.stitcher_process import StitcherProcess
     g, st, tiles, kw = load_golden("reg_2x2_mono")
     root = str(tmp_path / "acq")

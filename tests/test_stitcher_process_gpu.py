@@ -396,3 +396,50 @@ def test_tiles_of_another_shape_are_refused_before_the_c_abi(tmp_path):
             s.ctx.fuse_region([(a[::2], 0, 0, 0, 0, 0, 0, 0, 0)], a.shape, (1, 1, 64, 64), out=np.zeros((1, 1, 1, 64, 64), np.uint16))
     finally:
         s.cleanup()
+
+
+def test_run_fast_path_equals_the_plain_path_level_by_level(tmp_path, monkeypatch):
+    """``run()`` on uint16 / paste / OME-Zarr jobs takes the pinned, chunk-ordered fast path (RegionPipeline): level 0
+    arrives in zarr-chunk order from the GPU, levels 1.. from ``sb_pyramid`` on the resident canvas.  Every level of every
+    region equals what the plain path (row-major canvas, host re-tiling; SB_NO_FAST_IO=1) writes, and level 0 equals the
+    oracle; the multiscales / omero name follows the reference (f"{region}_t{timepoint}", :1086)."""
+    import json
+    import shutil
+    from oracle import stitch_ref as sr
+    root = str(tmp_path / "acq")
+    regions = {}
+    for k, name in enumerate(["A1", "A2", "A3", "A4"]):                    # more regions than lanes: buffers get reused
+        st, tiles, _ = synth.make_region(rows=2, cols=3, tile_h=640, tile_w=768, seed=200 + k, jitter=0, region=name,
+                                         channels=("Fluorescence 405 nm Ex", "Fluorescence 488 nm Ex"), apply_flatfield=True)
+        regions[name] = (st, tiles)
+    synth.write_squid_layout(root, {n: t for n, (_, t) in regions.items()}, timepoint=0)
+    st0 = regions["A1"][0]
+
+    def run_once(out_name, fast):
+        if fast:
+            monkeypatch.delenv("SB_NO_FAST_IO", raising=False)
+        else:
+            monkeypatch.setenv("SB_NO_FAST_IO", "1")
+        s = _make(root, st0)
+        s.set_flatfields(st0.flatfields)
+        s.chunks = (1, 1, 1, 512, 512)                                     # several chunks per plane, ragged edges
+        s.run()
+        used = s.fast_io_used
+        dst = str(tmp_path / out_name)
+        shutil.move(s.output_folder, dst)
+        return dst, used, s.num_pyramid_levels
+
+    fast_dir, used_fast, n_levels = run_once("fast", True)
+    plain_dir, used_plain, _ = run_once("plain", False)
+    assert used_fast and not used_plain and n_levels >= 2
+    for name, (st, tiles) in regions.items():
+        pf = os.path.join(fast_dir, "0_stitched", f"{name}_stitched.ome.zarr")
+        pp = os.path.join(plain_dir, "0_stitched", f"{name}_stitched.ome.zarr")
+        exp = sr.stitch_region(st, tiles)
+        for level in range(n_levels):
+            a, b = ozw.read_ome_zarr_level(pf, level), ozw.read_ome_zarr_level(pp, level)
+            assert a.shape == b.shape and np.array_equal(a, b), (name, level)
+            if level == 0:
+                assert np.array_equal(a, exp)
+        za, zb = json.load(open(os.path.join(pf, ".zattrs"))), json.load(open(os.path.join(pp, ".zattrs")))
+        assert za == zb and za["multiscales"][0]["name"] == f"{name}_t0" == za["omero"]["name"]
