@@ -56,7 +56,10 @@ constexpr int kEpiWarp0 = kCvWarps + 1;  // warps 17-20 (warp % 4 = 1, 2, 3, 0: 
 constexpr int kLoadWarp = kCvWarps + 5;  // warp 21
 constexpr int kBWarp = kCvWarps + 6;     // warp 22
 constexpr int kTcThreads = (kCvWarps + 7) * 32;
+constexpr int kTcSh = 1024;              // the long strip axis these kernels are built for (sb_tc_plan admits no other)
 constexpr int kTcStages = 3;             // operand ring depth (A + B)
+constexpr int kCvDepth = 6;              // MODE 1 / 2: chunks each converter warp keeps in flight (cp.async into its own ring)
+constexpr int kCvRingBytes = kCvDepth * kCvWarps * 8 * 144;      // 108 KB: per warp and chunk 8 lines x (16 rows x 8 B + 16)
 constexpr int kAStage = 4 * 128 * 32;    // part0_hi | part0_lo | part1_hi | part1_lo, each 128 rows x 8 k (K-major, LBO 2048, SBO 128)
 
 struct TcSmem {                          // offsets into dynamic shared memory
@@ -118,8 +121,9 @@ __device__ long long g_tc_prof[3][16];      // per mode: cycles block 0 spent pe
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int Sh = g.Sh, n = g.n, NP = g.NP, nchunks = g.nchunks;
-    const TcSmem L = tc_smem_layout(NP, g.stg_bytes, MODE == 0 ? g.stg_bufs : 0);
+    constexpr int Sh = kTcSh;                   // (compile-time: every row / tile index below is a shift or a mask)
+    const int n = g.n, NP = g.NP, nchunks = g.nchunks;
+    const TcSmem L = tc_smem_layout(NP, g.stg_bytes, g.stg_bufs);      // (MODE 1 / 2: one "staged tile" = the converters' prefetch ring)
     uint8_t* a_st = smem + L.a_off;
     uint8_t* b_st = smem + L.b_off;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
@@ -230,6 +234,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
         // =========================================================================== converters: thread = (row, 4 k)
         const int grp = warp >> 3;                                 // this group converts the chunks c = grp (mod 2)
         const int row = 16 * (warp & 7) + (lane >> 1), kg = lane & 1;
+        // MODE 1 / 2: the source elements of a warp -- its 16 rows of the 8 lines of a chunk, Y or R stored [line][y] -- are
+        // fetched kCvDepth chunks ahead by cp.async into a ring only this warp reads back (wait_group + __syncwarp, no
+        // block barrier): 16-byte copies that BYPASS L1 (two adjacent rows of one line each; lane = line + 8 * row pair).
+        // History (r2): held in registers, 2 chunks ahead, the loads bounded the upsampled-DFT stage (63 % of its stall
+        // samples on the long scoreboard); 8-byte cp.async.ca did not help either -- with 220 KB of the SM's 256 KB carved
+        // out as shared memory the L1 holds only ~28 KB of lines in flight, both forms ran at 7.5 B / cycle / SM.
+        // Mirrored lines (MODE 2 on a HALF array, k > n/2: R[y][n-kx] = conj(R[-y][kx])) run backwards in memory, so their
+        // row pairs are not 16-byte aligned: those stay 8-byte copies of each thread's own elements.
+        constexpr int kLinePitch = 144;                            // bytes: 16 rows x 8 + 16 (bank spread for the read-back)
+        constexpr int kWarpRing = 8 * kLinePitch;                  // one chunk of one warp
+        uint8_t* ring = smem + L.stg_off + (size_t)warp * (kCvDepth * kWarpRing);
+        const int cl = lane & 7, crp = lane >> 3;                  // copy role: line of the chunk, row pair (and row pair + 4)
+        int is_it = 0, is_c = grp, is_m = 0;                       // the next chunk to fetch: tile, chunk, ring slot
+        const float2 *is_p = nullptr, *is_pm = nullptr;            // direct: (line 8 c + cl, rows 2 crp ..); mirrored: this thread's own
+        auto issue_tile = [&]() {                                  // pointers for the first chunk of tile is_it
+            const int tile2 = blockIdx.x + is_it * gridDim.x;
+            const int yw = ((tile2 % tiles) << 7) + 16 * (warp & 7);
+            const float2* base = g.Y + (size_t)(tile2 / tiles) * g.lines_in * Sh;
+            is_p = base + (size_t)(8 * grp + cl) * Sh + yw + 2 * crp;
+            is_pm = base + (ptrdiff_t)(n - (8 * grp + 4 * kg)) * Sh + ((Sh - (yw + (lane >> 1))) & (Sh - 1));
+        };
+        auto issue_next = [&]() {
+            if (is_it < my_tiles) {
+                uint8_t* dst = ring + is_m * kWarpRing;
+                const int kd = 8 * is_c + cl;                      // direct copy: two 16-byte pieces of line kd
+                if (kd < kdim && !(MODE == 2 && g.half && kd >= nb)) {
+                    umma::cp_async16(dst + cl * kLinePitch + crp * 16, is_p);
+                    umma::cp_async16(dst + cl * kLinePitch + (crp + 4) * 16, is_p + 8);
+                }
+                if (MODE == 2 && g.half) {
+                    const int k0 = 8 * is_c + 4 * kg;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (k0 + i >= nb && k0 + i < kdim)
+                            umma::cp_async8(dst + (4 * kg + i) * kLinePitch + (lane >> 1) * 8, is_pm - i * Sh);
+                }
+                if (++is_m == kCvDepth) is_m = 0;
+                is_c += 2;
+                is_p += 16 * Sh;
+                is_pm -= 16 * Sh;
+                if (is_c >= nchunks) {
+                    is_c = grp;
+                    if (++is_it < my_tiles) issue_tile();
+                }
+            }
+            umma::cp_async_commit();                               // (an empty group keeps the count in step at the tail)
+        };
+        int rd_m = 0;                                              // ring slot of the chunk being converted
+        if (MODE != 0) {
+            if (my_tiles > 0) issue_tile();
+#pragma unroll 1
+            for (int d = 0; d < kCvDepth; ++d) issue_next();
+        }
         for (int it = 0; it < my_tiles && ok; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int mt = tile % tiles;
@@ -243,20 +300,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
             unsigned sb_ = 1u;
             float inv = 0.f, inv_lo = 0.f;
             unsigned magic_b = 0u;
-            const float2* yrow = nullptr;
-            const float2* yrow_m = nullptr;                        // MODE 2, half arrays: row -y of the same pair
-            // MODE 1 / 2 source element k of this thread's row.  MODE 2 on a HALF cross-power array (lines 0 .. n/2): the
-            // columns beyond n/2 are the conjugates of the mirrored column at row -y, R[y][n-kx] = conj(R[-y][kx])
-            auto ld_src = [&](int k) -> float2 {
-                if (k >= kdim) return make_float2(0.f, 0.f);
-                if (MODE == 2 && g.half && k >= nb) {
-                    const float2 v = yrow_m[(size_t)(n - k) * Sh];
-                    return make_float2(v.x, -v.y);
-                }
-                return yrow[(size_t)k * Sh];
-            };
-            constexpr int PF = 2;                                  // MODE 1 / 2: chunks (of this group) kept in flight per thread
-            float2 nxt[PF][4];
             if (MODE == 0) {
                 { TC_T0(); ok = umma::mbar_wait(stg_full + b, u & 1); if (blockIdx.x == 0 && t == 0) TC_ACC(1); }
                 const int4 ti = tile_info[b];
@@ -276,13 +319,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                     sbase = reinterpret_cast<const uint16_t*>(stg + a0) + row;
                     sstep = pitch_sw >> 1;
                 }
-            } else {
-                yrow = g.Y + (size_t)p * g.lines_in * Sh + y0 + row;
-                yrow_m = g.Y + (size_t)p * g.lines_in * Sh + ((Sh - (y0 + row)) & (Sh - 1));
-#pragma unroll
-                for (int d = 0; d < PF; ++d)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) nxt[d][i] = ld_src(8 * (grp + 2 * d) + 4 * kg + i);
             }
             for (int c = grp; c < nchunks && ok; c += 2) {
                 const int gc = it * nchunks + c;                   // position of this chunk in the operand ring
@@ -373,20 +409,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                         umma::split_tf32(o, qh[i], ql[i]);
                     }
                 } else {
-                    float2 cur[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) cur[i] = nxt[0][i];
-#pragma unroll
-                    for (int d = 0; d + 1 < PF; ++d)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) nxt[d][i] = nxt[d + 1][i];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)                    // PF chunks ahead: global latency stays off the ring's critical path
-                        nxt[PF - 1][i] = ld_src(8 * (c + 2 * PF) + 4 * kg + i);
+                    umma::cp_async_wait<kCvDepth - 1>();             // every lane's copies for this chunk have landed ...
+                    __syncwarp();                                  // ... and are visible to the whole warp
+                    const uint8_t* src = ring + rd_m * kWarpRing + (4 * kg) * kLinePitch + (lane >> 1) * 8;
+                    float2 v[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        umma::split_tf32(cur[i].x, ph[i], pl[i]);
-                        umma::split_tf32(cur[i].y, qh[i], ql[i]);
+                        const int k = 8 * c + 4 * kg + i;
+                        v[i] = k < kdim ? *reinterpret_cast<const float2*>(src + i * kLinePitch) : make_float2(0.f, 0.f);
+                        if (MODE == 2 && g.half && k >= nb) v[i].y = -v[i].y;
+                    }
+                    __syncwarp();                                  // all reads of the slot done before any lane refills it
+                    if (++rd_m == kCvDepth) rd_m = 0;
+                    issue_next();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        umma::split_tf32(v[i].x, ph[i], pl[i]);
+                        umma::split_tf32(v[i].y, qh[i], ql[i]);
                     }
                 }
 #ifdef SB_TC_PROFILE
@@ -903,7 +942,7 @@ size_t sb_tc_zh_bytes(const TcPlan& plan, int n_pairs) { return (size_t)n_pairs 
 int sb_tc_plan(sb_ctx* ctx, int Sh, int n, TcPlan* plan) {
     *plan = TcPlan();
     static const bool off = getenv("SB_REG_NO_TC") != nullptr;
-    if (off || Sh != 1024 || n < 8 || n > 400) return SB_OK;
+    if (off || Sh != kTcSh || n < 8 || n > 400) return SB_OK;
     plan->Sh = Sh;
     plan->n = n;
     plan->nb = n / 2 + 1;
@@ -980,9 +1019,9 @@ int sb_tc_plan(sb_ctx* ctx, int Sh, int n, TcPlan* plan) {
         iti = ctx->twiddle_cache.emplace(keyi, b).first;
     }
     plan->Binv = reinterpret_cast<const uint8_t*>(iti->second.p);
-    plan->smem_inv = tc_smem_layout(NP, 0, 0).total;
+    plan->smem_inv = tc_smem_layout(NP, kCvRingBytes, 1).total;
     static const bool no_inv = getenv("SB_REG_NO_TC_INV") != nullptr;
-    plan->inverse = !no_inv;
+    plan->inverse = !no_inv && plan->smem_inv <= 226 * 1024;      // (n > 268: the tables + the prefetch ring no longer fit -- radix inverse)
     // column-pass twiddles: tw[k2][l] = exp(-2 pi i l k2 / 1024)
     const uint64_t key2 = ((uint64_t)3 << 40) | 1024u;
     auto it2 = ctx->twiddle_cache.find(key2);
@@ -1033,11 +1072,11 @@ int sb_tc_inverse(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pairs,
         configured = plan.smem_inv;
     }
     TcArgs g = {};
-    g.Sh = plan.Sh; g.n = plan.n; g.NP = plan.NP; g.nchunks = plan.nchunks; g.swap = swap; g.stg_bytes = 0;
+    g.Sh = plan.Sh; g.n = plan.n; g.NP = plan.NP; g.nchunks = plan.nchunks; g.swap = swap; g.stg_bytes = kCvRingBytes;
     g.Bmat = plan.Binv; g.fault = d_fault;
     g.Y = static_cast<const float2*>(Y); g.lines_in = lines_in;
     g.best = static_cast<CtaBest*>(best); g.rowmax = rowmax;
-    g.n_tiles = n_pairs * (plan.Sh >> 7); g.stg_bufs = 0; g.acc_bufs = plan.acc_bufs;
+    g.n_tiles = n_pairs * (plan.Sh >> 7); g.stg_bufs = 1; g.acc_bufs = plan.acc_bufs;
     const int grid = std::min(g.n_tiles, ctx->sm_count);
     xdft_tc_kernel<1><<<grid, kTcThreads, plan.smem_inv, st>>>(g);
     ctx->launches++;
@@ -1056,18 +1095,18 @@ int sb_tc_updft_rows(sb_ctx* ctx, cudaStream_t st, const TcPlan& plan, int n_pai
     const int nch = (plan.n + 7) / 8;
     updft_tables_tc_kernel<<<dim3(8, n_pairs), 256, 0, st>>>(static_cast<const PeakOut*>(d_peaks), plan.Sh, plan.n, uf, rs, dftshift, nch,
                                                              static_cast<float*>(Bimg), static_cast<float2*>(Ey));
-    const int smem = tc_smem_layout(32, 0, 0).total;
+    const int smem = tc_smem_layout(32, kCvRingBytes, 1).total;
     static int configured = 0;
     if (smem > configured) {
         SB_CUDA(ctx, cudaFuncSetAttribute(xdft_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
     TcArgs g = {};
-    g.Sh = plan.Sh; g.n = plan.n; g.NP = 32; g.nchunks = nch; g.swap = 0; g.stg_bytes = 0;
+    g.Sh = plan.Sh; g.n = plan.n; g.NP = 32; g.nchunks = nch; g.swap = 0; g.stg_bytes = kCvRingBytes;
     g.Bmat = static_cast<const uint8_t*>(Bimg); g.fault = d_fault;
     g.Y = static_cast<const float2*>(R); g.lines_in = lines_in; g.half = lines_in < plan.n ? 1 : 0;
     g.Tm = static_cast<float2*>(Tm); g.rs = rs;
-    g.n_tiles = n_pairs * (plan.Sh >> 7); g.stg_bufs = 0; g.acc_bufs = 2;
+    g.n_tiles = n_pairs * (plan.Sh >> 7); g.stg_bufs = 1; g.acc_bufs = 2;
     const int grid = std::min(g.n_tiles, ctx->sm_count);
     xdft_tc_kernel<2><<<grid, kTcThreads, smem, st>>>(g);
     ctx->launches += 2;

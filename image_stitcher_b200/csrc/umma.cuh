@@ -154,6 +154,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  : "memory");
 }
 
+// ---- cp.async (LDGSTS), 8 bytes: global -> shared without staging registers; groups complete in order
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {      // .cg: L2 only, no L1 line allocated
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- tf32 split: hi = v rounded to tf32 (RNA), lo = v - hi (exactly representable in fp32; its own tf32 rounding is
 // applied by the tensor core when it reads the operand, which truncates the 13 low mantissa bits)
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {

@@ -378,6 +378,37 @@ def test_fuse_regions_batch_equals_region_by_region_and_oracle(ctx, layout):
     ctx.clear_fields()
 
 
+@pytest.mark.parametrize("layout", ["rowmajor", "chunked"])
+def test_fuse_regions_wide_tiles_equal_region_by_region(ctx, layout):
+    """Tiles wide enough for the four-group interior chunks of ``paste_rect_jobs_kernel`` (flat-field vectors parked in
+    shared memory, several regions per block), more regions than one block carries (8 + 1), every tile offset: the batch
+    equals one ``sb_fuse_region`` per well (itself checked against the oracle above and in test_configs_gpu)."""
+    import torch
+    from image_stitcher_b200 import _ffi
+    from image_stitcher_b200.plate import PlateSpec, make_plate
+    spec = PlateSpec(wells=9, rows=2, cols=3, tile_h=96, tile_w=2560, channels=2, num_z=1, jitter=5, seed=23)
+    plate = make_plate(spec, device="cuda:0")
+    ctx.clear_fields()
+    for c in range(spec.channels):
+        ctx.set_flatfield(c, plate.flat[c], mem=_ffi.SB_MEM_DEVICE)
+    Wc, Hc = spec.canvas_size()
+    planes = spec.channels * spec.num_z
+    if layout == "rowmajor":
+        shape, kw = (spec.wells, planes, Hc, _ffi.canvas_pitch(Wc)), {}
+    else:
+        ch, cw = 64, 512
+        shape, kw = (spec.wells, planes, -(-Hc // ch), -(-Wc // cw), ch, cw), dict(layout=_ffi.SB_LAYOUT_CHUNKED, chunk=(ch, cw))
+    batch = torch.full(shape, 0x5A5A, dtype=torch.int16, device="cuda:0")
+    single = torch.full(shape, 0x1111, dtype=torch.int16, device="cuda:0")
+    torch.cuda.synchronize()
+    ctx.fuse_regions(_plate_jobs(spec, plate, batch, apply_flatfield=True, **kw))
+    for job in _plate_jobs(spec, plate, single, apply_flatfield=True, **kw):
+        tiles = job.pop("tiles"); ts = job.pop("tile_shape"); cs = job.pop("canvas_shape")
+        ctx.fuse_region(tiles, ts, cs, **job)
+    assert torch.equal(batch, single)
+    ctx.clear_fields()
+
+
 def test_fuse_regions_falls_back_region_by_region(ctx):
     """Regions with different geometry (or host memory) are not batched: same results as separate calls."""
     rng = np.random.default_rng(21)
