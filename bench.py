@@ -714,6 +714,200 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_mosaic(args, rank, world, local_rank):
+    """--config 4 --scaling strong: ONE large mosaic (20 x 20 tiles of 3000^2, 5 z-planes) split over the ranks the way
+    SURVEY 8e prescribes -- registration by grid-row bands of the pair list (shard.mosaic_pairs_for_rank), fusion by
+    (plane, chunk-row) bands of the canvas (shard.fusion_units_for_rank + tiles_for_band), no data-path collective: the
+    shifts are all-gathered after the timed region only to be checked.  Every rank generates the same mosaic (seeded);
+    rank 0 also fuses plane 0 in ONE call and compares it band by band with what the owners produced.  Works at N = 1
+    (all bands on one GPU) -- the base of the strong-scaling ratio."""
+    import torch
+    from image_stitcher_b200 import _ffi, shard
+    from image_stitcher_b200 import geometry as geo
+    from image_stitcher_b200.plate import FusePlan, PlateSpec, RegisterPlan, make_plate, well_fuse_tiles
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    affinity = None if args.no_affinity else bind_to_gpu_cpus(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)                                        # NCCL's banner must not land on the JSON line's stdout
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    spec = PlateSpec(wells=1, rows=args.grid, cols=args.grid, tile_h=args.tile, tile_w=args.tile, channels=args.channels,
+                     num_z=args.num_z, reg_channel=min(1, args.channels - 1), seed=0)
+    use_flat = not args.no_flatfield
+    ctx = _ffi.Context(local_rank)
+    plate = make_plate(spec, device=dev, with_flat=use_flat, well_ids=[0])
+    if use_flat:
+        for c in range(spec.channels):
+            ctx.set_flatfield(c, plate.flat[c], mem=_ffi.SB_MEM_DEVICE)
+    Wc, Hc = spec.canvas_size()
+    pitch = _ffi.canvas_pitch(Wc)
+    planes = spec.channels * spec.num_z
+    ovx, ovy = spec.strip_overlaps()
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.synchronize()
+    ctx.set_lane_stream(0, stream.cuda_stream)
+    ptr = lambda r, c, ch, z: plate.pool[0, r, c, ch, z].data_ptr()
+
+    # ---- this rank's pairs: grid-row bands of the mosaic's pair list
+    mine = shard.mosaic_pairs_for_rank(spec.rows, spec.cols, world, rank)
+    reg = [(ptr(r0, c0, spec.reg_channel, 0), ptr(r1, c1, spec.reg_channel, 0),
+            _ffi.SB_DIR_HORIZONTAL if kind == "h" else _ffi.SB_DIR_VERTICAL) for kind, (r0, c0), (r1, c1) in mine]
+    reg_plan = RegisterPlan(ctx, reg, (spec.tile_h, spec.tile_w), ovx, ovy, mem=_ffi.SB_MEM_DEVICE, lane=0) if reg else None
+    # ---- this rank's output bands: (plane, chunk-row) units, each fused from the tiles that reach its rows
+    chunk_h = 2048
+    tiles = well_fuse_tiles(spec, ptr)
+    units = shard.fusion_units_for_rank(planes, Hc, chunk_h, world, rank)
+    bands, plans = [], []
+    for plane, y0, y1 in units:
+        c, z = divmod(plane, spec.num_z)
+        sub = [t for t in tiles if t[3] == c and t[4] == z]
+        band_tiles = [(t[0], t[1], t[2], 0, 0, *t[5:]) for t in shard.tiles_for_band(sub, spec.tile_h, y0, y1)]
+        out = torch.empty((1, y1 - y0, pitch), dtype=torch.int16, device=dev)
+        bands.append(out)
+        # (a band of channel c fuses as channel 0 of a one-plane job: the field slot is selected per unit below)
+        plans.append((c, FusePlan(ctx, band_tiles, (spec.tile_h, spec.tile_w), (1, 1, y1 - y0, Wc), out, tile_mem=_ffi.SB_MEM_DEVICE,
+                                  out_mem=_ffi.SB_MEM_DEVICE, apply_flatfield=use_flat and c == 0)))
+    if use_flat and spec.channels > 1:
+        raise RuntimeError("bench.py: the mosaic split with a flat-field is wired for one channel (BASELINE configs[4] has none)")
+    px_mine = sum((y1 - y0) * Wc for _, y0, y1 in units)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(rec):
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record(stream)
+        if reg_plan is not None:
+            reg_plan.run()
+        e1.record(stream)
+        for _, pl in plans:
+            pl.run(0)
+        e2.record(stream)
+        if rec is not None:
+            rec.append((e0, e1, e2))
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step(None)
+    torch.cuda.synchronize()
+    t_load0 = time.perf_counter()
+    for _ in range(args.warmup):
+        step(None)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    launches0 = ctx.kernel_launches
+    torch.cuda.synchronize()
+    t_start, t_end, recs = ev(), ev(), []
+    wall0 = time.perf_counter()
+    t_start.record(stream)
+    for _ in range(args.steps):
+        step(recs)
+    t_end.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop(t_load0, wall0, wall0 + wall)
+    total_ms = t_start.elapsed_time(t_end)
+    reg_sum = float(sum(a.elapsed_time(b) for a, b, _ in recs))
+    fuse_sum = float(sum(b.elapsed_time(c) for _, b, c in recs))
+    px_all, pairs_all = px_mine, len(reg)
+    if dist:
+        t = torch.tensor([total_ms, reg_sum, fuse_sum], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, reg_sum, fuse_sum = (float(v) for v in t.tolist())
+        l = torch.tensor([launches, px_mine, len(reg)], device=dev, dtype=torch.int64)
+        dist.all_reduce(l)
+        launches, px_all, pairs_all = (int(v) for v in l.tolist())
+
+    # ---- checks (outside the timed region): every pair's shift equals the generator's drift; plane 0 of the sharded
+    # canvas equals the canvas ONE sb_fuse_region call produces on rank 0, band by band (sum + xor-rotate checksums)
+    res = reg_plan.results() if reg_plan is not None else []
+    shifts_ok = all((r["dy"], r["dx"]) == plate.truth[0][kind] for r, (kind, _, _) in zip(res, mine))
+
+    def checksum(tensor2d):
+        v = tensor2d[:, :Wc].to(torch.int64) & 0xFFFF
+        w = torch.arange(1, v.shape[1] + 1, device=v.device, dtype=torch.int64)
+        return int(v.sum().item()), int((v * w).sum().item() & 0x7FFFFFFFFFFFFFFF)
+
+    my_sums = [(plane, y0, *checksum(b[0])) for (plane, y0, y1), b in zip(units, bands) if plane == 0]
+    ok_t = torch.tensor([int(shifts_ok)], device=dev, dtype=torch.int64)
+    gathered = None
+    if dist:
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, my_sums)
+    else:
+        gathered = [my_sums]
+    canvas_ok = None
+    if rank == 0:
+        sub0 = [(t[0], t[1], t[2], 0, 0, *t[5:]) for t in tiles if t[3] == 0 and t[4] == 0]
+        whole = torch.empty((1, Hc, pitch), dtype=torch.int16, device=dev)
+        torch.cuda.synchronize()
+        ctx.fuse_region(sub0, (spec.tile_h, spec.tile_w), (1, 1, Hc, Wc), out=whole, tile_mem=_ffi.SB_MEM_DEVICE,
+                        out_mem=_ffi.SB_MEM_DEVICE, apply_flatfield=use_flat, dtype=_ffi.SB_U16)
+        torch.cuda.synchronize()
+        n_bands, canvas_ok = 0, True
+        for part in gathered:
+            for plane, y0, s1, s2 in part:
+                y1 = min(y0 + chunk_h, Hc)
+                canvas_ok = canvas_ok and checksum(whole[0, y0:y1]) == (s1, s2)
+                n_bands += 1
+        canvas_ok = bool(canvas_ok and n_bands == -(-Hc // chunk_h))
+        del whole
+
+    peaks = {}
+    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = 4.0 * px_all                                   # 2 B winning source px + 2 B written (all ranks)
+    achieved = alg_bytes * args.steps / (fuse_sum * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": px_all * args.steps / 1e6 / (total_ms * 1e-3), "unit": "Mpx/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "u16 pixels; f32 FFT with f64 redo of low-confidence pairs", "data": "synthetic",
+        "config": {"workload": workload_name(spec, use_flat, args.blend, args.config),
+                   "sharding": "ONE mosaic: pairs by grid-row bands (shard.mosaic_pairs_for_rank), canvas by (plane, chunk-row) "
+                               f"bands of {chunk_h} rows (shard.fusion_units_for_rank + tiles_for_band); no data-path collective",
+                   "pairs_per_step": pairs_all, "canvas": [planes, Hc, Wc], "bands": planes * -(-Hc // chunk_h),
+                   "l2": "inputs (36 GB) and outputs (29 GB) per step exceed L2 (126 MB); no flush needed",
+                   "timing": "CUDA events on the launching stream, max over ranks"},
+        "tile_pairs_per_s": pairs_all * args.steps / (reg_sum * 1e-3) if reg_sum else None,
+        "fusion_mpx_per_s": px_all * args.steps / 1e6 / (fuse_sum * 1e-3),
+        "registration_ms_per_step": reg_sum / args.steps, "fusion_ms_per_step": fuse_sum / args.steps,
+        "wall_ms_per_step": wall / args.steps * 1e3,
+        "registration_truth_all_pairs_ok": bool(int(ok_t.item())),
+        "plane0_equals_single_call_canvas": canvas_ok,
+        "gpu_launches": int(launches), "cpu_affinity": affinity, "clocks": clocks,
+        "roofline": {"kernel": "paste_rect_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs * world, "unit": "GB/s",
+                     "frac": achieved / (peak_gbs * world), "traffic": None,
+                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs) x ranks" if "hbm_gbs" in peaks else "fallback 6650 GB/s x ranks",
+                     "algorithmic_bytes_per_step": alg_bytes},
+        "e2e": None,
+    }
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -721,6 +915,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.scaling == "strong" and args.wells == 1:
+        run_mosaic(args, rank, world, local_rank)         # one region: split inside the mosaic (bands), not by wells
     else:
         run_b200(args, rank, world, local_rank)
 
