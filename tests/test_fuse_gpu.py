@@ -409,6 +409,36 @@ def test_fuse_regions_wide_tiles_equal_region_by_region(ctx, layout):
     ctx.clear_fields()
 
 
+@pytest.mark.parametrize("blend", ["linear", "feather"])
+def test_fuse_regions_blend_batch_equals_region_by_region(ctx, blend):
+    """Blend modes through ``sb_fuse_regions``: the cells are built once, the single-cover cells of every region go through
+    one paste launch and the overlap cells through one ``blend_cells_kernel`` launch (region = grid z) -- bit-equal to one
+    ``sb_fuse_region`` per well (itself within 1 LSB of oracle/blend_ref.py, test_blend_modes_*)."""
+    import torch
+    from image_stitcher_b200 import _ffi
+    from image_stitcher_b200.plate import PlateSpec, make_plate
+    spec = PlateSpec(wells=7, rows=2, cols=2, tile_h=256, tile_w=384, channels=3, num_z=1, jitter=2, seed=31)
+    plate = make_plate(spec, device="cuda:0")
+    ctx.clear_fields()
+    for c in (0, 2):
+        ctx.set_flatfield(c, plate.flat[c], mem=_ffi.SB_MEM_DEVICE)
+    Wc, Hc = spec.canvas_size()
+    ovx, ovy = spec.strip_overlaps()
+    shape = (spec.wells, spec.channels * spec.num_z, Hc, _ffi.canvas_pitch(Wc))
+    kw = dict(apply_flatfield=True, blend=_ffi.BLEND_MODES[blend], blend_ov=(ovx, ovy))
+    batch = torch.full(shape, 0x5A5A, dtype=torch.int16, device="cuda:0")
+    single = torch.full(shape, 0x1111, dtype=torch.int16, device="cuda:0")
+    torch.cuda.synchronize()
+    launches0 = ctx.kernel_launches
+    ctx.fuse_regions(_plate_jobs(spec, plate, batch, **kw))
+    assert ctx.kernel_launches - launches0 == 2                  # paste of the single-cover cells + blend of the overlaps
+    for job in _plate_jobs(spec, plate, single, **kw):
+        tiles = job.pop("tiles"); ts = job.pop("tile_shape"); cs = job.pop("canvas_shape")
+        ctx.fuse_region(tiles, ts, cs, **job)
+    assert torch.equal(batch, single)
+    ctx.clear_fields()
+
+
 def test_fuse_regions_falls_back_region_by_region(ctx):
     """Regions with different geometry (or host memory) are not batched: same results as separate calls."""
     rng = np.random.default_rng(21)
