@@ -769,9 +769,12 @@ int run_group(sb_ctx* ctx, Lane* lane, const std::vector<PairDesc>& pairs, const
     // strict L2 residency.  The persistent tensor-core kernels (r2) want MANY tiles per block -- at 54 pairs a block sees
     // 3-6 tiles and the pipeline fill / drain is a third of the launch -- so the budget is 4 GB over 2 streams: the 576
     // pairs of one direction of a 96-well plate in one sub-batch (7.8 -> 7.35 ms per 1152 pairs at 4.5 GB / 1 stream).
-    static const int kWays = getenv("SB_REG_WAYS") ? std::max(1, std::min(4, atoi(getenv("SB_REG_WAYS")))) : 2;
+    // (the radix engine -- float64, or strips the tensor-core kernels do not take -- keeps its round-1 optimum: 768 MB / 4)
+    static const int kWaysEnv = getenv("SB_REG_WAYS") ? std::max(1, std::min(4, atoi(getenv("SB_REG_WAYS")))) : 0;
+    static const int kBudgetEnv = getenv("SB_REG_L2_MB") ? std::max(8, atoi(getenv("SB_REG_L2_MB"))) : 0;
+    const int kWays = kWaysEnv ? kWaysEnv : (tc.ok ? 2 : 4);
     const size_t per_pair = 2 * strip * sizeof(T2);
-    static const size_t kL2Budget = (size_t)(getenv("SB_REG_L2_MB") ? std::max(8, atoi(getenv("SB_REG_L2_MB"))) : 4096) << 20;
+    const size_t kL2Budget = (size_t)(kBudgetEnv ? kBudgetEnv : (tc.ok ? 4096 : 768)) << 20;
     int B = (int)std::max<size_t>(1, kL2Budget / per_pair);
     int ways = 1;
     while (ways < kWays && B / (ways + 1) >= 2 && n > B / (ways + 1)) ++ways;
