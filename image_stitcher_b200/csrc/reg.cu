@@ -1296,8 +1296,9 @@ int sb_normalize_impl(sb_ctx* ctx, const void* tiles, void* out, int n_tiles, in
 }
 
 // ------------------------------------------------------------------------------------------ self-test (test hook)
-// Exhaustive proof that the integer stretches fused into the strip loads (stretch_px of the radix kernels; stretch_bits and
-// stretch_core of the tensor-core converters, with their hand-over to stretch_px) equal the float64 expression of
+// Exhaustive proof that the integer stretches fused into the strip loads (stretch_px of the radix kernels; stretch_mulhi and
+// stretch_core of the tensor-core converters -- and stretch_bits, the form stretch_mulhi replaced -- with their hand-over to
+// stretch_px) equal the float64 expression of
 // normalize_image (stretch_px_f64, stitcher_process.py:844-855) for EVERY pixel value and tile range: all pairs
 // a = v - min, b = max - min with 0 <= a <= b, 1 <= b <= maxval (2^31 pairs for uint16).
 namespace {
@@ -1306,6 +1307,7 @@ __global__ void __launch_bounds__(256) selftest_stretch_kernel(int maxval, unsig
     const float inv = (float)maxval / (float)b;                         // as rows_fwd_kernel forms it
     const float inv_lo = stretch_inv_lo((unsigned)b, (unsigned)maxval);   // as the tensor-core converters form it
     const unsigned magic_b = kStretchMagic * (unsigned)b;
+    const StretchMagic smagic = stretch_magic((unsigned)b, (unsigned)maxval);
     unsigned long long bad = 0, first = ~0ull, fallbacks = 0;
     for (int a = threadIdx.x; a <= b; a += blockDim.x) {
         const int fast = stretch_px((unsigned)a, 0, b, inv, maxval), ref = stretch_px_f64((unsigned)a, 0, b, maxval);
@@ -1315,8 +1317,11 @@ __global__ void __launch_bounds__(256) selftest_stretch_kernel(int maxval, unsig
         const int fast_tc = ex ? fast : (int)(bits - kStretchMagic);
         const int core = stretch_core((unsigned)a, (unsigned)b, inv, (unsigned)maxval, ex2);      // (edge chunks, b < maxval)
         const int fast_core = (ex2 || b == maxval) ? fast : core;
-        fallbacks += ex ? 1 : 0;
-        if (fast != ref || fast_tc != ref || fast_core != ref) {
+        bool ex3 = false;                                                                         // interior chunks: multiply-high
+        const unsigned mh = stretch_mulhi((unsigned)a, (unsigned)b, smagic, (unsigned)maxval, ex3);
+        const int fast_mh = (ex3 || b == maxval) ? fast : (int)mh;
+        fallbacks += ex3 ? 1 : 0;
+        if (fast != ref || fast_tc != ref || fast_core != ref || fast_mh != ref || ex3 != ex) {
             ++bad;
             const unsigned long long key = ((unsigned long long)b << 32) | (unsigned)a;
             first = key < first ? key : first;

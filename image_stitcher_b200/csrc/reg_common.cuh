@@ -74,6 +74,22 @@ __device__ __forceinline__ unsigned stretch_bits(unsigned a, unsigned b, float i
     return bits;
 }
 
+// The integer form the tensor-core converters run since r2 call 23: k = floor(a * maxval / b) = (a * M) >> 32 with the
+// 48-bit magic M = ceil(2^32 * maxval / b).  Exact: a * M / 2^32 exceeds the true quotient by less than a * 2^-32 <= 2^-16,
+// and a non-integer a * maxval / b lies at least 1 / b > 2^-16 below the next integer (b <= 65535).  Two instructions
+// (IMAD.HI on the low word + IMAD on the high word); `exact` as above from the remainder.
+struct StretchMagic { unsigned lo, hi; };
+__device__ __forceinline__ StretchMagic stretch_magic(unsigned b, unsigned maxval) {          // once per tile (b >= 1)
+    const unsigned long long num = (unsigned long long)maxval << 32;
+    const unsigned long long m = (num + b - 1) / b;
+    return {(unsigned)m, (unsigned)(m >> 32)};
+}
+__device__ __forceinline__ unsigned stretch_mulhi(unsigned a, unsigned b, StretchMagic m, unsigned maxval, bool& exact) {
+    const unsigned k = a * m.hi + __umulhi(a, m.lo);
+    exact = exact || (a * maxval - k * b == 0u && a != 0u);
+    return k;
+}
+
 // The same value without the float64 divide.  With a = v - min, b = max - min the exact quotient a * 65535 / b is
 // rational with denominator b <= 65535, so unless it is an integer it lies at least 1 / 65535 away from the next
 // one, while the float64 evaluation is off by at most 65535 * 2^-52: trunc() of both agree.  When b divides

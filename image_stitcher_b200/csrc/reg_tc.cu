@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
     uint64_t* acc_full = bars + 4 + 2 * kTcStages;   // [2] tcgen05.commit -> epilogue
     uint64_t* acc_empty = acc_full + 2;         // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    int4* tile_info = reinterpret_cast<int4*>(smem + L.bar_off + 128);     // [2] MODE 0: (min, max, row misalignment) of a staged tile
+    int4* tile_info = reinterpret_cast<int4*>(smem + L.bar_off + 128);     // [2] MODE 0: (min, max, row misalignment | stretch magic hi, stretch magic lo) of a staged tile
     __shared__ double s_val[4], s_sec[4];       // MODE 1: block reduction of the epilogue warps
     __shared__ int s_idx[4];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                 // to open every tile of every converter thread; here they ride on the loader, a tile ahead
                 if (lane == 1) {
                     const int2 m = g.mm[img ? pd.b_tile : pd.a_tile];
-                    tile_info[b] = make_int4(m.x, m.y, (int)a0, 0);
+                    // (+ the 48-bit stretch magic of the tile, one 64-bit divide here instead of one per converter thread)
+                    const StretchMagic sm = stretch_magic(m.y > m.x ? (unsigned)(m.y - m.x) : 1u, (unsigned)g.maxval);
+                    tile_info[b] = make_int4(m.x, m.y, (int)(a0 | (sm.hi << 4)), (int)sm.lo);
                     umma::mbar_arrive(stg_full + b);               // (release: the record is visible to whoever sees the phase)
                 }
             }
@@ -298,8 +300,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
             int sstep = 0;                                         // ... and the distance (uint16 elements) between its columns
             int mn = 0, mx = 0, seen = 0, smode = 0;
             unsigned sb_ = 1u;
-            float inv = 0.f, inv_lo = 0.f;
-            unsigned magic_b = 0u;
+            float inv = 0.f;
+            StretchMagic smagic = {0u, 0u};
             if (MODE == 0) {
                 { TC_T0(); ok = umma::mbar_wait(stg_full + b, u & 1); if (blockIdx.x == 0 && t == 0) TC_ACC(1); }
                 const int4 ti = tile_info[b];
@@ -307,11 +309,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                 mx = ti.y;
                 inv = mx > mn ? (float)g.maxval / (float)(mx - mn) : 0.f;
                 sb_ = mx > mn ? (unsigned)(mx - mn) : 1u;
-                inv_lo = stretch_inv_lo(sb_, (unsigned)g.maxval);
-                magic_b = kStretchMagic * sb_;
+                smagic = {(unsigned)ti.w, (unsigned)ti.z >> 4};
                 smode = mx <= mn ? 0 : (sb_ == (unsigned)g.maxval ? 1 : 2);     // constant tile / full range (identity) / general
                 const uint8_t* stg = smem + L.stg_off + b * g.stg_bytes;
-                const uint32_t a0 = (uint32_t)ti.z;
+                const uint32_t a0 = (uint32_t)ti.z & 15u;
                 if (!g.swap) {
                     sbase = reinterpret_cast<const uint16_t*>(stg + row * pitch_ns + a0);
                     sstep = 1;
@@ -335,7 +336,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
 #endif
                 if (MODE == 0 && smode == 2 && c >= 1 && 8 * c + 7 <= no) {
                     // interior chunk of a general tile (12 of the 14 chunks of a 214-wide strip): every j has both fold
-                    // partners, no guards; stretch on the 2^23 magic-number bit patterns (stretch_bits)
+                    // partners, no guards; stretch by a 48-bit multiply-high (stretch_mulhi: 2 instructions per pixel + the
+                    // exact-quotient check; the float-estimate forms before it cost 16-19)
                     unsigned ra[4], rb[4], ba[4], bb[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -346,19 +348,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) xdft_tc_kernel(const TcArgs g) 
                     bool exact = false;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        ba[i] = stretch_bits(ra[i] - (unsigned)mn, sb_, inv_lo, (unsigned)g.maxval, magic_b, exact);
-                        bb[i] = stretch_bits(rb[i] - (unsigned)mn, sb_, inv_lo, (unsigned)g.maxval, magic_b, exact);
+                        ba[i] = stretch_mulhi(ra[i] - (unsigned)mn, sb_, smagic, (unsigned)g.maxval, exact);
+                        bb[i] = stretch_mulhi(rb[i] - (unsigned)mn, sb_, smagic, (unsigned)g.maxval, exact);
                     }
                     if (exact) {                                   // (rare) an exact quotient somewhere: the float64 expression decides
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            ba[i] = kStretchMagic + (unsigned)stretch_px(ra[i], mn, mx, inv, g.maxval);
-                            bb[i] = kStretchMagic + (unsigned)stretch_px(rb[i], mn, mx, inv, g.maxval);
+                            ba[i] = (unsigned)stretch_px(ra[i], mn, mx, inv, g.maxval);
+                            bb[i] = (unsigned)stretch_px(rb[i], mn, mx, inv, g.maxval);
                         }
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const unsigned es = ba[i] + bb[i] - 2u * kStretchMagic;          // a + b       in [0, 2^17)
+                        const unsigned es = ba[i] + bb[i];                               // a + b       in [0, 2^17)
                         const unsigned os = ba[i] - bb[i] + 0x400000u;                   // a - b + 2^22 in (0, 2^23)
                         seen |= (int)es;
                         const float e = __uint_as_float(kStretchMagic | es) - 8388608.0f;
