@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--fuse-lanes", type=int, default=3, help="library lanes (streams) the per-well fusion launches rotate over")
     ap.add_argument("--per-well-fusion", action="store_true",
                     help="one sb_fuse_region launch per well (round-1 behaviour) instead of one sb_fuse_regions launch per plate")
+    ap.add_argument("--no-coordinate-only", action="store_true", help="skip the informational fusion pass without the flat-field")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-wells", type=int, default=0, help="wells in the CPU sample (0 = one per host core)")
@@ -605,6 +606,40 @@ def run_b200(args, rank, world, local_rank):
                                     "note": "registration (lane 0 + aux streams) and fusion (other lanes) enqueued together; "
                                             "informational, not the contract value (no gain on B200: the registration blocks "
                                             "hold the whole register file, so fusion blocks cannot co-reside)"}
+
+    # ---------------------------------------------------------------- informational: coordinate-only fusion (no flat-field)
+    # BASELINE.json names configs[2] "coordinate-only fusion (fusion-kernel bandwidth test)"; the contract value above keeps
+    # the flat-field ON (the harder case: + 4 B of field per pixel through L2 and the exact divide).  The same launch without
+    # the field is the kernel against the copy roofline alone.
+    if use_flat and args.blend == "paste" and batch is not None and not args.no_coordinate_only:
+        plans_nf = [FusePlan(ctx, well_fuse_tiles(spec, dev_ptr(w)), (spec.tile_h, spec.tile_w),
+                             (spec.channels, spec.num_z, Hc, Wc), canvases[w], tile_mem=_ffi.SB_MEM_DEVICE,
+                             out_mem=_ffi.SB_MEM_DEVICE, apply_flatfield=False, blend=blend, blend_ov=(ovx, ovy))
+                    for w in range(spec.wells)]
+        batch_nf = FuseBatchPlan(ctx, plans_nf)
+        for _ in range(2):
+            batch_nf.run(0)
+        torch.cuda.synchronize()
+        nf = []
+        for _ in range(max(3, args.steps)):
+            a, b = ev(), ev()
+            a.record(stream)
+            batch_nf.run(0)
+            b.record(stream)
+            torch.cuda.synchronize()
+            nf.append(a.elapsed_time(b))
+        nf_ms = float(np.mean(nf))
+        if dist:
+            t = torch.tensor([nf_ms], device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            nf_ms = float(t.item())
+        nf_gbs = alg_bytes / (nf_ms * 1e-3) / 1e9
+        out["fusion_coordinate_only"] = {"ms_per_step": nf_ms, "fusion_mpx_per_s": px_all / 1e6 / (nf_ms * 1e-3),
+                                         "achieved": nf_gbs, "unit": "GB/s", "frac": nf_gbs / peak_gbs,
+                                         "frac_of_spec_8000": nf_gbs / 8000.0,
+                                         "note": "same plate, same launch (sb_fuse_regions), apply_flatfield = False"}
+        batch.run(0)                                     # leave the flat-field canvases in place for the checks below
+        torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- e2e: host buffers through the public API
     if not args.no_e2e:

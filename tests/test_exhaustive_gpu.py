@@ -28,8 +28,12 @@ def test_integer_stretch_equals_float64_for_every_pixel_and_range(ctx, maxval):
     assert 0 < fallbacks < checked // 10                      # exact quotients exist and are rare (4.5 % of the 8-bit pairs, far fewer of the 16-bit ones)"
 
 
-@pytest.mark.parametrize("expo", [-5, -1, 0, 19])
+@pytest.mark.parametrize("expo", list(range(-5, 20)))
 def test_packed_divide_equals_ieee_for_every_numerator_and_mantissa(ctx, expo):
+    """Every binade of the accepted field range [2^-5, 2^20): the quotient bits are scale-invariant, but which quotients sit
+    next to an integer -- what ``trunc_sat_pack`` / ``round_sat_pack`` (denormal-scale products) must get right -- depends
+    on the binade.  (A divide without the Newton step passed 23 of the 25 binades and failed ONE case in each of 2^-2 and
+    2^-1: r2 call 28.)"""
     checked, bad, first, _ = ctx.selftest(1, expo)
     assert checked == (1 << 23) * 65536
     assert bad == 0, f"{bad} mismatches, first at mantissa={first >> 16}, a={first & 0xffff}"
