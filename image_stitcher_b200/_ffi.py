@@ -45,7 +45,7 @@ class SbFuseJob(C.Structure):
                 ("height", C.c_int32), ("width", C.c_int32), ("apply_flatfield", C.c_int32), ("blend", C.c_int32),
                 ("blend_ov_x", C.c_int32), ("blend_ov_y", C.c_int32), ("out", C.c_void_p), ("out_mem", C.c_int32),
                 ("out_layout", C.c_int32), ("out_row_pitch", C.c_int64), ("chunk_h", C.c_int32),
-                ("chunk_w", C.c_int32)]
+                ("chunk_w", C.c_int32), ("field_c0", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class SbPair(C.Structure):
@@ -273,10 +273,13 @@ class Context:
     # ------------------------------------------------------------------ fusion
     def fuse_region(self, tiles: Sequence[tuple], tile_shape, canvas_shape, *, out, tile_mem=SB_MEM_HOST,
                     out_mem=SB_MEM_HOST, apply_flatfield=False, blend=SB_BLEND_PASTE, blend_ov=(0, 0),
-                    layout=SB_LAYOUT_ROWMAJOR, out_row_pitch=0, chunk=(0, 0), lane=-1, keepalive=None, dtype=None):
+                    layout=SB_LAYOUT_ROWMAJOR, out_row_pitch=0, chunk=(0, 0), lane=-1, keepalive=None, dtype=None,
+                    field_c0=0):
         """``tiles``: sequence of ``(px, x, y, c, z, crop_t, crop_b, crop_l, crop_r)`` in paste order.
 
         ``canvas_shape`` = ``(num_c, num_z, height, width)``.  ``out`` is a numpy array / address / tensor.
+        ``field_c0``: the job fuses a window of a region's planes numbered from 0; tile channel ``c`` takes the
+        context's field of channel ``field_c0 + c``.
         """
         n = len(tiles)
         arr = (SbTile * max(n, 1))()
@@ -291,7 +294,7 @@ class Context:
         job = SbFuseJob(arr, n, int(tile_shape[0]), int(tile_shape[1]), int(dtype), tile_mem,
                         int(canvas_shape[0]), int(canvas_shape[1]), int(canvas_shape[2]), int(canvas_shape[3]),
                         int(bool(apply_flatfield)), int(blend), int(blend_ov[0]), int(blend_ov[1]),
-                        _ptr(out), out_mem, layout, int(out_row_pitch), int(chunk[0]), int(chunk[1]))
+                        _ptr(out), out_mem, layout, int(out_row_pitch), int(chunk[0]), int(chunk[1]), int(field_c0), 0)
         self._check(self.lib.sb_fuse_region(self.handle, C.byref(job), lane), "sb_fuse_region")
 
     def fuse_regions(self, jobs: Sequence[dict], *, lane=-1):
@@ -317,7 +320,7 @@ class Context:
                                    int(cs[2]), int(cs[3]), int(bool(kw.get("apply_flatfield", False))),
                                    int(kw.get("blend", SB_BLEND_PASTE)), int(bo[0]), int(bo[1]), _ptr(out),
                                    kw.get("out_mem", SB_MEM_HOST), kw.get("layout", SB_LAYOUT_ROWMAJOR),
-                                   int(kw.get("out_row_pitch", 0)), int(ch[0]), int(ch[1])))
+                                   int(kw.get("out_row_pitch", 0)), int(ch[0]), int(ch[1]), int(kw.get("field_c0", 0)), 0))
         cj = (SbFuseJob * max(len(cjobs), 1))(*cjobs)
         self._check(self.lib.sb_fuse_regions(self.handle, cj, len(cjobs), lane), "sb_fuse_regions")
 

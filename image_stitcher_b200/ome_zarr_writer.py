@@ -168,6 +168,89 @@ def write_ome_zarr_chunked(path: str, chunked: np.ndarray, shape, chunk_hw, *, p
     return path
 
 
+def pyramid_level_shapes(height: int, width: int, n_levels: int):
+    """``(h_l, w_l)`` of levels ``0 .. n_levels - 1`` under ``[..., ::2, ::2]`` per level."""
+    out = [(int(height), int(width))]
+    for _ in range(1, max(1, int(n_levels))):
+        out.append(((out[-1][0] + 1) // 2, (out[-1][1] + 1) // 2))
+    return out
+
+
+def _dump_atomic(path: str, obj) -> None:
+    tmp = f"{path}.{os.getpid()}.tmp"
+    _dump(tmp, obj)
+    os.replace(tmp, path)                                  # several workers write the same metadata: never a torn file
+
+
+def _chunk_view(level_dir: str, idx: Sequence[int], chunk_hw, dtype) -> np.memmap:
+    """Read-write view of one uncompressed chunk file, created at its full size if it does not exist yet (a sparse file
+    reads as the fill value 0).  Workers that own different rows of the same chunk write through their own views."""
+    d = os.path.join(level_dir, *[str(i) for i in idx[:-1]])
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, str(idx[-1]))
+    nbytes = int(chunk_hw[0]) * int(chunk_hw[1]) * np.dtype(dtype).itemsize
+    fd = os.open(path, os.O_RDWR | os.O_CREAT, 0o644)
+    try:
+        if os.fstat(fd).st_size < nbytes:
+            os.ftruncate(fd, nbytes)
+    finally:
+        os.close(fd)
+    return np.memmap(path, dtype=dtype, mode="r+", shape=(int(chunk_hw[0]), int(chunk_hw[1])))
+
+
+def write_ome_zarr_band(path: str, chunked: np.ndarray, levels: Sequence[np.ndarray], *, plane, row0: int, full_shape,
+                        chunk_hw, n_levels: int, pixel_size_um: float, dz_um: float = 1.0, channel_names: Sequence[str],
+                        channel_colors: Sequence[int], name: Optional[str] = None) -> str:
+    """One worker's share of a region that several GPUs fuse together (the reference's out-of-core
+    analogue is zarr_stitcher.py:570-612): the rows ``[row0, row0 + band_h)`` of plane ``(c, z)``.
+
+    ``chunked`` is the band's level 0 in the library's chunk order ``(1, ncy_band, ncx, chunk_h, chunk_w)`` (``row0`` is a
+    multiple of ``chunk_h``, so the band owns whole chunks: one ``tofile`` each); ``levels`` are the band's multiscale
+    levels ``1 ..`` as ``(1, 1, 1, h, w)`` arrays -- ``row0`` is a multiple of every ``2**l``, so decimating the band
+    equals decimating the region -- whose rows land INSIDE chunks shared with other workers: written through a memory map
+    of the (uncompressed, full-size) chunk file.  Every worker writes the same metadata (atomically)."""
+    C, Z, H, W = (int(v) for v in full_shape)
+    c, z = int(plane[0]), int(plane[1])
+    ch_y, ch_x = int(chunk_hw[0]), int(chunk_hw[1])
+    if row0 % ch_y:
+        raise ValueError(f"band origin {row0} is not a multiple of the chunk height {ch_y}")
+    buf = np.asarray(chunked)
+    ncx = -(-W // ch_x)
+    buf = buf.reshape(-1, ncx, ch_y, ch_x)
+    shapes = pyramid_level_shapes(H, W, n_levels)
+    n_written = 1 + min(len(levels), len(shapes) - 1)
+    os.makedirs(path, exist_ok=True)
+    _dump_atomic(os.path.join(path, ".zgroup"), {"zarr_format": 2})
+    for l in range(n_written):
+        os.makedirs(os.path.join(path, str(l)), exist_ok=True)
+        _dump_atomic(os.path.join(path, str(l), ".zarray"),
+                     _zarray((1, C, Z, shapes[l][0], shapes[l][1]), (1, 1, 1, ch_y, ch_x), buf.dtype, None))
+    _dump_atomic(os.path.join(path, ".zattrs"),
+                 _group_attrs(name or os.path.basename(path).replace(".ome.zarr", ""), n_written, pixel_size_um, dz_um,
+                              channel_names, channel_colors, buf.dtype))
+    for iy in range(buf.shape[0]):
+        for ix in range(ncx):
+            _write_chunk(os.path.join(path, "0"), (0, c, z, row0 // ch_y + iy, ix), buf[iy, ix], None)
+    for l in range(1, n_written):
+        lv = np.asarray(levels[l - 1])
+        lv = lv.reshape(lv.shape[-2], lv.shape[-1])
+        r0 = row0 >> l
+        if lv.shape[1] != shapes[l][1] or r0 + lv.shape[0] > shapes[l][0]:
+            raise ValueError(f"level {l}: band {lv.shape} at row {r0} does not fit the region level {shapes[l]}")
+        y = r0
+        while y < r0 + lv.shape[0]:
+            iy = y // ch_y
+            y1 = min((iy + 1) * ch_y, r0 + lv.shape[0])
+            for ix in range(-(-lv.shape[1] // ch_x)):
+                x0, x1 = ix * ch_x, min((ix + 1) * ch_x, lv.shape[1])
+                mm = _chunk_view(os.path.join(path, str(l)), (0, c, z, iy, ix), (ch_y, ch_x), buf.dtype)
+                mm[y - iy * ch_y:y1 - iy * ch_y, :x1 - x0] = lv[y - r0:y1 - r0, x0:x1]
+                mm.flush()
+                del mm
+            y = y1
+    return path
+
+
 def read_ome_zarr_level(path: str, level: int = 0) -> np.ndarray:
     """Read one level back into a dense array (used by the tests; zarr itself is not installed)."""
     ldir = os.path.join(path, str(level))

@@ -133,7 +133,7 @@ class RegionPipeline:
             st[key + "_cap"] = nbytes
         return st[key + "_dev"]
 
-    def submit(self, job, canvas_shape, n_levels, apply_flatfield):
+    def submit(self, job, canvas_shape, n_levels, apply_flatfield, field_c0=0):
         """``job``: ``(plane ndarray, x, y, c, z, crop_t, crop_b, crop_l, crop_r)`` in paste order.  Returns a ticket;
         ``finish(ticket)`` waits for the lane and yields ``(chunked level 0, [levels 1..])`` as arrays over pinned memory
         that stay valid until the lane is used again."""
@@ -158,7 +158,8 @@ class RegionPipeline:
         ncy, ncx = -(-Hc // ch), -(-Wc // cw)
         l0 = self._grow(lane, "pinned_l0", C * Z * ncy * ncx * ch * cw * 2, pinned=True).view(np.uint16)
         l0 = l0[:C * Z * ncy * ncx * ch * cw].reshape(C * Z, ncy, ncx, ch, cw)
-        common = dict(tile_mem=_ffi.SB_MEM_DEVICE, apply_flatfield=apply_flatfield, lane=lane, dtype=_ffi.SB_U16)
+        common = dict(tile_mem=_ffi.SB_MEM_DEVICE, apply_flatfield=apply_flatfield, lane=lane, dtype=_ffi.SB_U16,
+                      field_c0=field_c0)           # (a band of one plane of a shared region names its channel here)
         levels = []
         if n_levels > 1:
             # row-major device canvas -> multiscale levels while it is resident (Scaler.nearest, :1061-1062)

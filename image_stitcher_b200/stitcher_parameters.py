@@ -41,6 +41,8 @@ class StitchingParameters:
     device: int = 0
     rank: int = 0                         # multi-GPU: this worker stitches regions rank, rank + world, ...
     world: int = 1
+    split_regions: bool = False           # multi-GPU: every worker fuses its (plane, chunk-row) bands of EVERY region
+                                          # (automatic when there are fewer regions than workers)
 
     def __post_init__(self):
         self.input_folder = os.path.abspath(self.input_folder)

@@ -78,6 +78,9 @@ class StitcherProcess(Process):
         # multi-GPU: worker `rank` of `world` stitches regions rank, rank + world, ... on its own device.  Every worker
         # registers the same first region itself (2-3 pairs), so all of them hold the same lattice without any exchange.
         self.rank, self.world = int(getattr(params, "rank", 0)), max(1, int(getattr(params, "world", 1)))
+        # One region on several GPUs: with fewer regions than workers (or split_regions=True) every worker takes part in
+        # EVERY region and fuses its share of the (plane, chunk-row) bands of the canvas (shard.fusion_units_for_rank).
+        self.split_regions = bool(getattr(params, "split_regions", False))
         self._ctx: Optional[_ffi.Context] = None
         self._pyramids = {}                               # (timepoint, region) -> (n_levels, GPU-made levels 1..)
         self._flat_dirty = True
@@ -613,6 +616,108 @@ class StitcherProcess(Process):
             self.place_single_channel_tile(stitched_region, plane, x_pixel, y_pixel, z_level, c, 0)
 
     # ------------------------------------------------------------------ output
+    # ------------------------------------------------------------------ one region on several GPUs
+    def _channel_planes(self, channel: str):
+        """Canvas channel indices a file of ``channel`` feeds (one for mono, three for RGB) -- without decoding it."""
+        if channel in self.monochrome_channels:
+            return [self.monochrome_channels.index(channel)]
+        base = channel.split("_")[0]
+        return [self.monochrome_channels.index(f"{base}_{c}") for c in "RGB" if f"{base}_{c}" in self.monochrome_channels]
+
+    def band_groups(self, height: int):
+        """This worker's share of a region's canvas: ``(plane, y0, y1)`` with consecutive chunk rows of a plane merged
+        (``shard.fusion_units_for_rank`` splits the (plane, chunk-row) product evenly over the workers)."""
+        from .shard import fusion_units_for_rank
+        groups = []
+        for p, y0, y1 in fusion_units_for_rank(self.num_c * self.num_z, height, int(self.chunks[-2]), self.world, self.rank):
+            if groups and groups[-1][0] == p and groups[-1][2] == y0:
+                groups[-1] = (p, groups[-1][1], y1)
+            else:
+                groups.append((p, y0, y1))
+        return groups
+
+    def _band_job(self, timepoint, region, plane, y0, y1):
+        """Paste-ordered job of the tiles of plane ``(c, z)`` whose kept rows reach canvas rows ``[y0, y1)``, re-based to
+        the band (``shard.tiles_for_band``).  Only those files are decoded."""
+        from concurrent.futures import ThreadPoolExecutor
+        from .shard import tiles_for_band
+        c, z = divmod(int(plane), self.num_z)
+        data = self.get_region_data(int(timepoint), region)
+        lattice = self._lattice()
+        xs, ys = list(self.x_positions), list(self.y_positions)
+        want = []
+        for key, info in data.items():                     # dict order == paste order
+            if key[3] != z or c not in self._channel_planes(key[4]):
+                continue
+            p = geo.place_tile(info["x"], info["y"], self.input_width, self.input_height, xs, ys, self.pixel_size_um, lattice)
+            if p.y + p.crop_t < y1 and p.y + self.input_height - p.crop_b > y0:
+                want.append((key, info, p))
+
+        def _load(item):
+            key, info, p = item
+            try:
+                return item, read_image(info["filepath"]), None
+            except Exception as exc:
+                return item, None, exc
+        with ThreadPoolExecutor(max_workers=self.decode_threads) as pool:
+            loaded = list(pool.map(_load, want))
+        job = []
+        for (key, info, p), tile, exc in loaded:
+            if tile is None:
+                self.emit_status(f"Error Loading Image {info['filepath']}: {exc}")
+                continue
+            for ci, arr in self._tile_planes(tile, key[4]):
+                if ci != c:
+                    continue
+                if arr.shape != (self.input_height, self.input_width):
+                    self.emit_status(f"Error Loading Image {info['filepath']}: shape {arr.shape} != "
+                                     f"{(self.input_height, self.input_width)}")
+                    continue
+                job.append((np.ascontiguousarray(arr, dtype=self._pixel_np()), p.x, p.y, 0, 0,
+                            p.crop_t, p.crop_b, p.crop_l, p.crop_r))
+        return tiles_for_band(job, self.input_height, y0, y1), c, z
+
+    def _save_band(self, timepoint, region, pipe, ticket, c, z, y0, full_shape, n_levels):
+        from .ome_zarr_writer import write_ome_zarr_band
+        l0, levels = pipe.finish(ticket)
+        path = self.per_timepoint_region_output_template.format(timepoint=timepoint, region=region)
+        dz = self.acquisition_params.get("dz(um)", 1.0) if self.acquisition_params else 1.0
+        return write_ome_zarr_band(path, l0, levels, plane=(c, z), row0=y0, full_shape=full_shape, chunk_hw=self.chunks[-2:],
+                                   n_levels=n_levels, pixel_size_um=self.pixel_size_um, dz_um=dz,
+                                   channel_names=self.monochrome_channels, channel_colors=self.monochrome_colors,
+                                   name=f"{region}_t{timepoint}")
+
+    def _run_bands(self, pipe, writer):
+        """Every worker walks every (timepoint, region) and fuses ITS bands: decode of the band's tiles, one
+        ``RegionPipeline`` submission per (plane, row range) -- level 0 in chunk order + the band's pyramid levels --
+        and a writer thread that drops the chunks into the shared OME-Zarr.  No exchange between the workers: chunk
+        files of level 0 have one owner; rows of the coarser levels go through memory maps of shared chunk files."""
+        last_path, lane_writes = "", {}
+        for timepoint in self.timepoints:
+            for region in self.regions:
+                self.check_stop()
+                width, height = self.calculate_output_dimensions(timepoint, region)
+                full_shape = (self.num_c, self.num_z, height, width)
+                n_levels = self.num_pyramid_levels
+                if self.apply_flatfield:
+                    self._sync_fields()
+                groups = self.band_groups(height)
+                self.emit_status(f"Stitching... (Timepoint:{timepoint} Region:{region}) bands {len(groups)} of worker "
+                                 f"{self.rank}/{self.world}")
+                for gi, (plane, y0, y1) in enumerate(groups):
+                    self.check_stop()
+                    job, c, z = self._band_job(timepoint, region, plane, y0, y1)
+                    busy = lane_writes.pop(pipe.next, None)
+                    if busy is not None:
+                        last_path = busy.result()          # the lane's pinned buffers are free again
+                    ticket = pipe.submit(job, (1, 1, y1 - y0, width), n_levels, self.apply_flatfield, field_c0=c)
+                    self.emit_progress(gi + 1, len(groups))
+                    lane_writes[ticket["lane"]] = writer.submit(self._save_band, timepoint, region, pipe, ticket, c, z, y0,
+                                                                full_shape, n_levels)
+        for fut in lane_writes.values():
+            last_path = fut.result()
+        return last_path
+
     def save_region_ome_zarr(self, timepoint, region, stitched_region, num_levels=None):
         from .ome_zarr_writer import write_ome_zarr
         path = self.per_timepoint_region_output_template.format(timepoint=timepoint, region=region)
@@ -663,7 +768,9 @@ class StitcherProcess(Process):
                 self.calculate_shifts(self.timepoints[0], self.regions[0])
             from concurrent.futures import ThreadPoolExecutor
             from .shard import wells_for_rank
-            my_regions = [self.regions[i] for i in wells_for_rank(len(self.regions), self.world, self.rank)]
+            band_mode = self.world > 1 and (self.split_regions or len(self.regions) < self.world)
+            my_regions = list(self.regions) if band_mode else \
+                [self.regions[i] for i in wells_for_rank(len(self.regions), self.world, self.rank)]
             work = [(t, r) for t in self.timepoints for r in my_regions]
             for timepoint in self.timepoints:
                 os.makedirs(os.path.join(self.output_folder, f"{timepoint}_stitched"), exist_ok=True)
@@ -674,6 +781,14 @@ class StitcherProcess(Process):
                     RegionPipeline.eligible(self.dtype, _ffi.BLEND_MODES[self.blend_mode], self.output_format, self.chunks))
             pipe = RegionPipeline(self.ctx, (self.input_height, self.input_width), self.chunks[-2:]) if fast and work else None
             self.fast_io_used = pipe is not None
+            self.band_mode = self.world > 1 and (self.split_regions or len(self.regions) < self.world)
+            if self.band_mode and pipe is None:
+                raise RuntimeError("splitting a region over several GPUs needs the OME-Zarr fast path (uint16, paste mode, "
+                                   "lattice placement, power-of-two chunk width)")
+            if self.band_mode:
+                with ThreadPoolExecutor(max_workers=1) as writer:
+                    last_path = self._run_bands(pipe, writer)
+                work = []
             with ThreadPoolExecutor(max_workers=1) as prefetch, ThreadPoolExecutor(max_workers=1) as writer:
                 nxt = prefetch.submit(self._decode_region, *work[0]) if work else None
                 pending_write = None

@@ -47,6 +47,9 @@ def parse_args(argv=None) -> argparse.Namespace:
     p.add_argument("--device", type=int, default=0, help="CUDA device index")
     p.add_argument("--devices", default="", help="comma-separated CUDA devices: one worker process per device, regions "
                                                  "(wells) split round-robin, no inter-process exchange needed")
+    p.add_argument("--split-regions", action="store_true",
+                   help="with --devices: every worker fuses its (plane, chunk-row) bands of EVERY region into one shared "
+                        "OME-Zarr (automatic when there are fewer regions than devices)")
     return p.parse_args(argv)
 
 
@@ -61,7 +64,7 @@ def create_params(args: argparse.Namespace) -> StitchingParameters:
         "merge_hcs_regions": args.merge_hcs_regions, "dynamic_registration": args.dynamic_registration,
         "blend_mode": args.blend_mode, "placement": args.placement, "upsample_factor": args.upsample_factor,
         "registration_precision": args.registration_precision, "device": args.device,
-        "visualize_registration": args.visualize_registration})
+        "visualize_registration": args.visualize_registration, "split_regions": args.split_regions})
 
 
 def monitor_process(proc, progress_queue, status_queue, complete_queue, stop_event, poll_s: float = 0.1) -> int:

@@ -131,6 +131,12 @@ typedef struct sb_fuse_job {
     int64_t out_row_pitch;    /* elements between rows (ROWMAJOR).  Host: any >= width.  Device:
                                  multiple of 64.  0 = default (width on host, round_up(width,64) on device) */
     int32_t chunk_h, chunk_w; /* CHUNKED: chunk shape, multiples of 64 (reference: 2048 or 512)    */
+    int32_t field_c0;         /* flat / dark field of tile channel c = the context's field of channel
+                                 field_c0 + c.  0 for a whole region; a job that fuses a WINDOW of a
+                                 region's planes (one (channel, z) band of a large mosaic on one of
+                                 several GPUs) numbers its planes from 0 and names the
+                                 window's first channel here                                        */
+    int32_t reserved0;        /* 0                                                                  */
 } sb_fuse_job;
 
 /* lane < 0: run and wait.  lane in [0, sb_num_lanes): enqueue H2D -> kernels -> D2H on that

@@ -219,6 +219,46 @@ def test_ome_zarr_takes_precomputed_levels_and_pyramid_shapes(tmp_path):
     assert np.array_equal(ozw.read_ome_zarr_level(path, 2), marked[..., ::2, ::2])
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+def test_ome_zarr_bands_written_by_several_workers_equal_the_whole_store(tmp_path, world):
+    """``write_ome_zarr_band``: the (plane, chunk-row) bands of ``shard.fusion_units_for_rank``, each written by its
+    owner -- level 0 as whole chunks, coarser levels through memory maps of chunk files shared between workers (written
+    here in REVERSE rank order) -- give the store ``write_ome_zarr`` writes from the whole canvas, level by level."""
+    import json
+    from image_stitcher_b200 import shard
+    rng = np.random.default_rng(11)
+    C, Z, H, W, ch, n_levels = 2, 2, 333, 205, 64, 4
+    dense = rng.integers(1, 65535, (1, C, Z, H, W), dtype=np.uint16)
+    whole, banded = str(tmp_path / "whole.ome.zarr"), str(tmp_path / "banded.ome.zarr")
+    meta = dict(pixel_size_um=0.5, dz_um=1.5, channel_names=["a", "b"], channel_colors=[0xFF0000, 0x00FF00], name="R_t0")
+    ozw.write_ome_zarr(whole, dense, num_levels=n_levels, chunks=(1, 1, 1, ch, ch), **meta)
+    ncx = -(-W // ch)
+    for rank in reversed(range(world)):
+        for plane, y0, y1 in shard.fusion_units_for_rank(C * Z, H, ch, world, rank):
+            c, z = divmod(plane, Z)
+            band = dense[0, c, z, y0:y1]
+            ncy = -(-band.shape[0] // ch)
+            buf = np.zeros((1, ncy, ncx, ch, ch), np.uint16)
+            for iy in range(ncy):
+                for ix in range(ncx):
+                    blk = band[iy * ch:(iy + 1) * ch, ix * ch:(ix + 1) * ch]
+                    buf[0, iy, ix, :blk.shape[0], :blk.shape[1]] = blk
+            levels, lv = [], band
+            for _ in range(1, n_levels):
+                lv = lv[::2, ::2]
+                levels.append(lv[None, None, None])
+            ozw.write_ome_zarr_band(banded, buf, levels, plane=(c, z), row0=y0, full_shape=(C, Z, H, W), chunk_hw=(ch, ch),
+                                    n_levels=n_levels, **meta)
+    for level in range(n_levels):
+        a, b = ozw.read_ome_zarr_level(whole, level), ozw.read_ome_zarr_level(banded, level)
+        assert a.shape == b.shape and np.array_equal(a, b), level
+        assert json.load(open(os.path.join(whole, str(level), ".zarray"))) == json.load(open(os.path.join(banded, str(level), ".zarray")))
+    assert json.load(open(os.path.join(whole, ".zattrs"))) == json.load(open(os.path.join(banded, ".zattrs")))
+    with pytest.raises(ValueError):
+        ozw.write_ome_zarr_band(banded, buf, [], plane=(0, 0), row0=ch + 1, full_shape=(C, Z, H, W), chunk_hw=(ch, ch),
+                                n_levels=1, **meta)
+
+
 def test_integration_md_stub_matches_the_binding():
     """The ctypes stub printed in INTEGRATION.md must stay in step with the header: its structures have the layout of
     the real binding's, and every prototype it sets names an exported symbol."""

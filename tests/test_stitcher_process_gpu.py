@@ -443,3 +443,83 @@ def test_run_fast_path_equals_the_plain_path_level_by_level(tmp_path, monkeypatc
                 assert np.array_equal(a, exp)
         za, zb = json.load(open(os.path.join(pf, ".zattrs"))), json.load(open(os.path.join(pp, ".zattrs")))
         assert za == zb and za["multiscales"][0]["name"] == f"{name}_t0" == za["omero"]["name"]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_one_region_split_over_several_workers_equals_the_single_worker_zarr(tmp_path, world):
+    """SURVEY 8e inside the orchestrator: with fewer regions than workers every worker fuses ITS (plane, chunk-row)
+    bands of the region (only the tiles that reach them are decoded) and drops the chunks into one shared OME-Zarr --
+    level 0 chunk files have one owner, rows of the coarser levels go through memory maps of shared chunk files.  The
+    result equals the single-worker store level by level, byte for byte, and level 0 equals the oracle.  (Workers run
+    one after the other here, all on device 0: there is nothing to exchange, so order and concurrency cannot matter.)"""
+    import json
+    import shutil
+    from oracle import stitch_ref as sr
+    root = str(tmp_path / "acq")
+    st, tiles, _ = synth.make_region(rows=3, cols=3, tile_h=640, tile_w=768, seed=77, jitter=2, region="B2",
+                                     channels=("Fluorescence 405 nm Ex", "Fluorescence 488 nm Ex"), apply_flatfield=True,
+                                     use_registration=True, registration_channel="Fluorescence 488 nm Ex")
+    synth.write_squid_layout(root, {"B2": tiles}, timepoint=0)
+
+    def worker(rank, n, stamp):
+        s = _make(root, st, rank=rank, world=n)
+        s.params._stamp = stamp
+        s.output_folder = s.params.stitched_folder
+        s.per_timepoint_region_output_template = os.path.join(s.output_folder, "{timepoint}_stitched",
+                                                              "{region}_stitched" + s.output_format)
+        s.set_flatfields(st.flatfields)
+        s.chunks = (1, 1, 1, 512, 512)
+        s.run()
+        return s
+
+    single = worker(0, 1, "single")
+    assert single.fast_io_used and not single.band_mode
+    ranks = [worker(r, world, f"split{world}") for r in range(world)]
+    assert all(s.band_mode for s in ranks)
+    n_levels = single.num_pyramid_levels
+    assert n_levels >= 2
+    ps = os.path.join(single.output_folder, "0_stitched", "B2_stitched.ome.zarr")
+    pb = os.path.join(ranks[0].output_folder, "0_stitched", "B2_stitched.ome.zarr")
+    exp = sr.stitch_region(st, tiles) if not st.use_registration else None
+    for level in range(n_levels):
+        a, b = ozw.read_ome_zarr_level(ps, level), ozw.read_ome_zarr_level(pb, level)
+        assert a.shape == b.shape and np.array_equal(a, b), level
+    if exp is not None:
+        assert np.array_equal(ozw.read_ome_zarr_level(pb, 0), exp)
+    assert json.load(open(os.path.join(ps, ".zattrs"))) == json.load(open(os.path.join(pb, ".zattrs")))
+    for level in range(n_levels):
+        assert json.load(open(os.path.join(ps, str(level), ".zarray"))) == json.load(open(os.path.join(pb, str(level), ".zarray")))
+    # the bands of the workers are disjoint and cover the canvas
+    H = ozw.read_ome_zarr_level(ps, 0).shape[-2]
+    cover = np.zeros((single.num_c * single.num_z, -(-H // 512)), dtype=int)
+    for s in ranks:
+        for p, y0, y1 in s.band_groups(H):
+            cover[p, y0 // 512:-(-y1 // 512)] += 1
+    assert (cover == 1).all()
+    shutil.rmtree(single.output_folder), shutil.rmtree(ranks[0].output_folder)
+
+
+def test_process_cli_splits_one_region_over_two_concurrent_workers(tmp_path):
+    """``--devices 0,0``: two worker PROCESSES at once (same GPU here; any two GPUs in production) share the one region
+    of the acquisition by (plane, chunk-row) bands and write one OME-Zarr between them: level 0 equals the reference
+    golden, the coarser levels (if the canvas is large enough to have any) equal ``[::2, ::2]`` of it."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    g, st, tiles, kw = load_golden("reg_2x2_mono")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    r = subprocess.run([sys.executable, "-m", "image_stitcher_b200.stitcher_process_cli", "-i", root, "-r", "--devices", "0,0"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "of worker 0/2" in r.stdout and "of worker 1/2" in r.stdout
+    path = r.stdout.split("Output saved to:")[1].split()[0]
+    level = ozw.read_ome_zarr_level(path, 0)
+    assert np.array_equal(level, g["canvas"])
+    l = 1
+    while os.path.isdir(os.path.join(path, str(l))):
+        level = level[..., ::2, ::2]
+        assert np.array_equal(ozw.read_ome_zarr_level(path, l), level), l
+        l += 1
+    import json
+    assert l == len(json.load(open(os.path.join(path, ".zattrs")))["multiscales"][0]["datasets"])
