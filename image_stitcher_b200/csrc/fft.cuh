@@ -116,6 +116,74 @@ __device__ __forceinline__ void pass_radix2(const T2* __restrict__ a, T2* __rest
     }
 }
 
+// Radix 3 and radix 5 as straight butterflies (r2 call 32): 1500 = 5 * 5 * 5 * 4 * 3, the long axis of the strips of
+// 3000 x 3000 tiles, went through the generic odd-radix pass -- a 64-bit modulo per twiddle and a fold pass per
+// factor -- and cols_xpower_kernel took half of the registration time of BASELINE configs[4].  Same item mapping as
+// pass_radix4: one thread per butterfly and group of LB lines; r * k * tstep < N for r < R, no reduction needed.
+template <typename T2, int LB>
+__device__ __forceinline__ void pass_radix3(const T2* __restrict__ a, T2* __restrict__ b, const T2* __restrict__ tw, int N, int Ns,
+                                            int M, int tstep, unsigned mM, unsigned mNs, int groups, bool inverse) {
+    using T = decltype(T2().x);
+    const T kS = (T)0.86602540378443864676372317075294L;          // sin(2 pi / 3)
+    const T sg = inverse ? (T)-1 : (T)1;
+    const int items = M * groups;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int g = fastdiv(it, mM), j = it - g * M;
+        const int jq = fastdiv(j, mNs), k = j - jq * Ns;
+        T2 w1 = tw[k * tstep], w2 = tw[2 * k * tstep];
+        if (inverse) { w1.y = -w1.y; w2.y = -w2.y; }
+        const int dst = jq * Ns * 3 + k;
+#pragma unroll
+        for (int l = 0; l < LB; ++l) {
+            const T2* in = a + (size_t)(g * LB + l) * N + j;
+            const T2 x0 = in[0], x1 = cmul(in[M], w1), x2 = cmul(in[2 * M], w2);
+            const T2 s = mk2<T2>(x1.x + x2.x, x1.y + x2.y), d = mk2<T2>(x1.x - x2.x, x1.y - x2.y);
+            const T2 m = mk2<T2>(x0.x - (T)0.5 * s.x, x0.y - (T)0.5 * s.y);
+            const T2 e = mk2<T2>(sg * kS * d.y, sg * kS * d.x);     // forward: X1 = m - i kS d = (m.x + kS d.y, m.y - kS d.x)
+            T2* out = b + (size_t)(g * LB + l) * N + dst;
+            out[0] = mk2<T2>(x0.x + s.x, x0.y + s.y);
+            out[Ns] = mk2<T2>(m.x + e.x, m.y - e.y);
+            out[2 * Ns] = mk2<T2>(m.x - e.x, m.y + e.y);
+        }
+    }
+}
+
+template <typename T2, int LB>
+__device__ __forceinline__ void pass_radix5(const T2* __restrict__ a, T2* __restrict__ b, const T2* __restrict__ tw, int N, int Ns,
+                                            int M, int tstep, unsigned mM, unsigned mNs, int groups, bool inverse) {
+    using T = decltype(T2().x);
+    const T c1 = (T)0.30901699437494742410229341718282L, c2 = (T)-0.80901699437494742410229341718282L;   // cos(2 pi / 5), cos(4 pi / 5)
+    const T s1 = (T)0.95105651629515357211643933337938L, s2 = (T)0.58778525229247312916870595463907L;    // sin(2 pi / 5), sin(4 pi / 5)
+    const T sg = inverse ? (T)-1 : (T)1;
+    const int items = M * groups;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int g = fastdiv(it, mM), j = it - g * M;
+        const int jq = fastdiv(j, mNs), k = j - jq * Ns;
+        const int kt = k * tstep;
+        T2 w1 = tw[kt], w2 = tw[2 * kt], w3 = tw[3 * kt], w4 = tw[4 * kt];
+        if (inverse) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; w4.y = -w4.y; }
+        const int dst = jq * Ns * 5 + k;
+#pragma unroll
+        for (int l = 0; l < LB; ++l) {
+            const T2* in = a + (size_t)(g * LB + l) * N + j;
+            const T2 x0 = in[0], x1 = cmul(in[M], w1), x2 = cmul(in[2 * M], w2), x3 = cmul(in[3 * M], w3), x4 = cmul(in[4 * M], w4);
+            const T2 p1 = mk2<T2>(x1.x + x4.x, x1.y + x4.y), d1 = mk2<T2>(x1.x - x4.x, x1.y - x4.y);
+            const T2 p2 = mk2<T2>(x2.x + x3.x, x2.y + x3.y), d2 = mk2<T2>(x2.x - x3.x, x2.y - x3.y);
+            const T2 a1 = mk2<T2>(fma(c2, p2.x, fma(c1, p1.x, x0.x)), fma(c2, p2.y, fma(c1, p1.y, x0.y)));
+            const T2 a2 = mk2<T2>(fma(c1, p2.x, fma(c2, p1.x, x0.x)), fma(c1, p2.y, fma(c2, p1.y, x0.y)));
+            // forward: X1 = a1 - i b1, X4 = a1 + i b1, X2 = a2 - i b2, X3 = a2 + i b2; inverse: the conjugate signs
+            const T2 b1 = mk2<T2>(sg * fma(s2, d2.x, s1 * d1.x), sg * fma(s2, d2.y, s1 * d1.y));
+            const T2 b2 = mk2<T2>(sg * fma(-s1, d2.x, s2 * d1.x), sg * fma(-s1, d2.y, s2 * d1.y));
+            T2* out = b + (size_t)(g * LB + l) * N + dst;
+            out[0] = mk2<T2>(x0.x + p1.x + p2.x, x0.y + p1.y + p2.y);
+            out[Ns] = mk2<T2>(a1.x + b1.y, a1.y - b1.x);
+            out[4 * Ns] = mk2<T2>(a1.x - b1.y, a1.y + b1.x);
+            out[2 * Ns] = mk2<T2>(a2.x + b2.y, a2.y - b2.x);
+            out[3 * Ns] = mk2<T2>(a2.x - b2.y, a2.y + b2.x);
+        }
+    }
+}
+
 template <typename T2, int LB, int QT>
 __device__ __forceinline__ void pass_generic(const T2* __restrict__ a, T2* __restrict__ b, const T2* __restrict__ tw, int N, int Ns,
                                              int R, int groups, bool inverse) {
@@ -488,6 +556,8 @@ __device__ T2* fft_lines(T2* buf0, T2* buf1, const T2* __restrict__ tw, const Ff
         bool in_place = false;
         if (R == 4) pass_radix4<T2, LB>(a, b, tw, N, Ns, plan.M[f], plan.tstep[f], plan.mM[f], plan.mNs[f], groups, inverse);
         else if (R == 2) pass_radix2<T2, LB>(a, b, tw, N, Ns, plan.M[f], plan.tstep[f], plan.mM[f], plan.mNs[f], groups, inverse);
+        else if (R == 5) pass_radix5<T2, LB>(a, b, tw, N, Ns, plan.M[f], plan.tstep[f], plan.mM[f], plan.mNs[f], groups, inverse);
+        else if (R == 3) pass_radix3<T2, LB>(a, b, tw, N, Ns, plan.M[f], plan.tstep[f], plan.mM[f], plan.mNs[f], groups, inverse);
         else if (ctab != nullptr && R == plan.gemm_radix && (nlines & 3) == 0 &&
                  OddGemm<T2>::run(a, b, tw, ctab, N, Ns, R, nlines, inverse)) in_place = true;
         else if (R & 1) pass_odd_sym<T2, LB, (sizeof(T2) == 8 ? (LB >= 4 ? 4 : 8) : (LB >= 4 ? 2 : 4))>(a, b, tw, N, Ns, R, groups, inverse);
