@@ -200,6 +200,14 @@ __device__ __forceinline__ float4 ldg_f4_hint(const float4* p, uint64_t policy) 
                  : "l"(p), "l"(policy));
     return v;
 }
+// read-only 256-bit load (sm_100: LDG.E.256): 8 floats of one lane from a 32-byte aligned address.  A warp reading 32 x 32
+// contiguous bytes this way costs the L1 data pipe 8 wavefronts (1 KB / 128 B); the same bytes as two 128-bit loads at a
+// lane stride of 32 bytes cost 8 wavefronts EACH (every load touches all 8 lines).
+__device__ __forceinline__ void ldg_f8(const float* p, float4& lo, float4& hi) {
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+        : "l"(p));
+}
 // streaming 128-bit store: written once, never re-read by this kernel
 __device__ __forceinline__ void st_stream_v4(void* p, uint4 v) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
