@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--per-well-fusion", action="store_true",
                     help="one sb_fuse_region launch per well (round-1 behaviour) instead of one sb_fuse_regions launch per plate")
     ap.add_argument("--no-coordinate-only", action="store_true", help="skip the informational fusion pass without the flat-field")
+    ap.add_argument("--e2e-partial-upload", action="store_true",
+                    help="e2e leg: upload only the pixels that can reach the canvas (measured slower: strided copies)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-wells", type=int, default=0, help="wells in the CPU sample (0 = one per host core)")
@@ -645,7 +647,7 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_e2e:
         from image_stitcher_b200.pipeline import WellPipeline
         hw = max(1, min(args.host_wells, spec.wells))
-        pipe = WellPipeline(ctx, spec, apply_flatfield=use_flat, blend=args.blend)
+        pipe = WellPipeline(ctx, spec, apply_flatfield=use_flat, blend=args.blend, partial_upload=args.e2e_partial_upload)
         host_tiles = [ctx.pinned_empty((spec.rows, spec.cols, spec.channels, spec.num_z, spec.tile_h, spec.tile_w),
                                        np.uint16) for _ in range(hw)]
         for i in range(hw):
@@ -685,18 +687,23 @@ def run_b200(args, rank, world, local_rank):
         exp = canvases[src_w].cpu().numpy().view(np.uint16)[:, :, :Wc]
         # the node's raw copy ceiling with every rank copying both ways at once: what the end-to-end number is bound by
         ceil_gbs = pcie_ceiling(ctx, torch, local_rank, dist)
-        h2d_step = int(spec.wells * spec.tiles_per_well * spec.tile_h * spec.tile_w * 2)
+        h2d_full = int(spec.wells * spec.tiles_per_well * spec.tile_h * spec.tile_w * 2)
+        h2d_step = int(spec.wells * pipe.upload_bytes)            # bytes actually copied: paste mode skips pixels a later tile overwrites
         d2h_step = int(px_per_step * 2)
         floor_s = max(h2d_step, d2h_step) / (ceil_gbs * 1e9)      # both directions run concurrently
         out["e2e"] = {"value": px_all * e2e_steps / 1e6 / e2e_s, "unit": "Mpx/s",
                       "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "steps": e2e_steps,
+                      "h2d_bytes_all_tile_pixels": h2d_full,
+                      "h2d_note": ("--e2e-partial-upload: only the part of each tile that can reach the canvas is uploaded (the pixels a "
+                                   "later tile overwrites are never read; registration-channel tiles go up whole)"
+                                   if h2d_step != h2d_full else "every tile pixel is uploaded (one contiguous copy per well)"),
                       "ms_per_step": e2e_s / e2e_steps * 1e3,
                       "pcie_ceiling": {"gb_per_s_per_direction_per_gpu": ceil_gbs, "ranks_copying_at_once": world,
                                        "ms_per_step_at_ceiling": floor_s * 1e3,
                                        "e2e_frac_of_ceiling": floor_s / (e2e_s / e2e_steps),
                                        "how": "512 MiB pinned H2D and D2H on two streams at once, every rank at the same time, max over ranks"},
                       "tile_pairs_per_s": pairs_all * e2e_steps / e2e_s,
-                      "api": "WellPipeline.submit(pinned host tiles) -> host canvas + shifts (sb_memcpy_async + "
+                      "api": "WellPipeline.submit(pinned host tiles) -> host canvas + shifts (sb_memcpy_async / sb_memcpy2d_async + "
                              "sb_register_pairs_async + sb_fuse_region, rotating over 3 lanes)",
                       "registration_truth_wells_ok": f"{e2e_reg_ok}/{spec.wells}",
                       "host_wells_distinct": hw, "matches_device_result": bool(np.array_equal(got, exp))}

@@ -27,7 +27,7 @@ BLEND_MODES = {"paste": SB_BLEND_PASTE, "linear": SB_BLEND_LINEAR, "feather": SB
 EXPORTS = [
     "sb_version", "sb_create", "sb_destroy", "sb_last_error", "sb_kernel_launches", "sb_num_lanes",
     "sb_device_sm_count", "sb_host_alloc", "sb_host_free", "sb_device_alloc", "sb_device_free",
-    "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_memcpy_async", "sb_set_flatfield", "sb_set_darkfield", "sb_clear_fields",
+    "sb_memcpy_h2d", "sb_memcpy_d2h", "sb_memcpy_async", "sb_memcpy2d_async", "sb_set_flatfield", "sb_set_darkfield", "sb_clear_fields",
     "sb_flatfield_apply", "sb_fuse_region", "sb_fuse_regions", "sb_sync", "sb_lane_mark", "sb_lane_wait_mark", "sb_set_lane_stream", "sb_canvas_pitch",
     "sb_chunked_plane_elems", "sb_register_pairs", "sb_register_pairs_async", "sb_normalize",
     "sb_pyramid_elems", "sb_pyramid", "sb_estimate_flatfield", "sb_selftest", "sb_debug_read", "sb_debug_tc_profile",
@@ -101,6 +101,7 @@ def load_library(path: Optional[str] = None):
     lib.sb_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
     lib.sb_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
     lib.sb_memcpy_async.argtypes = [vp, i32, vp, vp, C.c_size_t, i32]
+    lib.sb_memcpy2d_async.argtypes = [vp, i32, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, i32]
     for fn in (lib.sb_set_flatfield, lib.sb_set_darkfield):
         fn.argtypes = [vp, i32, vp, i32, i32, i32, i32]
     lib.sb_clear_fields.argtypes = [vp]
@@ -338,6 +339,11 @@ class Context:
         """kind: 0 = H2D, 1 = D2H, 2 = D2D, on the lane's stream."""
         self._check(self.lib.sb_memcpy_async(self.handle, lane, _ptr(dst), _ptr(src), int(nbytes), kind),
                     "sb_memcpy_async")
+
+    def memcpy2d_async(self, lane: int, dst, dst_pitch: int, src, src_pitch: int, width_bytes: int, height: int, kind: int):
+        """``height`` rows of ``width_bytes`` bytes between pitched buffers (addresses or arrays), on the lane's stream."""
+        self._check(self.lib.sb_memcpy2d_async(self.handle, lane, _ptr(dst), int(dst_pitch), _ptr(src), int(src_pitch),
+                                               int(width_bytes), int(height), kind), "sb_memcpy2d_async")
 
     @staticmethod
     def _pair_dicts(res):

@@ -212,6 +212,18 @@ int sb_memcpy_async(sb_ctx* ctx, int lane, void* dst, const void* src, size_t by
     return SB_OK;
 }
 
+int sb_memcpy2d_async(sb_ctx* ctx, int lane, void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                      size_t width_bytes, size_t height, int kind) {
+    SB_ENTER(ctx);
+    Lane* l = sb_lane(ctx, lane);
+    if (!l) return sb_fail(ctx, SB_ERR_INVALID, "lane %d out of range", lane);
+    SB_CHECK(ctx, dst != nullptr && src != nullptr && width_bytes <= dst_pitch && width_bytes <= src_pitch, "bad 2-D copy");
+    if (width_bytes == 0 || height == 0) return SB_OK;
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    SB_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height, k, l->stream));
+    return SB_OK;
+}
+
 static int set_field(sb_ctx* ctx, FieldPool& pool, const char* what, int channel, const void* field, int dtype, int mem,
                      int h, int w) {
     SB_CHECK(ctx, ctx != nullptr, "ctx is NULL");

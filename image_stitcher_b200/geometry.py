@@ -168,3 +168,58 @@ def solve_positions(n_tiles: int, tile_w: int, tile_h: int, pairs: Sequence[Tupl
     xi = np.rint(x - x.min()).astype(np.int64)
     yi = np.rint(y - y.min()).astype(np.int64)
     return [(int(a), int(b)) for a, b in zip(xi, yi)]
+
+
+def _rect_subtract(a, b):
+    """``a`` minus ``b`` (``(x0, y0, x1, y1)``, exclusive ends) as up to four disjoint rectangles."""
+    ix0, iy0, ix1, iy1 = max(a[0], b[0]), max(a[1], b[1]), min(a[2], b[2]), min(a[3], b[3])
+    if ix0 >= ix1 or iy0 >= iy1:
+        return [a]
+    out = []
+    if a[1] < iy0:
+        out.append((a[0], a[1], a[2], iy0))
+    if iy1 < a[3]:
+        out.append((a[0], iy1, a[2], a[3]))
+    if a[0] < ix0:
+        out.append((a[0], iy0, ix0, iy1))
+    if ix1 < a[2]:
+        out.append((ix1, iy0, a[2], iy1))
+    return out
+
+
+def visible_boxes(tiles: Sequence[tuple], tile_h: int, tile_w: int, canvas_h: int, canvas_w: int, align: int = 8):
+    """Per tile of a PASTE job (``(px, x, y, c, z, crop_t, crop_b, crop_l, crop_r)`` in paste order): the bounding box
+    ``(x0, y0, x1, y1)`` in TILE coordinates of the pixels that reach the canvas -- its kept rectangle minus what every
+    later tile of the same plane overwrites (stitcher_process.py:817) -- or ``None`` when nothing of it is visible.
+    ``x0`` / ``x1`` are rounded outwards to multiples of ``align`` pixels (the paste kernel loads whole 16-byte vectors).
+    The fusion kernels never read a pixel outside these boxes, so a host pipeline need not upload the rest."""
+    rects = []
+    for (_, x, y, c, z, ct, cb, cl, cr) in tiles:
+        rects.append((max(x + cl, 0), max(y + ct, 0), min(x + tile_w - cr, canvas_w), min(y + tile_h - cb, canvas_h)))
+    out = []
+    for i, t in enumerate(tiles):
+        r = rects[i]
+        if r[0] >= r[2] or r[1] >= r[3]:
+            out.append(None)
+            continue
+        pieces = [r]
+        for j in range(i + 1, len(tiles)):
+            if tiles[j][3] != t[3] or tiles[j][4] != t[4]:
+                continue
+            nxt = []
+            for pc in pieces:
+                nxt += _rect_subtract(pc, rects[j])
+            pieces = nxt
+            if not pieces:
+                break
+        if not pieces:
+            out.append(None)
+            continue
+        x0 = min(pc[0] for pc in pieces) - t[1]
+        y0 = min(pc[1] for pc in pieces) - t[2]
+        x1 = max(pc[2] for pc in pieces) - t[1]
+        y1 = max(pc[3] for pc in pieces) - t[2]
+        x0 = (x0 // align) * align
+        x1 = min(-(-x1 // align) * align, tile_w)
+        out.append((max(x0, 0), max(y0, 0), x1, min(y1, tile_h)))
+    return out

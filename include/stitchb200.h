@@ -83,6 +83,11 @@ int sb_memcpy_d2h(sb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes
 /* Asynchronous copy on a lane's stream (ordered with that lane's kernels); kind: 0 = host->device,
  * 1 = device->host, 2 = device->device.  Host memory should come from sb_host_alloc. */
 int sb_memcpy_async(sb_ctx* ctx, int lane, void* dst, const void* src, size_t bytes, int kind);
+/* The same for a rectangle of `height` rows of `width_bytes` bytes inside pitched buffers (cudaMemcpy2DAsync): the
+ * upload of the part of a tile that can reach the canvas -- in paste mode the pixels a later tile overwrites (:817) are
+ * never read by sb_fuse_region, so a host pipeline need not send them (WellPipeline). */
+int sb_memcpy2d_async(sb_ctx* ctx, int lane, void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                      size_t width_bytes, size_t height, int kind);
 
 /* ------------------------------------------------------------------ flat / dark fields
  * Replaces the *storage* of self.flatfields (:158, :524): one H x W field per

@@ -259,6 +259,39 @@ def test_ome_zarr_bands_written_by_several_workers_equal_the_whole_store(tmp_pat
                                 n_levels=1, **meta)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_visible_boxes_cover_exactly_what_paste_order_leaves_visible(seed):
+    """``geometry.visible_boxes`` against a brute-force owner map: paste the tile INDEX of every kept rectangle in paste
+    order; the pixels of tile i that survive lie inside its box, the box is tight in y and tight in x up to the 8-pixel
+    rounding, and a tile with no surviving pixel gets ``None``.  Jittered 3 x 3 lattice with seam crops, two planes, one
+    tile buried completely."""
+    rng = np.random.default_rng(seed)
+    th, tw, step = 48, 64, 40
+    tiles = []
+    for r in range(3):
+        for c in range(3):
+            for ch in range(2):
+                x, y = c * step + int(rng.integers(0, 5)), r * step + int(rng.integers(0, 5))
+                tiles.append((None, x, y, ch, 0, int(rng.integers(0, 3)), int(rng.integers(0, 3)), int(rng.integers(0, 3)),
+                              int(rng.integers(0, 3))))
+    tiles.insert(0, (None, 10, 10, 0, 0, 4, 4, 4, 4))            # buried under the first tiles of plane 0
+    Hc, Wc = 2 * step + th + 2, 2 * step + tw + 1                 # clips the last row / column of tiles
+    boxes = geo.visible_boxes(tiles, th, tw, Hc, Wc)
+    owner = -np.ones((2, Hc, Wc), dtype=int)
+    for i, (_, x, y, c, z, ct, cb, cl, cr) in enumerate(tiles):
+        owner[c, max(y + ct, 0):min(y + th - cb, Hc), max(x + cl, 0):min(x + tw - cr, Wc)] = i
+    assert boxes[0] is None and (owner != 0).all()
+    for i, (t, box) in enumerate(zip(tiles, boxes)):
+        ys, xs = np.nonzero(owner[t[3]] == i)
+        if len(ys) == 0:
+            assert box is None
+            continue
+        x0, y0, x1, y1 = box
+        assert 0 <= x0 < x1 <= tw and 0 <= y0 < y1 <= th and x0 % 8 == 0 and (x1 % 8 == 0 or x1 == tw)
+        assert y0 == ys.min() - t[2] and y1 == ys.max() + 1 - t[2]
+        assert x0 <= xs.min() - t[1] < x0 + 8 and x1 - 8 < xs.max() + 1 - t[1] <= x1
+
+
 def test_integration_md_stub_matches_the_binding():
     """The ctypes stub printed in INTEGRATION.md must stay in step with the header: its structures have the layout of
     the real binding's, and every prototype it sets names an exported symbol."""

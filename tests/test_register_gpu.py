@@ -190,8 +190,10 @@ def test_async_registration_matches_sync_and_overlaps_lanes(ctx):
     assert ctx.register_pairs_async([], (H, W), ov, ov).get() == []
 
 
-def test_well_pipeline_host_buffers_match_oracle(ctx):
-    """The end-to-end call the benchmark times (host tiles in -> shifts + host canvas out over 3 lanes)."""
+@pytest.mark.parametrize("partial_upload", [False, True])
+def test_well_pipeline_host_buffers_match_oracle(ctx, partial_upload):
+    """The end-to-end call the benchmark times (host tiles in -> shifts + host canvas out over 3 lanes); also with the
+    upload restricted to the pixels that can reach the canvas (``partial_upload``)."""
     import torch
     from image_stitcher_b200 import _ffi
     from image_stitcher_b200.pipeline import WellPipeline
@@ -202,7 +204,10 @@ def test_well_pipeline_host_buffers_match_oracle(ctx):
     ctx.clear_fields()
     for c in range(spec.channels):
         ctx.set_flatfield(c, plate.flat[c], mem=_ffi.SB_MEM_DEVICE)
-    pipe = WellPipeline(ctx, spec, apply_flatfield=True)
+    pipe = WellPipeline(ctx, spec, apply_flatfield=True, partial_upload=partial_upload)
+    # partial uploads: the staging buffers are reused by later wells, so a kernel that read a pixel outside the uploaded
+    # boxes would see another well's data and fail the comparison below
+    assert (pipe.uploads is not None and pipe.upload_bytes < pipe.well_bytes) if partial_upload else pipe.uploads is None
     Wc, Hc = spec.canvas_size()
     host = [plate.pool[w].cpu().numpy().view(np.uint16).copy() for w in range(spec.wells)]
     outs = [np.zeros((1, spec.channels, spec.num_z, Hc, Wc), np.uint16) for _ in range(spec.wells)]
