@@ -57,8 +57,8 @@ def parse_args():
     ap.add_argument("--per-well-fusion", action="store_true",
                     help="one sb_fuse_region launch per well (round-1 behaviour) instead of one sb_fuse_regions launch per plate")
     ap.add_argument("--no-coordinate-only", action="store_true", help="skip the informational fusion pass without the flat-field")
-    ap.add_argument("--e2e-partial-upload", action="store_true",
-                    help="e2e leg: upload only the pixels that can reach the canvas (measured slower: strided copies)")
+    ap.add_argument("--e2e-partial-upload", choices=["off", "boxes", "rows"], default="off",
+                    help="e2e leg: upload only the pixels (boxes) / rows that can reach the canvas")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-wells", type=int, default=0, help="wells in the CPU sample (0 = one per host core)")
@@ -647,7 +647,7 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_e2e:
         from image_stitcher_b200.pipeline import WellPipeline
         hw = max(1, min(args.host_wells, spec.wells))
-        pipe = WellPipeline(ctx, spec, apply_flatfield=use_flat, blend=args.blend, partial_upload=args.e2e_partial_upload)
+        pipe = WellPipeline(ctx, spec, apply_flatfield=use_flat, blend=args.blend, partial_upload={'off': False, 'boxes': True, 'rows': 'rows'}[args.e2e_partial_upload])
         host_tiles = [ctx.pinned_empty((spec.rows, spec.cols, spec.channels, spec.num_z, spec.tile_h, spec.tile_w),
                                        np.uint16) for _ in range(hw)]
         for i in range(hw):

@@ -18,7 +18,7 @@ from .plate import FusePlan, PlateSpec, well_fuse_tiles, well_pairs
 
 class WellPipeline:
     def __init__(self, ctx: _ffi.Context, spec: PlateSpec, *, apply_flatfield: bool, blend: str = "paste",
-                 register: bool = True, lattice: Optional[geo.Lattice] = None, partial_upload: bool = False):
+                 register: bool = True, lattice: Optional[geo.Lattice] = None, partial_upload=False):
         self.ctx, self.spec = ctx, spec
         self.depth = ctx.num_lanes
         self.register = register
@@ -64,6 +64,8 @@ class WellPipeline:
                 off = int(np.dot(strides, (r, c, ch, z))) * H * W
                 if register and ch == spec.reg_channel and z == 0:
                     box = (0, 0, W, H)
+                if box is not None and partial_upload == "rows":     # whole rows only: contiguous copies
+                    box = (0, box[1], W, box[3])
                 if box is not None:
                     ups.append((off, *box))
             self.uploads = sorted(ups)
