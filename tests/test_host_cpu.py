@@ -259,6 +259,50 @@ def test_ome_zarr_bands_written_by_several_workers_equal_the_whole_store(tmp_pat
                                 n_levels=1, **meta)
 
 
+def _band_writer_process(args):
+    """One worker of the concurrent band-writer test (module level: it runs in a forked process)."""
+    path, rank, world, seed, C, Z, H, W, ch, n_levels = args
+    from image_stitcher_b200 import shard
+    dense = np.random.default_rng(seed).integers(1, 65535, (1, C, Z, H, W), dtype=np.uint16)
+    ncx = -(-W // ch)
+    for plane, y0, y1 in shard.fusion_units_for_rank(C * Z, H, ch, world, rank):
+        c, z = divmod(plane, Z)
+        band = dense[0, c, z, y0:y1]
+        ncy = -(-band.shape[0] // ch)
+        buf = np.zeros((1, ncy, ncx, ch, ch), np.uint16)
+        for iy in range(ncy):
+            for ix in range(ncx):
+                blk = band[iy * ch:(iy + 1) * ch, ix * ch:(ix + 1) * ch]
+                buf[0, iy, ix, :blk.shape[0], :blk.shape[1]] = blk
+        levels, lv = [], band
+        for _ in range(1, n_levels):
+            lv = lv[::2, ::2]
+            levels.append(lv[None, None, None])
+        ozw.write_ome_zarr_band(path, buf, levels, plane=(c, z), row0=y0, full_shape=(C, Z, H, W), chunk_hw=(ch, ch),
+                                n_levels=n_levels, pixel_size_um=0.5, channel_names=["a", "b"], channel_colors=[1, 2], name="R_t0")
+    return rank
+
+
+def test_ome_zarr_bands_written_by_concurrent_processes(tmp_path):
+    """Four worker PROCESSES write their bands into one store at the same time: level-0 chunk files have one owner, the
+    coarser levels' chunk files are shared (each worker writes its rows through its own memory map), the metadata files
+    are replaced atomically by everyone.  The result is the store of the whole canvas."""
+    import multiprocessing as mp
+    C, Z, H, W, ch, n_levels, seed, world = 2, 1, 1111, 517, 64, 5, 5, 4
+    path = str(tmp_path / "shared.ome.zarr")
+    with mp.get_context("fork").Pool(world) as pool:
+        done = pool.map(_band_writer_process, [(path, r, world, seed, C, Z, H, W, ch, n_levels) for r in range(world)])
+    assert sorted(done) == list(range(world))
+    dense = np.random.default_rng(seed).integers(1, 65535, (1, C, Z, H, W), dtype=np.uint16)
+    level = dense
+    for l in range(n_levels):
+        if l:
+            level = level[..., ::2, ::2]
+        assert np.array_equal(ozw.read_ome_zarr_level(path, l), level), l
+    assert len(json.load(open(os.path.join(path, ".zattrs")))["multiscales"][0]["datasets"]) == n_levels
+    assert not [f for f in os.listdir(path) if f.endswith(".tmp")]
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_visible_boxes_cover_exactly_what_paste_order_leaves_visible(seed):
     """``geometry.visible_boxes`` against a brute-force owner map: paste the tile INDEX of every kept rectangle in paste
