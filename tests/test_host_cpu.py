@@ -135,6 +135,45 @@ def test_parse_squid_layout_and_geometry_match_reference_golden(name, tmp_path, 
     assert (1, s.num_c, s.num_z, h, w) == tuple(int(v) for v in g["canvas_shape"])
 
 
+@pytest.mark.parametrize("name,world", [("reg_2x2_mono", 2), ("coord_2x2_plain", 3), ("reg_2x3_negdrift", 4), ("coord_2x3_rgb_u8", 2)])
+def test_band_jobs_of_all_workers_paste_to_the_reference_canvas(name, world, tmp_path):
+    """One region over several workers, host side only (no GPU): every worker's ``band_groups`` / ``_band_job`` --
+    which files it decodes, how the tiles are re-based to the band and cropped -- pasted with plain NumPy slicing give,
+    band by band, the rows of the reference's golden canvas (flat-field off here: a paste is then a copy).  The bands of
+    all workers tile every plane exactly once."""
+    g, st, tiles, kw = load_golden(name)
+    if st.apply_flatfield:
+        pytest.skip("paste == copy only without a flat-field")
+    root = str(tmp_path / "acq")
+    synth.write_squid_layout(root, {"A1": tiles})
+    canvas = g["canvas"]
+    seen = np.zeros(canvas.shape[1:4], dtype=int)                       # (C, Z, H) rows covered
+    for rank in range(world):
+        s = _stitcher(root, use_registration=st.use_registration, scan_pattern=st.scan_pattern,
+                      registration_channel=st.registration_channel, rank=rank, world=world)
+        s.chunks = (1, 1, 1, 64, 64)
+        if st.use_registration:
+            s.h_shift, s.v_shift = tuple(int(v) for v in g["h_shift"]), tuple(int(v) for v in g["v_shift"])
+            if st.scan_pattern == "S-Pattern":
+                s.h_shift_rev = tuple(int(v) for v in g["h_shift_rev"])
+                s.h_shift_rev_odd = int(g["h_shift_rev_odd"])
+        w, h = s.calculate_output_dimensions(0, "A1")
+        assert (h, w) == canvas.shape[-2:]
+        H, W = s.input_height, s.input_width
+        for plane, y0, y1 in s.band_groups(h):
+            job, c, z = s._band_job(0, "A1", plane, y0, y1)
+            band = np.zeros((y1 - y0, w), canvas.dtype)
+            for arr, x, y, cc, zz, ct, cb, cl, cr in job:
+                assert (cc, zz) == (0, 0) and y + ct >= 0
+                ys0, ys1 = y + ct, min(y + H - cb, y1 - y0)
+                xs0, xs1 = max(x + cl, 0), min(x + W - cr, w)
+                if ys1 > ys0 and xs1 > xs0:
+                    band[ys0:ys1, xs0:xs1] = arr[ys0 - y:ys1 - y, xs0 - x:xs1 - x]
+            assert np.array_equal(band, canvas[0, c, z, y0:y1]), (rank, plane, y0, y1)
+            seen[c, z, y0:y1] += 1
+    assert (seen == 1).all()
+
+
 def test_parse_skips_hidden_and_focus_camera_and_handles_fov_ge_10(tmp_path):
     st, tiles, _ = synth.make_region(3, 4, 32, 32, seed=3, jitter=0, region="B2")
     root = str(tmp_path / "acq")
