@@ -326,12 +326,15 @@ def test_ome_zarr_bands_written_by_concurrent_processes(tmp_path):
     """Four worker PROCESSES write their bands into one store at the same time: level-0 chunk files have one owner, the
     coarser levels' chunk files are shared (each worker writes its rows through its own memory map), the metadata files
     are replaced atomically by everyone.  The result is the store of the whole canvas."""
-    import multiprocessing as mp
+    import subprocess
+    import sys
     C, Z, H, W, ch, n_levels, seed, world = 2, 1, 1111, 517, 64, 5, 5, 4
     path = str(tmp_path / "shared.ome.zarr")
-    with mp.get_context("fork").Pool(world) as pool:
-        done = pool.map(_band_writer_process, [(path, r, world, seed, C, Z, H, W, ch, n_levels) for r in range(world)])
-    assert sorted(done) == list(range(world))
+    code = ("import sys; sys.path[:0] = [%r, %r]; from test_host_cpu import _band_writer_process; "
+            "_band_writer_process(eval(sys.argv[1]))" % (ROOT, os.path.dirname(os.path.abspath(__file__))))
+    procs = [subprocess.Popen([sys.executable, "-c", code, repr((path, r, world, seed, C, Z, H, W, ch, n_levels))])
+             for r in range(world)]                                   # all four at once (fresh interpreters: no fork of a threaded process)
+    assert [p.wait(timeout=300) for p in procs] == [0] * world
     dense = np.random.default_rng(seed).integers(1, 65535, (1, C, Z, H, W), dtype=np.uint16)
     level = dense
     for l in range(n_levels):
